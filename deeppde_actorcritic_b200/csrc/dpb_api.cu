@@ -1,0 +1,486 @@
+// dpb_api.cu -- C ABI of libdeeppde_b200.so (include/deeppde_b200.h): handle, workspace layout and
+// the launch sequences of the exact path.  No torch types, no allocation per call, no stream sync
+// (except the *_host convenience entry points, which must deliver host-visible losses).
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+#include <string>
+#include "../../include/deeppde_b200.h"
+#include "dpb_host.h"
+#include "dpb_kernels.cuh"
+
+using namespace dpb;
+
+struct dpb_handle {
+    dpb_config cfg;
+    NetDev nA, nV, nG;
+    int num_sms;
+    int max_smem;
+    int sr, hrows, nhb;
+    long long launches;
+    std::string err;
+};
+
+static thread_local std::string g_err;
+
+static int fail(dpb_handle* h, int code, const std::string& msg) {
+    if (h) h->err = msg;
+    g_err = msg;
+    return code;
+}
+
+#define DPB_CUDA(h, call)                                                                      \
+    do {                                                                                       \
+        cudaError_t e_ = (call);                                                               \
+        if (e_ != cudaSuccess) return fail(h, DPB_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
+    } while (0)
+
+static inline size_t esize(const dpb_handle* h) { return h->cfg.dtype == DPB_F64 ? 8 : 4; }
+static inline size_t a256(size_t x) { return (x + 255) & ~(size_t)255; }
+static inline int tileP(const dpb_handle* h) { return h->cfg.dtype == DPB_F64 ? 8 * RT<double>::TP : 8 * RT<float>::TP; }
+static const double BN_C = 1.0 / sqrt(1.0 + 1e-6);       // solver.py:242 (epsilon), moving var = 1
+
+struct Layout {
+    int grid;
+    size_t pkA, pkV, pkG, loss_part, loss_out, scratch, slabs, raw, total;
+    long long scratch_per_cta;
+};
+
+static Layout make_layout(const dpb_handle* h, long long B_local, int N) {
+    Layout L;
+    const size_t es = esize(h);
+    const int P = tileP(h);
+    long long ntiles = (B_local + P - 1) / P;
+    L.grid = (int)(ntiles < h->num_sms ? (ntiles < 1 ? 1 : ntiles) : h->num_sms);
+    size_t o = 0;
+    L.pkA = o; o += a256(h->nA.ptotal * es);
+    L.pkV = o; o += a256(h->nV.ptotal * es);
+    L.pkG = o; o += a256(h->nG.ptotal * es);
+    L.loss_part = o; o += a256((size_t)L.grid * 2 * es);
+    L.loss_out = o; o += 256;
+    L.scratch_per_cta = (long long)N * (2 * h->sr + A_NSCAL) * P;
+    L.scratch = o; o += a256((size_t)L.grid * L.scratch_per_cta * es);
+    const long long gc = h->nV.gtotal + h->nG.gtotal, ga = h->nA.gtotal;
+    const long long gmax = gc > ga ? gc : ga;
+    L.slabs = o; o += a256((size_t)L.grid * gmax * es);
+    L.raw = o; o += a256((size_t)gmax * es);
+    L.total = o;
+    return L;
+}
+
+extern "C" {
+
+const char* dpb_version(void) { return "deeppde_b200 0.1 (exact CUDA-core path, sm_100a)"; }
+
+const char* dpb_last_error(const dpb_handle* h) { return h ? h->err.c_str() : g_err.c_str(); }
+
+int dpb_create(dpb_handle** out, const dpb_config* cfg) {
+    if (!out || !cfg) return fail(nullptr, DPB_ERR_ARG, "dpb_create: null argument");
+    *out = nullptr;
+    const dpb_config& c = *cfg;
+    if (c.dtype != DPB_F32 && c.dtype != DPB_F64) return fail(nullptr, DPB_ERR_ARG, "dtype must be DPB_F32 or DPB_F64");
+    if (c.eqn < DPB_EQN_LQR || c.eqn > DPB_EQN_LQR_VAR) return fail(nullptr, DPB_ERR_ARG, "unknown equation id");
+    if (c.dim < 1 || c.dim > DPB_MAX_DIM - 1 || c.control_dim < 1 || c.control_dim > DPB_MAX_DIM - 1)
+        return fail(nullptr, DPB_ERR_ARG, "dim / control_dim out of range (1..31)");
+    if (c.scheme != DPB_SCHEME_NAIVE && c.scheme != DPB_SCHEME_ADAPTIVE) return fail(nullptr, DPB_ERR_ARG, "unknown scheme");
+    if (c.td_type != DPB_TD1 && c.td_type != DPB_TD2) return fail(nullptr, DPB_ERR_ARG, "TD_type must be 1 or 2");
+    if (c.eqn == DPB_EQN_VDP && c.dim != 2 * c.control_dim) return fail(nullptr, DPB_ERR_ARG, "VDP needs dim == 2*control_dim (equation.py:186-187)");
+    if ((c.eqn == DPB_EQN_LQR || c.eqn == DPB_EQN_LQR_VAR || c.eqn == DPB_EQN_EKN) && c.dim != c.control_dim)
+        return fail(nullptr, DPB_ERR_ARG, "LQR / LQR_var / ekn need control_dim == dim (equation.py:164,261,305)");
+    if (c.n_hidden_actor < 1 || c.n_hidden_actor > DPB_MAX_HIDDEN || c.n_hidden_critic < 1 || c.n_hidden_critic > DPB_MAX_HIDDEN)
+        return fail(nullptr, DPB_ERR_ARG, "1..6 hidden layers per network");
+    int hmax = 0;
+    for (int i = 0; i < c.n_hidden_actor; ++i) { if (c.hidden_actor[i] < 1 || c.hidden_actor[i] > WS_NMAX) return fail(nullptr, DPB_ERR_ARG, "hidden width must be 1..256"); hmax = hmax > c.hidden_actor[i] ? hmax : c.hidden_actor[i]; }
+    for (int i = 0; i < c.n_hidden_critic; ++i) { if (c.hidden_critic[i] < 1 || c.hidden_critic[i] > WS_NMAX) return fail(nullptr, DPB_ERR_ARG, "hidden width must be 1..256"); hmax = hmax > c.hidden_critic[i] ? hmax : c.hidden_critic[i]; }
+    if (!(c.R > 0)) return fail(nullptr, DPB_ERR_ARG, "R must be positive");
+
+    dpb_handle* h = new dpb_handle();
+    h->cfg = c;
+    h->launches = 0;
+    const int ekn = (c.eqn == DPB_EQN_EKN);
+    netdev_init(h->nA, c.dim, c.hidden_actor, c.n_hidden_actor, ekn ? c.control_dim + 1 : c.control_dim, ekn, c.control_dim);   // solver.py:255-258
+    netdev_init(h->nV, c.dim, c.hidden_critic, c.n_hidden_critic, 1, 0, 0);                                                  // solver.py:251-252
+    netdev_init(h->nG, c.dim, c.hidden_critic, c.n_hidden_critic, c.dim, 0, 0);                                              // solver.py:253-254
+    const int mx = c.dim > c.control_dim + 1 ? c.dim : c.control_dim + 1;
+    h->sr = round8(mx);
+    h->hrows = round8(hmax);
+    const int lmax = c.n_hidden_actor > c.n_hidden_critic ? c.n_hidden_actor : c.n_hidden_critic;
+    h->nhb = lmax + 2;
+    h->num_sms = 0;
+    h->max_smem = 0;
+    int dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess) {
+        cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaDeviceGetAttribute(&h->max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    } else {
+        cudaGetLastError();
+    }
+    if (h->num_sms <= 0) h->num_sms = 148;                 // layout only; compute calls fail without a device
+    const size_t need = (c.dtype == DPB_F64 ? carve_elems<double>(h->sr, h->hrows, h->nhb) * 8 : carve_elems<float>(h->sr, h->hrows, h->nhb) * 4);
+    if (need > 227 * 1024) {
+        delete h;
+        return fail(nullptr, DPB_ERR_ARG, "networks too large for the on-chip activation tile (need " + std::to_string(need) + " B of shared memory)");
+    }
+    *out = h;
+    return DPB_OK;
+}
+
+int dpb_destroy(dpb_handle* h) {
+    delete h;
+    return DPB_OK;
+}
+
+int64_t dpb_param_count(const dpb_handle* h, int which) {
+    if (!h) return -1;
+    switch (which) {
+    case DPB_NET_ACTOR: return h->nA.ftotal;
+    case DPB_NET_CRITIC: return h->nV.ftotal;
+    case DPB_NET_CRITIC_GRAD: return h->nG.ftotal;
+    }
+    return -1;
+}
+
+int64_t dpb_workspace_bytes(const dpb_handle* h, int64_t B_local, int32_t N) {
+    if (!h || B_local < 1 || N < 1) return -1;
+    return (int64_t)make_layout(h, B_local, N).total;
+}
+
+int64_t dpb_staging_bytes(const dpb_handle* h, int64_t B_local, int32_t N, int32_t dw_mode) {
+    if (!h || B_local < 1 || N < 1) return -1;
+    const size_t es = esize(h);
+    size_t o = 2 * a256((size_t)B_local * h->cfg.dim * es);
+    if (dw_mode == DPB_DW_EXTERNAL) o += a256((size_t)B_local * h->cfg.dim * N * es);
+    return (int64_t)o;
+}
+
+int64_t dpb_launch_count(const dpb_handle* h) { return h ? h->launches : -1; }
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------------
+template <typename real>
+static int pack_net(dpb_handle* h, const NetDev& nd, const void* theta, void* pk, cudaStream_t st) {
+    const long long work = nd.ptotal;
+    int blocks = (int)((work + 255) / 256);
+    if (blocks > 296) blocks = 296;
+    pack_net_kernel<real><<<blocks, 256, 0, st>>>(nd, (const real*)theta, (real*)pk, (real)BN_C);
+    h->launches++;
+    DPB_CUDA(h, cudaGetLastError());
+    return DPB_OK;
+}
+
+template <typename real>
+static int finalize_net(dpb_handle* h, const NetDev& nd, const void* theta, const real* slabs, int nslab, real* raw, void* grad, cudaStream_t st) {
+    int blocks = (int)((nd.gtotal + 255) / 256);
+    if (blocks > 592) blocks = 592;
+    reduce_slabs_kernel<real><<<blocks, 256, 0, st>>>(slabs, nslab, nd.gtotal, raw);
+    finalize_grad_kernel<real><<<blocks, 256, 0, st>>>(nd, (const real*)theta, raw, (real*)grad, (real)BN_C);
+    h->launches += 2;
+    DPB_CUDA(h, cudaGetLastError());
+    return DPB_OK;
+}
+
+template <typename real>
+static void fill_common(dpb_handle* h, StepArgs<real>& a, const Layout& L, char* ws, const dpb_inputs* in, int64_t B_local, int64_t path_offset,
+                        int64_t B_global, int32_t N, double T, uint32_t flags, const dpb_path_outputs* outs) {
+    memset(&a, 0, sizeof(a));
+    fill_eqn(h->cfg, N, T, a.eq);
+    a.nA = h->nA; a.nV = h->nV; a.nG = h->nG;
+    a.pkA = (const real*)(ws + L.pkA); a.pkV = (const real*)(ws + L.pkV); a.pkG = (const real*)(ws + L.pkG);
+    a.x0 = (const real*)in->x0; a.dw = (const real*)in->dw; a.xb = (const real*)in->x_bdry;
+    a.dw_mode = in->dw_mode; a.seed = in->seed; a.stream = in->stream;
+    a.B_local = B_local; a.path_offset = path_offset;
+    a.invB = (real)(1.0 / (double)B_global);
+    a.N = N; a.flags = flags;
+    a.loss_part = (real*)(ws + L.loss_part);
+    a.scratch = (real*)(ws + L.scratch);
+    a.scratch_per_cta = L.scratch_per_cta;
+    a.sr = h->sr; a.hrows = h->hrows; a.nhb = h->nhb;
+    if (outs) {
+        a.o_x = (real*)outs->x_smp; a.o_dt = (real*)outs->dt; a.o_coef = (real*)outs->coef;
+        a.o_delta = (real*)outs->delta; a.o_delta_b = (real*)outs->delta_bdry; a.o_exit = outs->exit_index;
+    }
+}
+
+static int check_step_args(dpb_handle* h, const dpb_inputs* in, int64_t B_local, int64_t B_global, int32_t N, double T,
+                           void* ws, int64_t ws_bytes, const char* who) {
+    if (!h) return fail(nullptr, DPB_ERR_ARG, std::string(who) + ": null handle");
+    if (!in || !in->x0) return fail(h, DPB_ERR_ARG, std::string(who) + ": x0 is required");
+    if (B_local < 1 || B_global < B_local || N < 1 || !(T > 0)) return fail(h, DPB_ERR_ARG, std::string(who) + ": bad B_local/B_global/N/T");
+    if (in->dw_mode == DPB_DW_EXTERNAL && !in->dw) return fail(h, DPB_ERR_ARG, std::string(who) + ": dw is NULL but dw_mode is EXTERNAL");
+    if (in->dw_mode < DPB_DW_EXTERNAL || in->dw_mode > DPB_DW_PHILOX_BOUNDED) return fail(h, DPB_ERR_ARG, std::string(who) + ": bad dw_mode");
+    if (!ws) return fail(h, DPB_ERR_WORKSPACE, std::string(who) + ": workspace is NULL");
+    const int64_t need = dpb_workspace_bytes(h, B_local, N);
+    if (ws_bytes < need) return fail(h, DPB_ERR_WORKSPACE, std::string(who) + ": workspace too small, need " + std::to_string(need) + " bytes");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) {
+        cudaGetLastError();
+        return fail(h, DPB_ERR_CUDA, std::string(who) + ": no CUDA device (there is no CPU fallback)");
+    }
+    return DPB_OK;
+}
+
+template <typename real>
+static int critic_step_t(dpb_handle* h, const void* thA, const void* thV, const void* thG, const dpb_inputs* in, int64_t B_local,
+                         int64_t path_offset, int64_t B_global, int32_t N, double T, uint32_t flags, void* out_loss, void* grad_V,
+                         void* grad_G, const dpb_path_outputs* outs, void* workspace, cudaStream_t st) {
+    char* ws = (char*)workspace;
+    const Layout L = make_layout(h, B_local, N);
+    StepArgs<real> a;
+    fill_common<real>(h, a, L, ws, in, B_local, path_offset, B_global, N, T, flags, outs);
+    const bool cheat = flags & DPB_FLAG_CHEAT_CONTROL, need_grad = (flags & DPB_FLAG_NEED_GRAD) && !(flags & DPB_FLAG_PROPAGATE_ONLY);
+    const bool prop_only = flags & DPB_FLAG_PROPAGATE_ONLY;
+    const bool td1 = h->cfg.td_type == DPB_TD1;
+    int rc;
+    if (!cheat) { if ((rc = pack_net<real>(h, h->nA, thA, ws + L.pkA, st))) return rc; }
+    if (!prop_only) {
+        if ((rc = pack_net<real>(h, h->nV, thV, ws + L.pkV, st))) return rc;
+        if (td1) { if ((rc = pack_net<real>(h, h->nG, thG, ws + L.pkG, st))) return rc; }
+    }
+    if (need_grad) {
+        a.slabV = (real*)(ws + L.slabs);
+        a.slabG = a.slabV + (size_t)L.grid * h->nV.gtotal;
+        DPB_CUDA(h, cudaMemsetAsync(ws + L.slabs, 0, (size_t)L.grid * (h->nV.gtotal + h->nG.gtotal) * sizeof(real), st));
+    }
+    const size_t smem = carve_elems<real>(h->sr, h->hrows, h->nhb) * sizeof(real);
+    DPB_CUDA(h, cudaFuncSetAttribute(critic_kernel<real>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    critic_kernel<real><<<L.grid, NTHREADS, smem, st>>>(a);
+    h->launches++;
+    DPB_CUDA(h, cudaGetLastError());
+    if (out_loss && !prop_only) {
+        const real s = (real)(100.0 / (double)B_global);
+        reduce_loss_kernel<real><<<1, 32, 0, st>>>(a.loss_part, L.grid, s, s, (real*)out_loss);
+        h->launches++;
+    }
+    if (need_grad) {
+        real* raw = (real*)(ws + L.raw);
+        if (grad_V) { if ((rc = finalize_net<real>(h, h->nV, thV, a.slabV, L.grid, raw, grad_V, st))) return rc; }
+        if (grad_G) {
+            if (td1) { if ((rc = finalize_net<real>(h, h->nG, thG, a.slabG, L.grid, raw + h->nV.gtotal, grad_G, st))) return rc; }
+            else DPB_CUDA(h, cudaMemsetAsync(grad_G, 0, (size_t)h->nG.ftotal * sizeof(real), st));      // Keras skips None grads
+        }
+    }
+    DPB_CUDA(h, cudaGetLastError());
+    return DPB_OK;
+}
+
+template <typename real>
+static int actor_step_t(dpb_handle* h, const void* thA, const void* thV, const dpb_inputs* in, int64_t B_local, int64_t path_offset,
+                        int64_t B_global, int32_t N, double T, uint32_t flags, void* out_loss, void* grad_A,
+                        const dpb_path_outputs* outs, void* workspace, cudaStream_t st) {
+    char* ws = (char*)workspace;
+    const Layout L = make_layout(h, B_local, N);
+    StepArgs<real> a;
+    fill_common<real>(h, a, L, ws, in, B_local, path_offset, B_global, N, T, flags, outs);
+    const bool cheat = flags & DPB_FLAG_CHEAT_CONTROL, cheat_v = flags & DPB_FLAG_CHEAT_VALUE;
+    const bool need_grad = (flags & DPB_FLAG_NEED_GRAD) && !cheat;
+    int rc;
+    if (!cheat) { if ((rc = pack_net<real>(h, h->nA, thA, ws + L.pkA, st))) return rc; }
+    if (!cheat_v) { if ((rc = pack_net<real>(h, h->nV, thV, ws + L.pkV, st))) return rc; }
+    if (need_grad) {
+        a.slabA = (real*)(ws + L.slabs);
+        DPB_CUDA(h, cudaMemsetAsync(ws + L.slabs, 0, (size_t)L.grid * h->nA.gtotal * sizeof(real), st));
+    }
+    const size_t smem = carve_elems<real>(h->sr, h->hrows, h->nhb) * sizeof(real);
+    DPB_CUDA(h, cudaFuncSetAttribute(actor_kernel<real>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    actor_kernel<real><<<L.grid, NTHREADS, smem, st>>>(a);
+    h->launches++;
+    DPB_CUDA(h, cudaGetLastError());
+    if (out_loss) {
+        reduce_loss_kernel<real><<<1, 32, 0, st>>>(a.loss_part, L.grid, (real)(1.0 / (double)B_global), (real)0, (real*)out_loss);
+        h->launches++;
+    }
+    if (grad_A) {
+        if (need_grad) { if ((rc = finalize_net<real>(h, h->nA, thA, a.slabA, L.grid, (real*)(ws + L.raw), grad_A, st))) return rc; }
+        else if (flags & DPB_FLAG_NEED_GRAD) DPB_CUDA(h, cudaMemsetAsync(grad_A, 0, (size_t)h->nA.ftotal * sizeof(real), st));
+    }
+    DPB_CUDA(h, cudaGetLastError());
+    return DPB_OK;
+}
+
+extern "C" {
+
+int dpb_critic_step(dpb_handle* h, const void* theta_actor, const void* theta_V, const void* theta_G, const dpb_inputs* in,
+                    int64_t B_local, int64_t path_offset, int64_t B_global, int32_t N, double T, uint32_t flags, void* out_loss,
+                    void* grad_V, void* grad_G, const dpb_path_outputs* outs, void* workspace, int64_t workspace_bytes, void* stream) {
+    int rc = check_step_args(h, in, B_local, B_global, N, T, workspace, workspace_bytes, "dpb_critic_step");
+    if (rc) return rc;
+    const bool prop_only = flags & DPB_FLAG_PROPAGATE_ONLY, cheat = flags & DPB_FLAG_CHEAT_CONTROL;
+    if (!cheat && !theta_actor) return fail(h, DPB_ERR_ARG, "dpb_critic_step: theta_actor is NULL");
+    if (!prop_only && (!theta_V || !in->x_bdry)) return fail(h, DPB_ERR_ARG, "dpb_critic_step: theta_V and x_bdry are required");
+    if (!prop_only && h->cfg.td_type == DPB_TD1 && !theta_G) return fail(h, DPB_ERR_ARG, "dpb_critic_step: theta_G is NULL under TD1");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (h->cfg.dtype == DPB_F64)
+        return critic_step_t<double>(h, theta_actor, theta_V, theta_G, in, B_local, path_offset, B_global, N, T, flags, out_loss, grad_V, grad_G, outs, workspace, st);
+    return critic_step_t<float>(h, theta_actor, theta_V, theta_G, in, B_local, path_offset, B_global, N, T, flags, out_loss, grad_V, grad_G, outs, workspace, st);
+}
+
+int dpb_actor_step(dpb_handle* h, const void* theta_actor, const void* theta_V, const dpb_inputs* in, int64_t B_local,
+                   int64_t path_offset, int64_t B_global, int32_t N, double T, uint32_t flags, void* out_loss, void* grad_actor,
+                   const dpb_path_outputs* outs, void* workspace, int64_t workspace_bytes, void* stream) {
+    int rc = check_step_args(h, in, B_local, B_global, N, T, workspace, workspace_bytes, "dpb_actor_step");
+    if (rc) return rc;
+    if (!(flags & DPB_FLAG_CHEAT_CONTROL) && !theta_actor) return fail(h, DPB_ERR_ARG, "dpb_actor_step: theta_actor is NULL");
+    if (!(flags & DPB_FLAG_CHEAT_VALUE) && !theta_V) return fail(h, DPB_ERR_ARG, "dpb_actor_step: theta_V is NULL");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (h->cfg.dtype == DPB_F64)
+        return actor_step_t<double>(h, theta_actor, theta_V, in, B_local, path_offset, B_global, N, T, flags, out_loss, grad_actor, outs, workspace, st);
+    return actor_step_t<float>(h, theta_actor, theta_V, in, B_local, path_offset, B_global, N, T, flags, out_loss, grad_actor, outs, workspace, st);
+}
+
+static int host_stage(dpb_handle* h, const dpb_inputs* in_host, dpb_inputs* dev, int64_t B_local, int32_t N, char* ws, int64_t ws_bytes,
+                      int64_t* used, bool need_xb, cudaStream_t st) {
+    const size_t es = esize(h);
+    const int64_t base = dpb_workspace_bytes(h, B_local, N);
+    const int64_t stg = dpb_staging_bytes(h, B_local, N, in_host->dw_mode);
+    if (ws_bytes < base + stg) return fail(h, DPB_ERR_WORKSPACE, "host entry point: workspace too small, need " + std::to_string(base + stg) + " bytes");
+    char* p = ws + base;
+    const size_t nx = (size_t)B_local * h->cfg.dim * es;
+    *dev = *in_host;
+    DPB_CUDA(h, cudaMemcpyAsync(p, in_host->x0, nx, cudaMemcpyHostToDevice, st));
+    dev->x0 = p; p += a256(nx);
+    if (need_xb && in_host->x_bdry) {
+        DPB_CUDA(h, cudaMemcpyAsync(p, in_host->x_bdry, nx, cudaMemcpyHostToDevice, st));
+        dev->x_bdry = p;
+    }
+    p += a256(nx);
+    if (in_host->dw_mode == DPB_DW_EXTERNAL) {
+        DPB_CUDA(h, cudaMemcpyAsync(p, in_host->dw, nx * N, cudaMemcpyHostToDevice, st));
+        dev->dw = p;
+    }
+    *used = base;
+    return DPB_OK;
+}
+
+int dpb_critic_step_host(dpb_handle* h, const void* theta_actor, const void* theta_V, const void* theta_G, const dpb_inputs* in_host,
+                         int64_t B_local, int64_t path_offset, int64_t B_global, int32_t N, double T, uint32_t flags,
+                         void* out_loss_host, void* grad_V, void* grad_G, void* workspace, int64_t workspace_bytes, void* stream) {
+    if (!h || !in_host || !in_host->x0 || !workspace) return fail(h, DPB_ERR_ARG, "dpb_critic_step_host: null argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    dpb_inputs dev;
+    int64_t base = 0;
+    int rc = host_stage(h, in_host, &dev, B_local, N, (char*)workspace, workspace_bytes, &base, true, st);
+    if (rc) return rc;
+    const Layout L = make_layout(h, B_local, N);
+    void* loss_dev = (char*)workspace + L.loss_out;
+    rc = dpb_critic_step(h, theta_actor, theta_V, theta_G, &dev, B_local, path_offset, B_global, N, T, flags, loss_dev, grad_V, grad_G,
+                         nullptr, workspace, base, stream);
+    if (rc) return rc;
+    if (out_loss_host) DPB_CUDA(h, cudaMemcpyAsync(out_loss_host, loss_dev, 2 * esize(h), cudaMemcpyDeviceToHost, st));
+    DPB_CUDA(h, cudaStreamSynchronize(st));
+    return DPB_OK;
+}
+
+int dpb_actor_step_host(dpb_handle* h, const void* theta_actor, const void* theta_V, const dpb_inputs* in_host, int64_t B_local,
+                        int64_t path_offset, int64_t B_global, int32_t N, double T, uint32_t flags, void* out_loss_host,
+                        void* grad_actor, void* workspace, int64_t workspace_bytes, void* stream) {
+    if (!h || !in_host || !in_host->x0 || !workspace) return fail(h, DPB_ERR_ARG, "dpb_actor_step_host: null argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    dpb_inputs dev;
+    int64_t base = 0;
+    int rc = host_stage(h, in_host, &dev, B_local, N, (char*)workspace, workspace_bytes, &base, false, st);
+    if (rc) return rc;
+    const Layout L = make_layout(h, B_local, N);
+    void* loss_dev = (char*)workspace + L.loss_out;
+    rc = dpb_actor_step(h, theta_actor, theta_V, &dev, B_local, path_offset, B_global, N, T, flags, loss_dev, grad_actor, nullptr,
+                        workspace, base, stream);
+    if (rc) return rc;
+    if (out_loss_host) DPB_CUDA(h, cudaMemcpyAsync(out_loss_host, loss_dev, 2 * esize(h), cudaMemcpyDeviceToHost, st));
+    DPB_CUDA(h, cudaStreamSynchronize(st));
+    return DPB_OK;
+}
+
+int dpb_mlp_forward(dpb_handle* h, int which, const void* theta, const void* x, int64_t n, void* out, void* workspace,
+                    int64_t workspace_bytes, void* stream) {
+    if (!h) return fail(nullptr, DPB_ERR_ARG, "dpb_mlp_forward: null handle");
+    if (!theta || !x || !out || n < 1) return fail(h, DPB_ERR_ARG, "dpb_mlp_forward: null argument or n < 1");
+    const NetDev* nd = which == DPB_NET_ACTOR ? &h->nA : which == DPB_NET_CRITIC ? &h->nV : which == DPB_NET_CRITIC_GRAD ? &h->nG : nullptr;
+    if (!nd) return fail(h, DPB_ERR_ARG, "dpb_mlp_forward: unknown network id");
+    const size_t es = esize(h);
+    if (!workspace || workspace_bytes < (int64_t)a256(nd->ptotal * es)) return fail(h, DPB_ERR_WORKSPACE, "dpb_mlp_forward: workspace too small");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) { cudaGetLastError(); return fail(h, DPB_ERR_CUDA, "dpb_mlp_forward: no CUDA device (there is no CPU fallback)"); }
+    cudaStream_t st = (cudaStream_t)stream;
+    const int P = tileP(h);
+    long long ntiles = (n + P - 1) / P;
+    const int grid = (int)(ntiles < h->num_sms ? ntiles : h->num_sms);
+    int rc;
+    if (h->cfg.dtype == DPB_F64) {
+        if ((rc = pack_net<double>(h, *nd, theta, workspace, st))) return rc;
+        const size_t smem = carve_elems<double>(h->sr, h->hrows, 2) * 8;
+        DPB_CUDA(h, cudaFuncSetAttribute(mlp_forward_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        mlp_forward_kernel<double><<<grid, NTHREADS, smem, st>>>(*nd, (const double*)workspace, (const double*)x, n, (double*)out, h->sr, h->hrows);
+    } else {
+        if ((rc = pack_net<float>(h, *nd, theta, workspace, st))) return rc;
+        const size_t smem = carve_elems<float>(h->sr, h->hrows, 2) * 4;
+        DPB_CUDA(h, cudaFuncSetAttribute(mlp_forward_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        mlp_forward_kernel<float><<<grid, NTHREADS, smem, st>>>(*nd, (const float*)workspace, (const float*)x, n, (float*)out, h->sr, h->hrows);
+    }
+    h->launches++;
+    DPB_CUDA(h, cudaGetLastError());
+    return DPB_OK;
+}
+
+int dpb_closed_form(dpb_handle* h, int which, const void* x, const void* u, int64_t n, void* out, void* stream) {
+    if (!h) return fail(nullptr, DPB_ERR_ARG, "dpb_closed_form: null handle");
+    if (!x || !out || n < 1 || which < 0 || which > 4 || (which == 4 && !u)) return fail(h, DPB_ERR_ARG, "dpb_closed_form: bad argument");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) { cudaGetLastError(); return fail(h, DPB_ERR_CUDA, "dpb_closed_form: no CUDA device (there is no CPU fallback)"); }
+    EqnD e;
+    fill_eqn(h->cfg, 1, 1.0, e);
+    const int blocks = (int)((n + 127) / 128);
+    if (h->cfg.dtype == DPB_F64) closed_form_kernel<double><<<blocks, 128, 0, (cudaStream_t)stream>>>(e, which, (const double*)x, (const double*)u, n, (double*)out);
+    else closed_form_kernel<float><<<blocks, 128, 0, (cudaStream_t)stream>>>(e, which, (const float*)x, (const float*)u, n, (float*)out);
+    h->launches++;
+    DPB_CUDA(h, cudaGetLastError());
+    return DPB_OK;
+}
+
+int dpb_adam_step(dpb_handle* h, void* theta, const void* grad, void* m, void* v, int64_t n, double lr_t, double beta1, double beta2,
+                  double eps, void* stream) {
+    if (!h) return fail(nullptr, DPB_ERR_ARG, "dpb_adam_step: null handle");
+    if (!theta || !grad || !m || !v || n < 1) return fail(h, DPB_ERR_ARG, "dpb_adam_step: null argument");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) { cudaGetLastError(); return fail(h, DPB_ERR_CUDA, "dpb_adam_step: no CUDA device (there is no CPU fallback)"); }
+    int blocks = (int)((n + 255) / 256);
+    if (blocks > 1184) blocks = 1184;
+    if (h->cfg.dtype == DPB_F64) adam_kernel<double><<<blocks, 256, 0, (cudaStream_t)stream>>>((double*)theta, (const double*)grad, (double*)m, (double*)v, n, lr_t, beta1, beta2, eps);
+    else adam_kernel<float><<<blocks, 256, 0, (cudaStream_t)stream>>>((float*)theta, (const float*)grad, (float*)m, (float*)v, n, (float)lr_t, (float)beta1, (float)beta2, (float)eps);
+    h->launches++;
+    DPB_CUDA(h, cudaGetLastError());
+    return DPB_OK;
+}
+
+int dpb_philox_dw(dpb_handle* h, int32_t dw_mode, uint64_t seed, uint64_t stream_id, int64_t path_offset, int64_t B_local, int32_t N,
+                  void* dw_out, void* stream) {
+    if (!h) return fail(nullptr, DPB_ERR_ARG, "dpb_philox_dw: null handle");
+    if (!dw_out || B_local < 1 || N < 1 || (dw_mode != DPB_DW_PHILOX_NORMAL && dw_mode != DPB_DW_PHILOX_BOUNDED)) return fail(h, DPB_ERR_ARG, "dpb_philox_dw: bad argument");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) { cudaGetLastError(); return fail(h, DPB_ERR_CUDA, "dpb_philox_dw: no CUDA device (there is no CPU fallback)"); }
+    const int d = h->cfg.dim;
+    long long total = (long long)B_local * N * ((d + 3) / 4);
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > 2368) blocks = 2368;
+    if (h->cfg.dtype == DPB_F64) philox_dw_kernel<double><<<blocks, 256, 0, (cudaStream_t)stream>>>(dw_mode, seed, stream_id, path_offset, B_local, d, N, (double*)dw_out);
+    else philox_dw_kernel<float><<<blocks, 256, 0, (cudaStream_t)stream>>>(dw_mode, seed, stream_id, path_offset, B_local, d, N, (float*)dw_out);
+    h->launches++;
+    DPB_CUDA(h, cudaGetLastError());
+    return DPB_OK;
+}
+
+int dpb_sample_x(dpb_handle* h, uint64_t seed, uint64_t stream_id, int64_t path_offset, int64_t B_local, void* x0_out, void* xb_out,
+                 void* stream) {
+    if (!h) return fail(nullptr, DPB_ERR_ARG, "dpb_sample_x: null handle");
+    if ((!x0_out && !xb_out) || B_local < 1) return fail(h, DPB_ERR_ARG, "dpb_sample_x: bad argument");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) { cudaGetLastError(); return fail(h, DPB_ERR_CUDA, "dpb_sample_x: no CUDA device (there is no CPU fallback)"); }
+    const int blocks = (int)((B_local + 127) / 128);
+    if (h->cfg.dtype == DPB_F64) sample_x_kernel<double><<<blocks, 128, 0, (cudaStream_t)stream>>>(seed, stream_id, path_offset, B_local, h->cfg.dim, h->cfg.R, (double*)x0_out, (double*)xb_out);
+    else sample_x_kernel<float><<<blocks, 128, 0, (cudaStream_t)stream>>>(seed, stream_id, path_offset, B_local, h->cfg.dim, (float)h->cfg.R, (float*)x0_out, (float*)xb_out);
+    h->launches++;
+    DPB_CUDA(h, cudaGetLastError());
+    return DPB_OK;
+}
+
+}  // extern "C"

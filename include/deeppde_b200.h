@@ -40,6 +40,8 @@ enum { DPB_TD1 = 1, DPB_TD2 = 2 };                                              
 enum { DPB_F32 = 0, DPB_F64 = 1 };
 enum { DPB_NET_ACTOR = 0, DPB_NET_CRITIC = 1, DPB_NET_CRITIC_GRAD = 2 };            /* solver.py:145-146,200 */
 enum { DPB_DW_EXTERNAL = 0, DPB_DW_PHILOX_NORMAL = 1, DPB_DW_PHILOX_BOUNDED = 2 };  /* equation.py:19,31-32 */
+enum { DPB_IMPL_EXACT = 0, DPB_IMPL_TENSOR = 1 };
+enum { DPB_CF_V_TRUE = 0, DPB_CF_U_TRUE = 1, DPB_CF_V_GRAD_TRUE = 2, DPB_CF_Z = 3, DPB_CF_W = 4 };
 
 /* flags of dpb_critic_step / dpb_actor_step */
 enum {
@@ -59,7 +61,8 @@ typedef struct dpb_config {
     int32_t n_hidden_actor, n_hidden_critic;
     int32_t hidden_actor[DPB_MAX_HIDDEN];
     int32_t hidden_critic[DPB_MAX_HIDDEN];
-    int32_t reserved[4];
+    int32_t impl;                  /* DPB_IMPL_EXACT: FP32/FP64 CUDA-core FMA; DPB_IMPL_TENSOR: tcgen05 MLP layers */
+    int32_t reserved[3];
     double R, discount;            /* eqn_config.R, discount */
     double p, q, beta;             /* LQR / LQR_var */
     double a, epsilon;             /* VDP (a, epsilon) / LQR_var (epsilon) */
@@ -103,6 +106,10 @@ int64_t dpb_param_count(const dpb_handle* h, int which_net);
 /* Bytes of device workspace the step calls need for shards up to B_local paths of N steps. */
 int64_t dpb_workspace_bytes(const dpb_handle* h, int64_t B_local, int32_t N);
 
+/* Extra bytes the *_host entry points need after the first dpb_workspace_bytes() bytes of `workspace`
+ * to stage x0, x_bdry (and dw when dw_mode is EXTERNAL) on the device. */
+int64_t dpb_staging_bytes(const dpb_handle* h, int64_t B_local, int32_t N, int32_t dw_mode);
+
 /* CriticModel.call + loss_critic + grad_critic (solver.py:73-78,85-90,159-191).
  *   out_loss[2]: { 100/B_global * sum rho(delta), 100/B_global * sum rho(delta_bdry) } over the shard;
  *   grad_V, grad_G: gradient of loss_critic w.r.t. NN_value / NN_value_grad parameters restricted
@@ -126,6 +133,11 @@ int dpb_actor_step(dpb_handle* h, const void* theta_actor, const void* theta_V,
 int dpb_mlp_forward(dpb_handle* h, int which_net, const void* theta, const void* x, int64_t n,
                     void* out, void* workspace, int64_t workspace_bytes, void* stream);
 
+/* Closed forms of the equation on n points (equation.py:157-167,201-227,252-265,292-302):
+ *   which = DPB_CF_V_TRUE (out[n]), DPB_CF_U_TRUE (out[n][control_dim]), DPB_CF_V_GRAD_TRUE (out[n][dim]),
+ *   DPB_CF_Z (Z_tf, out[n]), DPB_CF_W (w_tf(x,u), out[n]; u[n][control_dim] required, else NULL). */
+int dpb_closed_form(dpb_handle* h, int which, const void* x, const void* u, int64_t n, void* out, void* stream);
+
 /* tf.keras Adam step as used at solver.py:16-21,99-107 on a flat vector:
  *   m += (g-m)(1-b1); v += (g*g-v)(1-b2); theta -= lr_t * m / (sqrt(v)+eps),  lr_t given by the host. */
 int dpb_adam_step(dpb_handle* h, void* theta, const void* grad, void* m, void* v, int64_t n,
@@ -136,9 +148,15 @@ int dpb_adam_step(dpb_handle* h, void* theta, const void* grad, void* m, void* v
 int dpb_philox_dw(dpb_handle* h, int32_t dw_mode, uint64_t seed, uint64_t stream_id, int64_t path_offset,
                   int64_t B_local, int32_t N, void* dw_out, void* stream);
 
+/* Device-side version of the x0 / x_bdry part of Equation.sample_normal (equation.py:14-22): x0 uniform
+ * in the ball |x|<R, x_bdry uniform on the sphere, Philox-keyed by the GLOBAL path index (so that a run
+ * sees the same paths however it is sharded).  Either output may be NULL. */
+int dpb_sample_x(dpb_handle* h, uint64_t seed, uint64_t stream_id, int64_t path_offset, int64_t B_local,
+                 void* x0_out, void* xb_out, void* stream);
+
 /* Host-buffer convenience used for end-to-end timing: same as dpb_critic_step / dpb_actor_step but
  * x0/dw/x_bdry are HOST pointers (pinned or pageable); they are copied to device staging inside
- * `workspace` on `stream`, and out_loss_host receives the losses after a stream synchronise. */
+ * `workspace` (after its first dpb_workspace_bytes() bytes; see dpb_staging_bytes) on `stream`, and out_loss_host receives the losses after a stream synchronise. */
 int dpb_critic_step_host(dpb_handle* h, const void* theta_actor, const void* theta_V, const void* theta_G,
                          const dpb_inputs* in_host, int64_t B_local, int64_t path_offset, int64_t B_global,
                          int32_t N, double T, uint32_t flags,
