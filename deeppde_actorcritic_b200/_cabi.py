@@ -78,6 +78,7 @@ SYMBOLS = {
     "dpb_actor_step_host": (C.c_int, [_P, _P, _P, C.POINTER(dpb_inputs), _I64, _I64, _I64, _I32, _D, _U32,
                                       _P, _P, _P, _I64, _P]),
     "dpb_launch_count": (_I64, [_P]),
+    "dpb_last_kernel_ms": (_D, [_P]),
 }
 
 _lib = None

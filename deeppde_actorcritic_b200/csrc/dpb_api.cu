@@ -19,8 +19,21 @@ struct dpb_handle {
     int max_smem;
     int sr, hrows, nhb;
     long long launches;
+    cudaEvent_t ev0, ev1;
+    bool have_ev, timed;
     std::string err;
 };
+
+static void ev_begin(dpb_handle* h, cudaStream_t st) {
+    if (!h->have_ev) {
+        if (cudaEventCreate(&h->ev0) != cudaSuccess || cudaEventCreate(&h->ev1) != cudaSuccess) { cudaGetLastError(); return; }
+        h->have_ev = true;
+    }
+    cudaEventRecord(h->ev0, st);
+}
+static void ev_end(dpb_handle* h, cudaStream_t st) {
+    if (h->have_ev) { cudaEventRecord(h->ev1, st); h->timed = true; }
+}
 
 static thread_local std::string g_err;
 
@@ -98,6 +111,8 @@ int dpb_create(dpb_handle** out, const dpb_config* cfg) {
     dpb_handle* h = new dpb_handle();
     h->cfg = c;
     h->launches = 0;
+    h->have_ev = false;
+    h->timed = false;
     const int ekn = (c.eqn == DPB_EQN_EKN);
     netdev_init(h->nA, c.dim, c.hidden_actor, c.n_hidden_actor, ekn ? c.control_dim + 1 : c.control_dim, ekn, c.control_dim);   // solver.py:255-258
     netdev_init(h->nV, c.dim, c.hidden_critic, c.n_hidden_critic, 1, 0, 0);                                                  // solver.py:251-252
@@ -127,6 +142,7 @@ int dpb_create(dpb_handle** out, const dpb_config* cfg) {
 }
 
 int dpb_destroy(dpb_handle* h) {
+    if (h && h->have_ev) { cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1); }
     delete h;
     return DPB_OK;
 }
@@ -155,6 +171,13 @@ int64_t dpb_staging_bytes(const dpb_handle* h, int64_t B_local, int32_t N, int32
 }
 
 int64_t dpb_launch_count(const dpb_handle* h) { return h ? h->launches : -1; }
+
+double dpb_last_kernel_ms(dpb_handle* h) {
+    if (!h || !h->timed) return -1.0;
+    float ms = -1.f;
+    if (cudaEventSynchronize(h->ev1) != cudaSuccess || cudaEventElapsedTime(&ms, h->ev0, h->ev1) != cudaSuccess) { cudaGetLastError(); return -1.0; }
+    return (double)ms;
+}
 
 }  // extern "C"
 
@@ -245,7 +268,9 @@ static int critic_step_t(dpb_handle* h, const void* thA, const void* thV, const 
     }
     const size_t smem = carve_elems<real>(h->sr, h->hrows, h->nhb) * sizeof(real);
     DPB_CUDA(h, cudaFuncSetAttribute(critic_kernel<real>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ev_begin(h, st);
     critic_kernel<real><<<L.grid, NTHREADS, smem, st>>>(a);
+    ev_end(h, st);
     h->launches++;
     DPB_CUDA(h, cudaGetLastError());
     if (out_loss && !prop_only) {
@@ -284,7 +309,9 @@ static int actor_step_t(dpb_handle* h, const void* thA, const void* thV, const d
     }
     const size_t smem = carve_elems<real>(h->sr, h->hrows, h->nhb) * sizeof(real);
     DPB_CUDA(h, cudaFuncSetAttribute(actor_kernel<real>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ev_begin(h, st);
     actor_kernel<real><<<L.grid, NTHREADS, smem, st>>>(a);
+    ev_end(h, st);
     h->launches++;
     DPB_CUDA(h, cudaGetLastError());
     if (out_loss) {

@@ -168,6 +168,51 @@ class Engine:
         res.update(loss=loss, grad_actor=gA)
         return res
 
+    # host-buffer entry points (end-to-end timing): x0 / x_bdry are pinned HOST tensors, the losses come
+    # back to the host; dw is generated in-kernel (Philox) unless a host dw tensor is given
+    def _host_ws(self, B, N, dw_mode):
+        nb = self.lib.dpb_workspace_bytes(self.handle, B, N) + self.lib.dpb_staging_bytes(self.handle, B, N, dw_mode)
+        return self.workspace(nb)
+
+    def critic_step_host(self, theta_actor, theta_V, theta_G, x0_h, dw_h, xb_h, N, T, *, B_global=None, path_offset=0,
+                         cheat_control=False, need_grad=True, dw_mode=_cabi.DW_PHILOX_NORMAL, seed=0, stream_id=0):
+        B = x0_h.shape[0]
+        Bg = B if B_global is None else B_global
+        if dw_h is not None:
+            dw_mode = _cabi.DW_EXTERNAL
+        flags = (1 if cheat_control else 0) | (4 if need_grad else 0)
+        ws = self._host_ws(B, N, dw_mode)
+        inp = self._inputs(x0_h, dw_h, xb_h, dw_mode, seed, stream_id)
+        loss_h = torch.zeros(2, dtype=self.dtype)
+        gV = torch.empty(self.n_params["critic"], dtype=self.dtype, device=self.device) if need_grad else None
+        gG = torch.empty(self.n_params["critic_grad"], dtype=self.dtype, device=self.device) if need_grad else None
+        rc = self.lib.dpb_critic_step_host(self.handle, self._p(theta_actor), self._p(theta_V), self._p(theta_G), C.byref(inp),
+                                           B, path_offset, Bg, N, float(T), flags, C.c_void_p(loss_h.data_ptr()), self._p(gV),
+                                           self._p(gG), C.c_void_p(ws.data_ptr()), ws.numel(), self._stream())
+        self._chk(rc)
+        return dict(loss=loss_h, grad_V=gV, grad_G=gG)
+
+    def actor_step_host(self, theta_actor, theta_V, x0_h, dw_h, N, T, *, B_global=None, path_offset=0, cheat_value=False,
+                        need_grad=True, dw_mode=_cabi.DW_PHILOX_NORMAL, seed=0, stream_id=0):
+        B = x0_h.shape[0]
+        Bg = B if B_global is None else B_global
+        if dw_h is not None:
+            dw_mode = _cabi.DW_EXTERNAL
+        flags = (2 if cheat_value else 0) | (4 if need_grad else 0)
+        ws = self._host_ws(B, N, dw_mode)
+        inp = self._inputs(x0_h, dw_h, None, dw_mode, seed, stream_id)
+        loss_h = torch.zeros(2, dtype=self.dtype)
+        gA = torch.empty(self.n_params["actor"], dtype=self.dtype, device=self.device) if need_grad else None
+        rc = self.lib.dpb_actor_step_host(self.handle, self._p(theta_actor), self._p(theta_V), C.byref(inp), B, path_offset, Bg,
+                                          N, float(T), flags, C.c_void_p(loss_h.data_ptr()), self._p(gA),
+                                          C.c_void_p(ws.data_ptr()), ws.numel(), self._stream())
+        self._chk(rc)
+        return dict(loss=loss_h, grad_actor=gA)
+
+    def last_kernel_ms(self):
+        """device time of the most recent critic/actor kernel launch (CUDA events recorded by the library)"""
+        return float(self.lib.dpb_last_kernel_ms(self.handle))
+
     def mlp_forward(self, kind, theta, x):
         """DeepNN.call (solver.py:260-278)."""
         which = {"actor": 0, "critic": 1, "critic_grad": 2}[kind]

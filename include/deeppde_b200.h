@@ -171,6 +171,10 @@ int dpb_actor_step_host(dpb_handle* h, const void* theta_actor, const void* thet
 /* Number of kernel launches issued by this handle since creation (for bench.py's gpu_launches). */
 int64_t dpb_launch_count(const dpb_handle* h);
 
+/* Device time in ms of the most recent critic/actor rollout kernel of this handle, from CUDA events the
+ * library records on the caller's stream around that launch (synchronises on the stop event; < 0 if none). */
+double dpb_last_kernel_ms(dpb_handle* h);
+
 #ifdef __cplusplus
 }
 #endif
