@@ -79,6 +79,7 @@ SYMBOLS = {
                                       _P, _P, _P, _I64, _P]),
     "dpb_launch_count": (_I64, [_P]),
     "dpb_last_kernel_ms": (_D, [_P]),
+    "dpb_tc_selftest": (C.c_int, [_P, _P, _P, C.c_int, _P]),
 }
 
 _lib = None

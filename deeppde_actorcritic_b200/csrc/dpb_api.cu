@@ -9,6 +9,7 @@
 #include "../../include/deeppde_b200.h"
 #include "dpb_host.h"
 #include "dpb_kernels.cuh"
+#include "dpb_tc_selftest.cuh"
 
 using namespace dpb;
 
@@ -511,3 +512,14 @@ int dpb_sample_x(dpb_handle* h, uint64_t seed, uint64_t stream_id, int64_t path_
 }
 
 }  // extern "C"
+
+extern "C" int dpb_tc_selftest(const float* A, const float* B, float* D, int K, void* stream) {
+    if (!A || !B || !D || K < 128 || K > 208 || (K % 16)) return fail(nullptr, DPB_ERR_ARG, "dpb_tc_selftest: need 128 <= K <= 208, K % 16 == 0");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) { cudaGetLastError(); return fail(nullptr, DPB_ERR_CUDA, "dpb_tc_selftest: no CUDA device"); }
+    const int smem = 128 * K * 2 + tc::ST_N * K * 2 + 128 * tc::ST_N * 2 + 64;
+    DPB_CUDA(nullptr, cudaFuncSetAttribute(tc::tc_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    tc::tc_selftest_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(A, B, D, K);
+    DPB_CUDA(nullptr, cudaGetLastError());
+    return DPB_OK;
+}

@@ -1,0 +1,116 @@
+// dpb_tc_selftest.cuh -- one-CTA check of the three tcgen05 product forms the tensor path uses:
+//   D1 = A * B^T          A[128][K], B[208][K] both K-major images in shared memory   (forward / dX)
+//   D2 = A * B^T          A read from TMEM (packed bf16 pairs written with tcgen05.st) (forward / dX)
+//   D3 = A^T * C          A[128 paths][K feats], C[128 paths][208 feats] read MN-major (dW)
+// Inputs are float (expected bf16-representable), outputs float [3][128][208].
+#pragma once
+#include "dpb_tc.cuh"
+
+namespace dpb {
+namespace tc {
+
+constexpr int ST_N = 208;
+
+__global__ void __launch_bounds__(128, 1) tc_selftest_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ D, int K) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int tid = threadIdx.x, warp = tid >> 5;
+    unsigned char* Aimg = smem;                              // R = 128
+    unsigned char* Bimg = Aimg + 128 * K * 2;                // R = 208
+    unsigned char* Cimg = Bimg + ST_N * K * 2;               // R = 128, K = 208 columns (features g)
+    uint64_t* bar = reinterpret_cast<uint64_t*>(Cimg + 128 * ST_N * 2);
+    uint32_t* tslot = reinterpret_cast<uint32_t*>(bar + 2);
+
+    for (int i = tid; i < 128 * K; i += 128) {
+        int r = i / K, k = i - r * K;
+        *reinterpret_cast<__nv_bfloat16*>(Aimg + img_off(r, k, 128)) = __float2bfloat16_rn(A[i]);
+    }
+    for (int i = tid; i < ST_N * K; i += 128) {
+        int r = i / K, k = i - r * K;
+        *reinterpret_cast<__nv_bfloat16*>(Bimg + img_off(r, k, ST_N)) = __float2bfloat16_rn(B[i]);
+    }
+    for (int i = tid; i < 128 * ST_N; i += 128) {
+        int p = i / ST_N, g = i - p * ST_N;
+        float v = (g < K) ? B[p * K + g] : 0.f;              // C[p][g] = B[p][g] (first 128 rows of B)
+        *reinterpret_cast<__nv_bfloat16*>(Cimg + img_off(p, g, 128)) = __float2bfloat16_rn(v);
+    }
+    if (tid == 0) { mbar_init(bar, 1); fence_barrier_init(); }
+    if (warp == 0) tmem_alloc(tslot, 512);
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tbase = *tslot;
+    const uint32_t lane_base = tbase + ((uint32_t)(warp * 32) << 16);
+    uint32_t phase = 0;
+    const uint32_t idK = idesc_bf16(128, ST_N, 0, 0), idMN = idesc_bf16(128, ST_N, 1, 1);
+
+    // ---- test 1: SS, K-major
+    if (tid == 0) {
+        for (int s = 0; s < K / 16; ++s) {
+            uint64_t ad = smem_desc(smem_u32(Aimg) + s * 2 * (128 / 8) * 128, (128 / 8) * 128, 128);
+            uint64_t bd = smem_desc(smem_u32(Bimg) + s * 2 * (ST_N / 8) * 128, (ST_N / 8) * 128, 128);
+            mma_ss(tbase, ad, bd, idK, s > 0);
+        }
+        tc_commit(bar);
+    }
+    mbar_wait(bar, phase); phase ^= 1;
+    tc_fence_after();
+    for (int c = 0; c < ST_N / 16; ++c) {
+        uint32_t v[16];
+        tmem_ld16(lane_base + c * 16, v);
+        tmem_ld_wait();
+        for (int j = 0; j < 16; ++j) D[(0 * 128 + tid) * ST_N + c * 16 + j] = __uint_as_float(v[j]);
+    }
+    // ---- test 2: TS (A row of this thread -> TMEM columns 256.. as packed pairs)
+    for (int c = 0; c < K / 16; ++c) {
+        uint32_t v[8];
+        for (int j = 0; j < 8; ++j)
+            v[j] = pack2(__float2bfloat16_rn(A[tid * K + c * 16 + 2 * j]), __float2bfloat16_rn(A[tid * K + c * 16 + 2 * j + 1]));
+        tmem_st8(lane_base + 256 + c * 8, v);
+    }
+    tmem_st_wait();
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+        tc_fence_after();
+        for (int s = 0; s < K / 16; ++s) {
+            uint64_t bd = smem_desc(smem_u32(Bimg) + s * 2 * (ST_N / 8) * 128, (ST_N / 8) * 128, 128);
+            mma_ts(tbase, tbase + 256 + s * 8, bd, idK, s > 0);
+        }
+        tc_commit(bar);
+    }
+    mbar_wait(bar, phase); phase ^= 1;
+    tc_fence_after();
+    for (int c = 0; c < ST_N / 16; ++c) {
+        uint32_t v[16];
+        tmem_ld16(lane_base + c * 16, v);
+        tmem_ld_wait();
+        for (int j = 0; j < 16; ++j) D[(1 * 128 + tid) * ST_N + c * 16 + j] = __uint_as_float(v[j]);
+    }
+    tc_fence_before();
+    __syncthreads();
+    // ---- test 3: SS, both MN-major: D3[f][g] = sum_p A[p][f] * C[p][g],  f < 128 (needs K >= 128)
+    if (tid == 0) {
+        tc_fence_after();
+        for (int s = 0; s < 128 / 16; ++s) {
+            uint64_t ad = smem_desc(smem_u32(Aimg) + s * 2 * 128, 128, (128 / 8) * 128);
+            uint64_t bd = smem_desc(smem_u32(Cimg) + s * 2 * 128, 128, (128 / 8) * 128);
+            mma_ss(tbase, ad, bd, idMN, s > 0);
+        }
+        tc_commit(bar);
+    }
+    mbar_wait(bar, phase); phase ^= 1;
+    tc_fence_after();
+    for (int c = 0; c < ST_N / 16; ++c) {
+        uint32_t v[16];
+        tmem_ld16(lane_base + c * 16, v);
+        tmem_ld_wait();
+        for (int j = 0; j < 16; ++j) D[(2 * 128 + tid) * ST_N + c * 16 + j] = __uint_as_float(v[j]);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tbase, 512);
+}
+
+}  // namespace tc
+}  // namespace dpb

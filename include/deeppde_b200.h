@@ -175,6 +175,11 @@ int64_t dpb_launch_count(const dpb_handle* h);
  * library records on the caller's stream around that launch (synchronises on the stop event; < 0 if none). */
 double dpb_last_kernel_ms(dpb_handle* h);
 
+/* Diagnostic: one CTA runs the three tcgen05 product forms of the tensor path on A[128][K], B[208][K]
+ * (device, float, bf16-representable) and writes D[3][128][208]: D0 = A B^T (operands in shared memory),
+ * D1 = A B^T (A read from tensor memory), D2[f][g] = sum_p A[p][f] B[p][g] (both operands MN-major). */
+int dpb_tc_selftest(const float* A, const float* B, float* D, int K, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
