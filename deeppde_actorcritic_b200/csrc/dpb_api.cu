@@ -10,12 +10,14 @@
 #include "dpb_host.h"
 #include "dpb_kernels.cuh"
 #include "dpb_tc_selftest.cuh"
+#include "dpb_tc_kernels.cuh"
 
 using namespace dpb;
 
 struct dpb_handle {
     dpb_config cfg;
     NetDev nA, nV, nG;
+    tc::TcNet tA, tV, tG;
     int num_sms;
     int max_smem;
     int sr, hrows, nhb;
@@ -58,16 +60,27 @@ static const double BN_C = 1.0 / sqrt(1.0 + 1e-6);       // solver.py:242 (epsil
 struct Layout {
     int grid;
     size_t pkA, pkV, pkG, loss_part, loss_out, scratch, slabs, raw, total;
+    size_t imgA, imgV, imgG, vecA, vecV, vecG;      // tensor path: operand images + vector blocks
     long long scratch_per_cta;
 };
 
 static Layout make_layout(const dpb_handle* h, long long B_local, int N) {
     Layout L;
     const size_t es = esize(h);
-    const int P = tileP(h);
+    const bool tensor = h->cfg.impl == DPB_IMPL_TENSOR;
+    const int P = tensor ? tc::TC_PATHS : tileP(h);
     long long ntiles = (B_local + P - 1) / P;
     L.grid = (int)(ntiles < h->num_sms ? (ntiles < 1 ? 1 : ntiles) : h->num_sms);
     size_t o = 0;
+    L.imgA = L.imgV = L.imgG = L.vecA = L.vecV = L.vecG = 0;
+    if (tensor) {
+        L.imgA = o; o += a256(h->tA.img_bytes);
+        L.imgV = o; o += a256(h->tV.img_bytes);
+        L.imgG = o; o += a256(h->tG.img_bytes);
+        L.vecA = o; o += a256((size_t)h->tA.vec_floats * 4);
+        L.vecV = o; o += a256((size_t)h->tV.vec_floats * 4);
+        L.vecG = o; o += a256((size_t)h->tG.vec_floats * 4);
+    }
     L.pkA = o; o += a256(h->nA.ptotal * es);
     L.pkV = o; o += a256(h->nV.ptotal * es);
     L.pkG = o; o += a256(h->nG.ptotal * es);
@@ -118,6 +131,14 @@ int dpb_create(dpb_handle** out, const dpb_config* cfg) {
     netdev_init(h->nA, c.dim, c.hidden_actor, c.n_hidden_actor, ekn ? c.control_dim + 1 : c.control_dim, ekn, c.control_dim);   // solver.py:255-258
     netdev_init(h->nV, c.dim, c.hidden_critic, c.n_hidden_critic, 1, 0, 0);                                                  // solver.py:251-252
     netdev_init(h->nG, c.dim, c.hidden_critic, c.n_hidden_critic, c.dim, 0, 0);                                              // solver.py:253-254
+    tc::tcnet_init(h->tA, c.dim, c.hidden_actor, c.n_hidden_actor, ekn ? c.control_dim + 1 : c.control_dim, ekn, c.control_dim);
+    tc::tcnet_init(h->tV, c.dim, c.hidden_critic, c.n_hidden_critic, 1, 0, 0);
+    tc::tcnet_init(h->tG, c.dim, c.hidden_critic, c.n_hidden_critic, c.dim, 0, 0);
+    if (c.impl != DPB_IMPL_EXACT && c.impl != DPB_IMPL_TENSOR) { delete h; return fail(nullptr, DPB_ERR_ARG, "impl must be DPB_IMPL_EXACT or DPB_IMPL_TENSOR"); }
+    if (c.impl == DPB_IMPL_TENSOR) {
+        if (c.dtype != DPB_F32) { delete h; return fail(nullptr, DPB_ERR_ARG, "the tensor path computes in float32 (bf16x3 products, FP32 accumulation): dtype must be DPB_F32"); }
+        if (!tc::tcnet_supported(h->tA) || !tc::tcnet_supported(h->tV) || !tc::tcnet_supported(h->tG)) { delete h; return fail(nullptr, DPB_ERR_ARG, "tensor path: layer width must be <= 255"); }
+    }
     const int mx = c.dim > c.control_dim + 1 ? c.dim : c.control_dim + 1;
     h->sr = round8(mx);
     h->hrows = round8(hmax);
@@ -327,6 +348,104 @@ static int actor_step_t(dpb_handle* h, const void* thA, const void* thV, const d
     return DPB_OK;
 }
 
+
+// ------------------------------------------------------------------------------------------------ tensor path
+static int tc_pack(dpb_handle* h, const tc::TcNet& t, const void* theta, char* ws, size_t img, size_t vec, cudaStream_t st) {
+    long long work = 0;
+    for (int l = 0; l <= t.L; ++l) work += (long long)t.ly[l].K16 * t.ly[l].N16;
+    int blocks = (int)((work + 255) / 256);
+    if (blocks > 592) blocks = 592;
+    tc::tc_pack_kernel<<<blocks, 256, 0, st>>>(t, (const float*)theta, (unsigned char*)(ws + img), (float*)(ws + vec), (float)BN_C);
+    h->launches++;
+    DPB_CUDA(h, cudaGetLastError());
+    return DPB_OK;
+}
+
+static void tc_fill(dpb_handle* h, tc::TcArgs& a, const Layout& L, char* ws, const dpb_inputs* in, int64_t B_local, int64_t path_offset,
+                    int64_t B_global, int32_t N, double T, uint32_t flags, const dpb_path_outputs* outs) {
+    memset(&a, 0, sizeof(a));
+    fill_eqn(h->cfg, N, T, a.eq);
+    a.nA = h->tA; a.nV = h->tV; a.nG = h->tG;
+    a.imgA = (const unsigned char*)(ws + L.imgA); a.imgV = (const unsigned char*)(ws + L.imgV); a.imgG = (const unsigned char*)(ws + L.imgG);
+    a.x0 = (const float*)in->x0; a.dw = (const float*)in->dw; a.xb = (const float*)in->x_bdry;
+    a.dw_mode = in->dw_mode; a.seed = in->seed; a.stream = in->stream;
+    a.B_local = B_local; a.path_offset = path_offset;
+    a.invB = (float)(1.0 / (double)B_global);
+    a.N = N; a.flags = flags;
+    a.loss_part = (float*)(ws + L.loss_part);
+    a.scratch = (float*)(ws + L.scratch);
+    a.scratch_per_cta = L.scratch_per_cta;
+    a.sr = h->sr;
+    if (outs) {
+        a.o_x = (float*)outs->x_smp; a.o_dt = (float*)outs->dt; a.o_coef = (float*)outs->coef;
+        a.o_delta = (float*)outs->delta; a.o_delta_b = (float*)outs->delta_bdry; a.o_exit = outs->exit_index;
+    }
+}
+
+static int critic_step_tc(dpb_handle* h, const void* thA, const void* thV, const void* thG, const dpb_inputs* in, int64_t B_local,
+                          int64_t path_offset, int64_t B_global, int32_t N, double T, uint32_t flags, void* out_loss, void* grad_V,
+                          void* grad_G, const dpb_path_outputs* outs, void* workspace, cudaStream_t st) {
+    char* ws = (char*)workspace;
+    const Layout L = make_layout(h, B_local, N);
+    tc::TcArgs a;
+    tc_fill(h, a, L, ws, in, B_local, path_offset, B_global, N, T, flags, outs);
+    const bool cheat = flags & DPB_FLAG_CHEAT_CONTROL, prop_only = flags & DPB_FLAG_PROPAGATE_ONLY;
+    const bool need_grad = (flags & DPB_FLAG_NEED_GRAD) && !prop_only;
+    const bool td1 = h->cfg.td_type == DPB_TD1;
+    if (need_grad) return fail(h, DPB_ERR_ARG, "tensor path: gradients not implemented yet");
+    int rc;
+    if (!cheat) { if ((rc = tc_pack(h, h->tA, thA, ws, L.imgA, L.vecA, st))) return rc; a.vecA = (const float*)(ws + L.vecA); }
+    if (!prop_only) {
+        if ((rc = tc_pack(h, h->tV, thV, ws, L.imgV, L.vecV, st))) return rc;
+        a.vecV = (const float*)(ws + L.vecV);
+        if (td1) { if ((rc = tc_pack(h, h->tG, thG, ws, L.imgG, L.vecG, st))) return rc; a.vecG = (const float*)(ws + L.vecG); }
+    }
+    const size_t smem = tc::tc_smem_bytes(h->tA.vec_floats, h->tV.vec_floats, h->tG.vec_floats);
+    DPB_CUDA(h, cudaFuncSetAttribute(tc::critic_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ev_begin(h, st);
+    tc::critic_tc_kernel<<<L.grid, tc::TC_THREADS, smem, st>>>(a);
+    ev_end(h, st);
+    h->launches++;
+    DPB_CUDA(h, cudaGetLastError());
+    if (out_loss && !prop_only) {
+        const float s = (float)(100.0 / (double)B_global);
+        reduce_loss_kernel<float><<<1, 32, 0, st>>>(a.loss_part, L.grid, s, s, (float*)out_loss);
+        h->launches++;
+    }
+    (void)grad_V; (void)grad_G;
+    DPB_CUDA(h, cudaGetLastError());
+    return DPB_OK;
+}
+
+static int actor_step_tc(dpb_handle* h, const void* thA, const void* thV, const dpb_inputs* in, int64_t B_local, int64_t path_offset,
+                         int64_t B_global, int32_t N, double T, uint32_t flags, void* out_loss, void* grad_A,
+                         const dpb_path_outputs* outs, void* workspace, cudaStream_t st) {
+    char* ws = (char*)workspace;
+    const Layout L = make_layout(h, B_local, N);
+    tc::TcArgs a;
+    tc_fill(h, a, L, ws, in, B_local, path_offset, B_global, N, T, flags, outs);
+    const bool cheat = flags & DPB_FLAG_CHEAT_CONTROL, cheat_v = flags & DPB_FLAG_CHEAT_VALUE;
+    const bool need_grad = (flags & DPB_FLAG_NEED_GRAD) && !cheat;
+    if (need_grad) return fail(h, DPB_ERR_ARG, "tensor path: gradients not implemented yet");
+    int rc;
+    if (!cheat) { if ((rc = tc_pack(h, h->tA, thA, ws, L.imgA, L.vecA, st))) return rc; a.vecA = (const float*)(ws + L.vecA); }
+    if (!cheat_v) { if ((rc = tc_pack(h, h->tV, thV, ws, L.imgV, L.vecV, st))) return rc; a.vecV = (const float*)(ws + L.vecV); }
+    const size_t smem = tc::tc_smem_bytes(h->tA.vec_floats, h->tV.vec_floats, h->tG.vec_floats);
+    DPB_CUDA(h, cudaFuncSetAttribute(tc::actor_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ev_begin(h, st);
+    tc::actor_tc_kernel<<<L.grid, tc::TC_THREADS, smem, st>>>(a);
+    ev_end(h, st);
+    h->launches++;
+    DPB_CUDA(h, cudaGetLastError());
+    if (out_loss) {
+        reduce_loss_kernel<float><<<1, 32, 0, st>>>(a.loss_part, L.grid, (float)(1.0 / (double)B_global), 0.f, (float*)out_loss);
+        h->launches++;
+    }
+    if (grad_A && (flags & DPB_FLAG_NEED_GRAD)) DPB_CUDA(h, cudaMemsetAsync(grad_A, 0, (size_t)h->nA.ftotal * sizeof(float), st));
+    DPB_CUDA(h, cudaGetLastError());
+    return DPB_OK;
+}
+
 extern "C" {
 
 int dpb_critic_step(dpb_handle* h, const void* theta_actor, const void* theta_V, const void* theta_G, const dpb_inputs* in,
@@ -339,6 +458,8 @@ int dpb_critic_step(dpb_handle* h, const void* theta_actor, const void* theta_V,
     if (!prop_only && (!theta_V || !in->x_bdry)) return fail(h, DPB_ERR_ARG, "dpb_critic_step: theta_V and x_bdry are required");
     if (!prop_only && h->cfg.td_type == DPB_TD1 && !theta_G) return fail(h, DPB_ERR_ARG, "dpb_critic_step: theta_G is NULL under TD1");
     cudaStream_t st = (cudaStream_t)stream;
+    if (h->cfg.impl == DPB_IMPL_TENSOR)
+        return critic_step_tc(h, theta_actor, theta_V, theta_G, in, B_local, path_offset, B_global, N, T, flags, out_loss, grad_V, grad_G, outs, workspace, st);
     if (h->cfg.dtype == DPB_F64)
         return critic_step_t<double>(h, theta_actor, theta_V, theta_G, in, B_local, path_offset, B_global, N, T, flags, out_loss, grad_V, grad_G, outs, workspace, st);
     return critic_step_t<float>(h, theta_actor, theta_V, theta_G, in, B_local, path_offset, B_global, N, T, flags, out_loss, grad_V, grad_G, outs, workspace, st);
@@ -352,6 +473,8 @@ int dpb_actor_step(dpb_handle* h, const void* theta_actor, const void* theta_V, 
     if (!(flags & DPB_FLAG_CHEAT_CONTROL) && !theta_actor) return fail(h, DPB_ERR_ARG, "dpb_actor_step: theta_actor is NULL");
     if (!(flags & DPB_FLAG_CHEAT_VALUE) && !theta_V) return fail(h, DPB_ERR_ARG, "dpb_actor_step: theta_V is NULL");
     cudaStream_t st = (cudaStream_t)stream;
+    if (h->cfg.impl == DPB_IMPL_TENSOR)
+        return actor_step_tc(h, theta_actor, theta_V, in, B_local, path_offset, B_global, N, T, flags, out_loss, grad_actor, outs, workspace, st);
     if (h->cfg.dtype == DPB_F64)
         return actor_step_t<double>(h, theta_actor, theta_V, in, B_local, path_offset, B_global, N, T, flags, out_loss, grad_actor, outs, workspace, st);
     return actor_step_t<float>(h, theta_actor, theta_V, in, B_local, path_offset, B_global, N, T, flags, out_loss, grad_actor, outs, workspace, st);

@@ -1,0 +1,302 @@
+// dpb_tc_nets.cuh -- DeepNN (reference solver.py:227-278) on the 5th-generation tensor cores.
+//
+// One CTA owns a tile of 128 paths; thread t of warps 0-3 ("path threads") owns path t = TMEM lane t;
+// lane 0 of warp 4 (the "control thread") streams the weights and issues every tcgen05.mma.
+//
+//   * Precision: FP32 emulated with bf16 pairs.  Every operand x is carried as hi = bf16(x) and
+//     lo = bf16(x - hi) and a product a*w is formed as ah*wh + ah*wl + al*wh with FP32 accumulation in
+//     tensor memory (error ~2^-16 relative per term; the dropped al*wl term is ~2^-18).
+//   * Activations never touch shared memory on the forward / dX products: the epilogue reads the FP32
+//     accumulator of layer l from TMEM (tcgen05.ld), applies the BatchNorm affine + y+relu(y), splits
+//     and writes the two bf16 planes back to TMEM (tcgen05.st), from where layer l+1 reads them as the
+//     A operand (tcgen05.mma with A in tensor memory).
+//   * Weights: the pack kernel turns the flat FP32 parameters into bf16 hi/lo operand images (layout in
+//     dpb_tc.cuh), cut into 16-wide contraction chunks of N16*64 bytes.  The control thread streams the
+//     chunks L2 -> shared memory through a ring of NSLOT slots with 1-D bulk copies (cp.async.bulk,
+//     completion on an mbarrier); a slot is released by the tcgen05.commit of the MMAs that read it.
+//     The chunk sequence of a phase is a cyclic schedule known in advance, so the stream runs ahead of
+//     the MMAs across layers, networks and time steps.
+//   * TMEM columns: [0,256) accumulator (N <= 256), [256,384) A hi plane, [384,512) A lo plane (K <= 256).
+#pragma once
+#include "dpb_nets.cuh"
+#include "dpb_tc.cuh"
+
+namespace dpb {
+namespace tc {
+
+constexpr int TC_PATHS = 128;
+constexpr int TC_THREADS = 160;                 // 4 path warps + 1 control warp
+constexpr int NSLOT = 12;
+constexpr int SLOT_BYTES = 256 * 64;            // one 16-wide contraction chunk of <= 256 rows, hi + lo planes
+constexpr uint32_t COL_ACC = 0, COL_AHI = 256, COL_ALO = 384;
+constexpr int MAXOPS = 40;
+
+__host__ __device__ inline int round16(int x) { return (x + 15) & ~15; }
+
+struct TcLayer {
+    int kl, nl;            // logical dims of linear layer l
+    int K16, N16;          // padded: K16 = round16(kl + 1) keeps one spare input feature (the constant 1 that
+                           // turns the bias column sums into one more row of the dW product), N16 = K16 of
+                           // the next layer, round16(out) for the last one
+    long long img_f;       // byte offset of the forward image  (rows N16, contraction K16): K16/16 chunks of N16*64 B
+    long long img_b;       // byte offset of the backward image (rows K16, contraction N16): N16/16 chunks of K16*64 B
+    int vec;               // float offset of gc[N16], bb[N16] in the vector block
+};
+
+struct TcNet {
+    int L, in, out, ekn_head, mctrl;
+    TcLayer ly[MAXLIN];
+    int vec_g0;            // g0c[K16_0], b0[K16_0]
+    int vec_floats;
+    long long img_bytes;
+    NetDev flat;           // flat parameter layout
+};
+
+inline void tcnet_init(TcNet& t, int in, const int* hid, int L, int out, int ekn_head, int mctrl) {
+    t.L = L; t.in = in; t.out = out; t.ekn_head = ekn_head; t.mctrl = mctrl;
+    netdev_init(t.flat, in, hid, L, out, ekn_head, mctrl);
+    long long img = 0;
+    int vec = 0;
+    int prev = in;
+    t.vec_g0 = vec; vec += 2 * round16(in + 1);
+    for (int l = 0; l <= L; ++l) {
+        TcLayer& y = t.ly[l];
+        y.kl = prev; y.nl = (l < L) ? hid[l] : out;
+        y.K16 = round16(y.kl + 1);
+        y.N16 = (l < L) ? round16(y.nl + 1) : round16(y.nl);
+        y.img_f = img; img += (long long)y.K16 * y.N16 * 4;          // hi + lo planes, 2 B each
+        y.img_b = img; img += (long long)y.K16 * y.N16 * 4;
+        y.vec = vec; vec += 2 * y.N16;
+        prev = y.nl;
+    }
+    t.img_bytes = (img + 255) & ~255LL;
+    t.vec_floats = (vec + 63) & ~63;
+}
+
+inline bool tcnet_supported(const TcNet& t) {
+    for (int l = 0; l <= t.L; ++l)
+        if (t.ly[l].K16 > 256 || t.ly[l].N16 > 256) return false;
+    return true;
+}
+
+// ------------------------------------------------------------------------------------------- pack
+// flat FP32 parameters -> bf16 hi/lo operand images + the FP32 vector block (gamma*c, beta, ...)
+__global__ void tc_pack_kernel(TcNet t, const float* __restrict__ th, unsigned char* __restrict__ img, float* __restrict__ vec, float c) {
+    const NetDev& nd = t.flat;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const long long t0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int K0 = t.ly[0].K16;
+    for (long long i = t0; i < K0; i += stride) {
+        vec[t.vec_g0 + i] = i < t.in ? th[nd.fg0 + i] * c : 0.f;
+        vec[t.vec_g0 + K0 + i] = i < t.in ? th[nd.fb0 + i] : 0.f;
+    }
+    for (int l = 0; l <= t.L; ++l) {
+        const TcLayer y = t.ly[l];
+        for (long long n = t0; n < y.N16; n += stride) {
+            float gc = n < y.nl ? th[nd.fg[l] + n] * c : 0.f;
+            float bb = n < y.nl ? th[nd.fb[l] + n] : 0.f;
+            if (l == t.L && n < y.nl) bb = th[nd.fbias + n] * gc + bb;
+            vec[y.vec + n] = gc;
+            vec[y.vec + y.N16 + n] = bb;
+        }
+        const long long tot = (long long)y.K16 * y.N16;
+        for (long long i = t0; i < tot; i += stride) {
+            const int k = (int)(i / y.N16), n = (int)(i - (long long)k * y.N16);
+            const bool in_rng = (k < y.kl && n < y.nl);
+            const float w = in_rng ? th[nd.fW[l] + (long long)k * y.nl + n] : 0.f;
+            __nv_bfloat16 hi, lo;
+            // forward image: rows n (N16), contraction k; chunk = k/16
+            split_bf16(w, hi, lo);
+            {
+                const long long cb = (long long)y.N16 * 64;
+                unsigned char* base = img + y.img_f + (k >> 4) * cb + (((k & 15) >> 3) * (y.N16 >> 3) + (n >> 3)) * 128 + (n & 7) * 16 + (k & 7) * 2;
+                *reinterpret_cast<__nv_bfloat16*>(base) = hi;
+                *reinterpret_cast<__nv_bfloat16*>(base + y.N16 * 32) = lo;
+            }
+            // backward image: rows k (K16), contraction n, value W[k][n] * gamma[n]*c; chunk = n/16
+            const float wg = in_rng ? w * (th[nd.fg[l] + n] * c) : 0.f;
+            split_bf16(wg, hi, lo);
+            {
+                const long long cb = (long long)y.K16 * 64;
+                unsigned char* base = img + y.img_b + (n >> 4) * cb + (((n & 15) >> 3) * (y.K16 >> 3) + (k >> 3)) * 128 + (k & 7) * 16 + (n & 7) * 2;
+                *reinterpret_cast<__nv_bfloat16*>(base) = hi;
+                *reinterpret_cast<__nv_bfloat16*>(base + y.K16 * 32) = lo;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------ control-thread side
+struct Sched {                       // cyclic chunk schedule of the current phase (shared memory)
+    const unsigned char* ptr[MAXOPS];
+    int nch[MAXOPS];
+    int cb[MAXOPS];
+    int nops;
+};
+
+struct Ctrl {
+    unsigned char* ring;
+    uint64_t *full, *empty, *acc_full, *a_ready;
+    Sched* sch;
+    int pf_op, pf_ch;
+    uint32_t n_loaded, n_consumed, op_count, tmem;
+};
+
+__device__ __forceinline__ void ctrl_prefetch(Ctrl& c) {
+    if (c.sch->nops == 0) return;
+    while (c.n_loaded - c.n_consumed < (uint32_t)NSLOT) {
+        const uint32_t slot = c.n_loaded % NSLOT, use = c.n_loaded / NSLOT;
+        if (use > 0) mbar_wait(&c.empty[slot], (use - 1) & 1);
+        const uint32_t bytes = (uint32_t)c.sch->cb[c.pf_op];
+        mbar_arrive_expect_tx(&c.full[slot], bytes);
+        bulk_g2s(c.ring + (size_t)slot * SLOT_BYTES, c.sch->ptr[c.pf_op] + (size_t)c.pf_ch * bytes, bytes, &c.full[slot]);
+        if (++c.pf_ch == c.sch->nch[c.pf_op]) {
+            c.pf_ch = 0;
+            if (++c.pf_op == c.sch->nops) c.pf_op = 0;
+        }
+        ++c.n_loaded;
+    }
+}
+
+// drop every chunk that was streamed ahead but will not be used (end of a phase / dead tile)
+__device__ __forceinline__ void ctrl_flush(Ctrl& c) {
+    while (c.n_consumed != c.n_loaded) {
+        const uint32_t slot = c.n_consumed % NSLOT, use = c.n_consumed / NSLOT;
+        mbar_wait(&c.full[slot], use & 1);
+        mbar_arrive(&c.empty[slot]);
+        ++c.n_consumed;
+    }
+    c.pf_op = 0; c.pf_ch = 0;
+    c.sch->nops = 0;
+}
+
+__device__ __forceinline__ void sched_add(Sched* s, const unsigned char* p, int nch, int cb) {
+    s->ptr[s->nops] = p; s->nch[s->nops] = nch; s->cb[s->nops] = cb; ++s->nops;
+}
+__device__ __forceinline__ void sched_add_fwd(Sched* s, const TcNet& t, const unsigned char* img, int upto /*layers 0..upto*/) {
+    for (int l = 0; l <= upto; ++l) sched_add(s, img + t.ly[l].img_f, t.ly[l].K16 / 16, t.ly[l].N16 * 64);
+}
+
+// D[acc] = A(planes in TMEM) x B(streamed image with R rows): nchunks contraction chunks, 3 split products
+__device__ __forceinline__ void ctrl_gemm_ts(Ctrl& c, int nchunks, int R) {
+    const uint32_t idesc = idesc_bf16(128, R, 0, 0);
+    ctrl_prefetch(c);
+    mbar_wait(c.a_ready, c.op_count & 1);
+    tc_fence_after();
+    for (int s = 0; s < nchunks; ++s) {
+        const uint32_t slot = c.n_consumed % NSLOT, use = c.n_consumed / NSLOT;
+        mbar_wait(&c.full[slot], use & 1);
+        const uint32_t sb = smem_u32(c.ring + (size_t)slot * SLOT_BYTES);
+        const uint64_t bhi = smem_desc(sb, (R >> 3) * 128, 128), blo = smem_desc(sb + R * 32, (R >> 3) * 128, 128);
+        const uint32_t ahi = c.tmem + COL_AHI + s * 8, alo = c.tmem + COL_ALO + s * 8;
+        mma_ts(c.tmem + COL_ACC, ahi, bhi, idesc, s > 0);
+        mma_ts(c.tmem + COL_ACC, ahi, blo, idesc, 1);
+        mma_ts(c.tmem + COL_ACC, alo, bhi, idesc, 1);
+        tc_commit(&c.empty[slot]);
+        ++c.n_consumed;
+        ctrl_prefetch(c);
+    }
+    tc_commit(c.acc_full);
+    ++c.op_count;
+}
+
+__device__ __forceinline__ void ctrl_net_forward(Ctrl& c, const TcNet& t, int upto) {
+    for (int l = 0; l <= upto; ++l) ctrl_gemm_ts(c, t.ly[l].K16 / 16, t.ly[l].N16);
+}
+
+// ---------------------------------------------------------------------------------- path-thread side
+struct PathCtx {
+    uint32_t tl;                   // TMEM address of this thread's lane (column 0)
+    uint64_t *acc_full, *a_ready;
+    uint32_t op_count;
+};
+
+__device__ __forceinline__ void path_publish(PathCtx& p) {   // A planes written and accumulator drained
+    tmem_st_wait();
+    tc_fence_before();
+    mbar_arrive(p.a_ready);
+}
+__device__ __forceinline__ void path_wait_acc(PathCtx& p) {
+    mbar_wait(p.acc_full, p.op_count & 1);
+    tc_fence_after();
+    ++p.op_count;
+}
+
+// features 16c .. 16c+15 of this thread's row -> hi / lo planes
+__device__ __forceinline__ void put16(uint32_t tl, int c, const float* v) {
+    uint32_t h[8], l[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        __nv_bfloat16 h0, l0, h1, l1;
+        split_bf16(v[2 * j], h0, l0);
+        split_bf16(v[2 * j + 1], h1, l1);
+        h[j] = pack2(h0, h1);
+        l[j] = pack2(l0, l1);
+    }
+    tmem_st8(tl + COL_AHI + c * 8, h);
+    tmem_st8(tl + COL_ALO + c * 8, l);
+}
+
+// y0 = x * g0c + b0 (solver.py:265) -> planes; x: this thread's point (in values)
+__device__ __forceinline__ void path_write_y0(PathCtx& p, const TcNet& t, const float* vec, const float* x) {
+    const int K0 = t.ly[0].K16;
+    const float* g0c = vec + t.vec_g0;
+    const float* b0 = g0c + K0;
+    for (int c = 0; c < K0 / 16; ++c) {
+        float v[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const int k = 16 * c + j;
+            v[j] = (k < t.in) ? x[k] * g0c[k] + b0[k] : 0.f;
+        }
+        put16(p.tl, c, v);
+    }
+    path_publish(p);
+}
+
+// hidden layer epilogue: a = z + relu(z), z = acc * gc + bb (solver.py:267-269) -> planes
+__device__ __forceinline__ void path_epi_hidden(PathCtx& p, const float* gcbb, int N16) {
+    path_wait_acc(p);
+    const float* gc = gcbb;
+    const float* bb = gcbb + N16;
+    for (int c = 0; c < N16 / 16; ++c) {
+        uint32_t r[16];
+        tmem_ld16(p.tl + COL_ACC + 16 * c, r);
+        tmem_ld_wait();
+        float v[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const float z = __uint_as_float(r[j]) * gc[16 * c + j] + bb[16 * c + j];
+            v[j] = z + fmaxf(z, 0.f);
+        }
+        put16(p.tl, c, v);
+    }
+    path_publish(p);
+}
+
+// last layer: out[n] = acc * gc + bb (solver.py:270-271), n < nl
+__device__ __forceinline__ void path_epi_last(PathCtx& p, const float* gcbb, int N16, int nl, float* out) {
+    path_wait_acc(p);
+    const float* gc = gcbb;
+    const float* bb = gcbb + N16;
+    for (int c = 0; c < N16 / 16; ++c) {
+        uint32_t r[16];
+        tmem_ld16(p.tl + COL_ACC + 16 * c, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const int n = 16 * c + j;
+            if (n < nl) out[n] = __uint_as_float(r[j]) * gc[n] + bb[n];
+        }
+    }
+}
+
+// whole network, forward only: x -> raw output (before the ekn head)
+__device__ __forceinline__ void path_net_forward(PathCtx& p, const TcNet& t, const float* vec, const float* x, float* out) {
+    path_write_y0(p, t, vec, x);
+    for (int l = 0; l < t.L; ++l) path_epi_hidden(p, vec + t.ly[l].vec, t.ly[l].N16);
+    path_epi_last(p, vec + t.ly[t.L].vec, t.ly[t.L].N16, t.ly[t.L].nl, out);
+}
+
+}  // namespace tc
+}  // namespace dpb

@@ -33,3 +33,89 @@ def test_tcgen05_product_forms(K):
     assert err[0] < tol, f"SS K-major product wrong: {err}"
     assert err[1] < tol, f"TS (A from TMEM) product wrong: {err}"
     assert err[2] < tol, f"SS MN-major product wrong: {err}"
+
+
+# ------------------------------------------------------------------------------------------------
+# tensor path (impl="tensor": bf16x3 products on tcgen05, FP32 accumulation) vs golden / exact path
+import glob
+import json
+import os
+
+from deeppde_actorcritic_b200.engine import Engine
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+CASES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "*.npz")) if "samplers" not in p)
+VTOL = dict(rtol=3e-4, atol=3e-4)          # stated tolerance of the tensor path: values
+
+
+def _load(name):
+    z = np.load(os.path.join(GOLDEN, name + ".npz"))
+    return z, json.loads(str(z["config_json"]))
+
+
+def _npy(t):
+    return t.detach().cpu().double().numpy()
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_tensor_forward_vs_golden(name):
+    z, cfg = _load(name)
+    eng = Engine(cfg["eqn_config"], cfg["net_config"], cfg["train_config"], dtype="float32", impl="tensor")
+    x0, dw, xb = (eng.tensor(z[k]) for k in ("x0", "dw", "xb"))
+    thA, thV, thG = (eng.tensor(z[k]) for k in ("theta_actor", "theta_critic", "theta_critic_grad"))
+    ec = cfg["eqn_config"]
+    N, T = ec["num_time_interval_critic"], ec["total_time_critic"]
+    r = eng.critic_step(thA, None, None, x0, dw, None, N, T, propagate_only=True, want=("x_smp", "dt", "coef", "exit_index"))
+    same = (_npy(r["coef"]) == z["prop_nn_coef"]).all(1)
+    assert same.mean() >= 0.95
+    np.testing.assert_allclose(_npy(r["x_smp"])[same], z["prop_nn_x"][same], rtol=2e-3, atol=2e-3)
+    np.testing.assert_allclose(_npy(r["dt"])[same], z["prop_nn_dt"][same], rtol=5e-3, atol=1e-7)
+    for cheat in (False, True):
+        tag = "cheat" if cheat else "nn"
+        r = eng.critic_step(thA, thV, thG, x0, dw, xb, N, T, cheat_control=cheat, want=("delta", "delta_bdry", "coef"))
+        same = (_npy(r["coef"]) == z[f"prop_{tag}_coef"]).all(1)
+        np.testing.assert_allclose(_npy(r["delta"])[same], z[f"critic_{tag}_delta"][same], **VTOL)
+        np.testing.assert_allclose(_npy(r["delta_bdry"]), z[f"critic_{tag}_delta_bdry"], **VTOL)
+        if same.all():
+            np.testing.assert_allclose(_npy(r["loss"]).sum(), float(z[f"critic_{tag}_loss"]), rtol=1e-3)
+    for cheat_v in (False, True):
+        tag = "cheatV" if cheat_v else "nn"
+        r = eng.actor_step(thA, thV, x0, dw, N, T, cheat_value=cheat_v, want=("delta", "coef"))
+        same = (_npy(r["coef"]) == z["prop_nn_coef"]).all(1)
+        np.testing.assert_allclose(_npy(r["delta"])[same], z[f"actor_{tag}_y"][same], **VTOL)
+        if same.all():
+            np.testing.assert_allclose(float(_npy(r["loss"])[0]), float(z[f"actor_{tag}_loss"]), rtol=1e-3, atol=1e-5)
+
+
+def test_tensor_forward_vs_exact_d20_3x200():
+    """lqr_var d=20, nets 3x200, several tiles with a ragged tail, in-kernel Philox increments:
+    tensor path against the exact FP32 path on identical inputs."""
+    e = {"eqn_name": "LQR_var", "discount": 1.0, "q": 1.0, "beta": 1.0, "epsilon": 0.05, "R": 1.0, "dim": 20, "control_dim": 20,
+         "total_time_critic": 0.2, "total_time_actor": 0.2, "num_time_interval_critic": 25, "num_time_interval_actor": 25}
+    net = {"num_hiddens_actor": [200, 200, 200], "num_hiddens_critic": [200, 200, 200]}
+    tr = {"scheme": "adaptive", "TD_type": "TD1"}
+    ex = Engine(e, net, tr, dtype="float32", impl="exact")
+    tn = Engine(e, net, tr, dtype="float32", impl="tensor")
+    from oracle import ref_solver as RS
+    rng = np.random.RandomState(12)
+    cfg = {"eqn_config": e, "net_config": net, "train_config": tr}
+    th = {}
+    for k in ("actor", "critic", "critic_grad"):
+        i, h, o, _ = RS.net_dims(cfg, k)
+        th[k] = ex.tensor(RS.init_params(i, h, o, rng))
+    B, N, T = 1000, 25, 0.2
+    x0, xb = ex.sample_x(5, 1, 0, B)
+    kw = dict(dw_mode=1, seed=5, stream_id=3)
+    a = ex.critic_step(th["actor"], th["critic"], th["critic_grad"], x0, None, xb, N, T, want=("delta", "delta_bdry", "coef", "exit_index"), **kw)
+    b = tn.critic_step(th["actor"], th["critic"], th["critic_grad"], x0, None, xb, N, T, want=("delta", "delta_bdry", "coef", "exit_index"), **kw)
+    same = (a["coef"] == b["coef"]).all(1).cpu().numpy()
+    print("tensor vs exact: identical exit pattern on", same.mean(), "of paths; max |d delta| =",
+          float((a["delta"] - b["delta"]).abs().cpu().numpy()[same].max()))
+    assert same.mean() > 0.99
+    np.testing.assert_allclose(_npy(b["delta"])[same], _npy(a["delta"])[same], **VTOL)
+    np.testing.assert_allclose(_npy(b["delta_bdry"]), _npy(a["delta_bdry"]), **VTOL)
+    ya = ex.actor_step(th["actor"], th["critic"], x0, None, N, T, want=("delta", "coef"), **kw)
+    yb = tn.actor_step(th["actor"], th["critic"], x0, None, N, T, want=("delta", "coef"), **kw)
+    same = (ya["coef"] == yb["coef"]).all(1).cpu().numpy()
+    np.testing.assert_allclose(_npy(yb["delta"])[same], _npy(ya["delta"])[same], **VTOL)
