@@ -18,6 +18,8 @@ struct dpb_handle {
     dpb_config cfg;
     NetDev nA, nV, nG;
     tc::TcNet tA, tV, tG;
+    tc::TcSlab sA, sV, sG;
+    int tc_maxw16;                  // widest padded layer extent of the three networks
     int num_sms;
     int max_smem;
     int sr, hrows, nhb;
@@ -60,8 +62,8 @@ static const double BN_C = 1.0 / sqrt(1.0 + 1e-6);       // solver.py:242 (epsil
 struct Layout {
     int grid;
     size_t pkA, pkV, pkG, loss_part, loss_out, scratch, slabs, raw, total;
-    size_t imgA, imgV, imgG, vecA, vecV, vecG;      // tensor path: operand images + vector blocks
-    long long scratch_per_cta;
+    size_t imgA, imgV, imgG, vecA, vecV, vecG, copies;      // tensor path: operand images, vector blocks, activation copies
+    long long scratch_per_cta, copies_per_cta;
 };
 
 static Layout make_layout(const dpb_handle* h, long long B_local, int N) {
@@ -88,7 +90,15 @@ static Layout make_layout(const dpb_handle* h, long long B_local, int N) {
     L.loss_out = o; o += 256;
     L.scratch_per_cta = (long long)N * (2 * h->sr + A_NSCAL) * P;
     L.scratch = o; o += a256((size_t)L.grid * L.scratch_per_cta * es);
-    const long long gc = h->nV.gtotal + h->nG.gtotal, ga = h->nA.gtotal;
+    L.copies = 0; L.copies_per_cta = 0;
+    if (tensor) {
+        long long cb = tc::tc_copy_bytes(h->tA);
+        if (tc::tc_copy_bytes(h->tV) > cb) cb = tc::tc_copy_bytes(h->tV);
+        if (tc::tc_copy_bytes(h->tG) > cb) cb = tc::tc_copy_bytes(h->tG);
+        L.copies_per_cta = (long long)a256((size_t)cb);
+        L.copies = o; o += a256((size_t)L.grid * L.copies_per_cta);
+    }
+    const long long gc = tensor ? h->sV.gtotal + h->sG.gtotal : h->nV.gtotal + h->nG.gtotal, ga = tensor ? h->sA.gtotal : h->nA.gtotal;
     const long long gmax = gc > ga ? gc : ga;
     L.slabs = o; o += a256((size_t)L.grid * gmax * es);
     L.raw = o; o += a256((size_t)gmax * es);
@@ -134,6 +144,13 @@ int dpb_create(dpb_handle** out, const dpb_config* cfg) {
     tc::tcnet_init(h->tA, c.dim, c.hidden_actor, c.n_hidden_actor, ekn ? c.control_dim + 1 : c.control_dim, ekn, c.control_dim);
     tc::tcnet_init(h->tV, c.dim, c.hidden_critic, c.n_hidden_critic, 1, 0, 0);
     tc::tcnet_init(h->tG, c.dim, c.hidden_critic, c.n_hidden_critic, c.dim, 0, 0);
+    tc::tcslab_init(h->sA, h->tA); tc::tcslab_init(h->sV, h->tV); tc::tcslab_init(h->sG, h->tG);
+    h->tc_maxw16 = 16;
+    for (const tc::TcNet* t : {&h->tA, &h->tV, &h->tG})
+        for (int l = 0; l <= t->L; ++l) {
+            if (t->ly[l].K16 > h->tc_maxw16) h->tc_maxw16 = t->ly[l].K16;
+            if (t->ly[l].N16 > h->tc_maxw16) h->tc_maxw16 = t->ly[l].N16;
+        }
     if (c.impl != DPB_IMPL_EXACT && c.impl != DPB_IMPL_TENSOR) { delete h; return fail(nullptr, DPB_ERR_ARG, "impl must be DPB_IMPL_EXACT or DPB_IMPL_TENSOR"); }
     if (c.impl == DPB_IMPL_TENSOR) {
         if (c.dtype != DPB_F32) { delete h; return fail(nullptr, DPB_ERR_ARG, "the tensor path computes in float32 (bf16x3 products, FP32 accumulation): dtype must be DPB_F32"); }
@@ -361,11 +378,24 @@ static int tc_pack(dpb_handle* h, const tc::TcNet& t, const void* theta, char* w
     return DPB_OK;
 }
 
+// ring geometry for a launch: slots of `slot_bytes` (largest chunk of the images used) in what is left of 227 KB
+static int tc_ring(dpb_handle* h, tc::TcArgs& a, bool grads) {
+    a.actdz_bytes = grads ? tc::TC_PATHS * h->tc_maxw16 * 2 : 0;
+    a.slot_bytes = h->tc_maxw16 * 64;
+    const size_t fixed = tc::tc_smem_fixed(h->tA.vec_floats, h->tV.vec_floats, h->tG.vec_floats, a.actdz_bytes);
+    const size_t avail = (size_t)227 * 1024;
+    if (fixed + 4 * (size_t)a.slot_bytes > avail) return fail(h, DPB_ERR_ARG, "tensor path: networks too wide for the shared-memory operand images");
+    size_t ns = (avail - fixed) / a.slot_bytes;
+    a.nslot = (int)(ns > tc::MAX_NSLOT ? tc::MAX_NSLOT : ns);
+    return DPB_OK;
+}
+
 static void tc_fill(dpb_handle* h, tc::TcArgs& a, const Layout& L, char* ws, const dpb_inputs* in, int64_t B_local, int64_t path_offset,
                     int64_t B_global, int32_t N, double T, uint32_t flags, const dpb_path_outputs* outs) {
     memset(&a, 0, sizeof(a));
     fill_eqn(h->cfg, N, T, a.eq);
     a.nA = h->tA; a.nV = h->tV; a.nG = h->tG;
+    a.gA = h->sA; a.gV = h->sV; a.gG = h->sG;
     a.imgA = (const unsigned char*)(ws + L.imgA); a.imgV = (const unsigned char*)(ws + L.imgV); a.imgG = (const unsigned char*)(ws + L.imgG);
     a.x0 = (const float*)in->x0; a.dw = (const float*)in->dw; a.xb = (const float*)in->x_bdry;
     a.dw_mode = in->dw_mode; a.seed = in->seed; a.stream = in->stream;
@@ -375,11 +405,24 @@ static void tc_fill(dpb_handle* h, tc::TcArgs& a, const Layout& L, char* ws, con
     a.loss_part = (float*)(ws + L.loss_part);
     a.scratch = (float*)(ws + L.scratch);
     a.scratch_per_cta = L.scratch_per_cta;
+    a.copies = (unsigned char*)(ws + L.copies);
+    a.copies_per_cta = L.copies_per_cta;
     a.sr = h->sr;
     if (outs) {
         a.o_x = (float*)outs->x_smp; a.o_dt = (float*)outs->dt; a.o_coef = (float*)outs->coef;
         a.o_delta = (float*)outs->delta; a.o_delta_b = (float*)outs->delta_bdry; a.o_exit = outs->exit_index;
     }
+}
+
+static int tc_finalize(dpb_handle* h, const tc::TcNet& t, const tc::TcSlab& g, const void* theta, const float* slabs, int nslab, float* raw,
+                       void* grad, cudaStream_t st) {
+    int blocks = (int)((g.gtotal + 255) / 256);
+    if (blocks > 592) blocks = 592;
+    reduce_slabs_kernel<float><<<blocks, 256, 0, st>>>(slabs, nslab, g.gtotal, raw);
+    tc::tc_finalize_grad_kernel<<<blocks, 256, 0, st>>>(t, g, (const float*)theta, raw, (float*)grad, (float)BN_C);
+    h->launches += 2;
+    DPB_CUDA(h, cudaGetLastError());
+    return DPB_OK;
 }
 
 static int critic_step_tc(dpb_handle* h, const void* thA, const void* thV, const void* thG, const dpb_inputs* in, int64_t B_local,
@@ -392,15 +435,20 @@ static int critic_step_tc(dpb_handle* h, const void* thA, const void* thV, const
     const bool cheat = flags & DPB_FLAG_CHEAT_CONTROL, prop_only = flags & DPB_FLAG_PROPAGATE_ONLY;
     const bool need_grad = (flags & DPB_FLAG_NEED_GRAD) && !prop_only;
     const bool td1 = h->cfg.td_type == DPB_TD1;
-    if (need_grad) return fail(h, DPB_ERR_ARG, "tensor path: gradients not implemented yet");
     int rc;
+    if ((rc = tc_ring(h, a, need_grad))) return rc;
     if (!cheat) { if ((rc = tc_pack(h, h->tA, thA, ws, L.imgA, L.vecA, st))) return rc; a.vecA = (const float*)(ws + L.vecA); }
     if (!prop_only) {
         if ((rc = tc_pack(h, h->tV, thV, ws, L.imgV, L.vecV, st))) return rc;
         a.vecV = (const float*)(ws + L.vecV);
         if (td1) { if ((rc = tc_pack(h, h->tG, thG, ws, L.imgG, L.vecG, st))) return rc; a.vecG = (const float*)(ws + L.vecG); }
     }
-    const size_t smem = tc::tc_smem_bytes(h->tA.vec_floats, h->tV.vec_floats, h->tG.vec_floats);
+    if (need_grad) {
+        a.slabV = (float*)(ws + L.slabs);
+        a.slabG = a.slabV + (size_t)L.grid * h->sV.gtotal;
+        DPB_CUDA(h, cudaMemsetAsync(ws + L.slabs, 0, (size_t)L.grid * (h->sV.gtotal + h->sG.gtotal) * sizeof(float), st));
+    }
+    const size_t smem = tc::tc_smem_bytes(h->tA.vec_floats, h->tV.vec_floats, h->tG.vec_floats, a.actdz_bytes, a.nslot, a.slot_bytes);
     DPB_CUDA(h, cudaFuncSetAttribute(tc::critic_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     ev_begin(h, st);
     tc::critic_tc_kernel<<<L.grid, tc::TC_THREADS, smem, st>>>(a);
@@ -412,7 +460,14 @@ static int critic_step_tc(dpb_handle* h, const void* thA, const void* thV, const
         reduce_loss_kernel<float><<<1, 32, 0, st>>>(a.loss_part, L.grid, s, s, (float*)out_loss);
         h->launches++;
     }
-    (void)grad_V; (void)grad_G;
+    if (need_grad) {
+        float* raw = (float*)(ws + L.raw);
+        if (grad_V) { if ((rc = tc_finalize(h, h->tV, h->sV, thV, a.slabV, L.grid, raw, grad_V, st))) return rc; }
+        if (grad_G) {
+            if (td1) { if ((rc = tc_finalize(h, h->tG, h->sG, thG, a.slabG, L.grid, raw + h->sV.gtotal, grad_G, st))) return rc; }
+            else DPB_CUDA(h, cudaMemsetAsync(grad_G, 0, (size_t)h->nG.ftotal * sizeof(float), st));
+        }
+    }
     DPB_CUDA(h, cudaGetLastError());
     return DPB_OK;
 }
@@ -426,11 +481,15 @@ static int actor_step_tc(dpb_handle* h, const void* thA, const void* thV, const 
     tc_fill(h, a, L, ws, in, B_local, path_offset, B_global, N, T, flags, outs);
     const bool cheat = flags & DPB_FLAG_CHEAT_CONTROL, cheat_v = flags & DPB_FLAG_CHEAT_VALUE;
     const bool need_grad = (flags & DPB_FLAG_NEED_GRAD) && !cheat;
-    if (need_grad) return fail(h, DPB_ERR_ARG, "tensor path: gradients not implemented yet");
     int rc;
+    if ((rc = tc_ring(h, a, need_grad))) return rc;
     if (!cheat) { if ((rc = tc_pack(h, h->tA, thA, ws, L.imgA, L.vecA, st))) return rc; a.vecA = (const float*)(ws + L.vecA); }
     if (!cheat_v) { if ((rc = tc_pack(h, h->tV, thV, ws, L.imgV, L.vecV, st))) return rc; a.vecV = (const float*)(ws + L.vecV); }
-    const size_t smem = tc::tc_smem_bytes(h->tA.vec_floats, h->tV.vec_floats, h->tG.vec_floats);
+    if (need_grad) {
+        a.slabA = (float*)(ws + L.slabs);
+        DPB_CUDA(h, cudaMemsetAsync(ws + L.slabs, 0, (size_t)L.grid * h->sA.gtotal * sizeof(float), st));
+    }
+    const size_t smem = tc::tc_smem_bytes(h->tA.vec_floats, h->tV.vec_floats, h->tG.vec_floats, a.actdz_bytes, a.nslot, a.slot_bytes);
     DPB_CUDA(h, cudaFuncSetAttribute(tc::actor_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     ev_begin(h, st);
     tc::actor_tc_kernel<<<L.grid, tc::TC_THREADS, smem, st>>>(a);
@@ -441,7 +500,10 @@ static int actor_step_tc(dpb_handle* h, const void* thA, const void* thV, const 
         reduce_loss_kernel<float><<<1, 32, 0, st>>>(a.loss_part, L.grid, (float)(1.0 / (double)B_global), 0.f, (float*)out_loss);
         h->launches++;
     }
-    if (grad_A && (flags & DPB_FLAG_NEED_GRAD)) DPB_CUDA(h, cudaMemsetAsync(grad_A, 0, (size_t)h->nA.ftotal * sizeof(float), st));
+    if (grad_A) {
+        if (need_grad) { if ((rc = tc_finalize(h, h->tA, h->sA, thA, a.slabA, L.grid, (float*)(ws + L.raw), grad_A, st))) return rc; }
+        else if (flags & DPB_FLAG_NEED_GRAD) DPB_CUDA(h, cudaMemsetAsync(grad_A, 0, (size_t)h->nA.ftotal * sizeof(float), st));
+    }
     DPB_CUDA(h, cudaGetLastError());
     return DPB_OK;
 }

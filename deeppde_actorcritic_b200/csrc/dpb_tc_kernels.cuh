@@ -21,37 +21,50 @@ struct TcArgs {
     int N;
     unsigned flags;
     float* loss_part;               // [grid][2]
-    float *slabV, *slabG, *slabA;   // per-CTA raw-gradient slabs
-    float* scratch;
+    float *slabV, *slabG, *slabA;   // per-CTA raw-gradient slabs (layout TcSlab)
+    TcSlab gA, gV, gG;
+    float* scratch;                 // per-CTA trajectory scratch (floats)
     long long scratch_per_cta;
+    unsigned char* copies;          // per-CTA activation-copy scratch (bytes)
+    long long copies_per_cta;
     int sr;
+    int nslot, slot_bytes, actdz_bytes;   // ring geometry; bytes of each of the ACT / DZ images (0: no gradients)
     float *o_x, *o_dt, *o_coef, *o_delta, *o_delta_b;
     int* o_exit;
 };
 
 struct TcSmem {
+    unsigned char *act, *dz;
     unsigned char* ring;
     float *vecA, *vecV, *vecG;
-    uint64_t *full, *empty, *acc_full, *a_ready;
+    uint64_t *full, *empty, *acc_full, *a_ready, *act_full;
     uint32_t* tslot;
     Sched* sch;
     float* red;
 };
 
-__host__ __device__ inline size_t tc_smem_bytes(int vfA, int vfV, int vfG) {
-    return (size_t)NSLOT * SLOT_BYTES + (size_t)(vfA + vfV + vfG) * 4 + (2 * NSLOT + 2) * 8 + 64 + sizeof(Sched) + 64 + 1024;
+// everything except the ring
+__host__ __device__ inline size_t tc_smem_fixed(int vfA, int vfV, int vfG, int actdz_bytes) {
+    return 2 * (size_t)actdz_bytes + (size_t)(vfA + vfV + vfG) * 4 + (2 * MAX_NSLOT + 3) * 8 + 64 + sizeof(Sched) + 64 + 1024;
+}
+__host__ __device__ inline size_t tc_smem_bytes(int vfA, int vfV, int vfG, int actdz_bytes, int nslot, int slot_bytes) {
+    return tc_smem_fixed(vfA, vfV, vfG, actdz_bytes) + (size_t)nslot * slot_bytes;
 }
 
-__device__ __forceinline__ void tc_carve(TcSmem& s, unsigned char* base, int vfA, int vfV, int vfG) {
+__device__ __forceinline__ void tc_carve(TcSmem& s, unsigned char* base, const TcArgs& a) {
+    const int vfA = a.nA.vec_floats, vfV = a.nV.vec_floats, vfG = a.nG.vec_floats;
     unsigned char* p = reinterpret_cast<unsigned char*>(((uintptr_t)base + 1023) & ~(uintptr_t)1023);
-    s.ring = p; p += (size_t)NSLOT * SLOT_BYTES;
+    s.act = p; p += a.actdz_bytes;
+    s.dz = p; p += a.actdz_bytes;
+    s.ring = p; p += (size_t)a.nslot * a.slot_bytes;
     s.vecA = reinterpret_cast<float*>(p); p += (size_t)vfA * 4;
     s.vecV = reinterpret_cast<float*>(p); p += (size_t)vfV * 4;
     s.vecG = reinterpret_cast<float*>(p); p += (size_t)vfG * 4;
-    s.full = reinterpret_cast<uint64_t*>(p); p += NSLOT * 8;
-    s.empty = reinterpret_cast<uint64_t*>(p); p += NSLOT * 8;
+    s.full = reinterpret_cast<uint64_t*>(p); p += MAX_NSLOT * 8;
+    s.empty = reinterpret_cast<uint64_t*>(p); p += MAX_NSLOT * 8;
     s.acc_full = reinterpret_cast<uint64_t*>(p); p += 8;
     s.a_ready = reinterpret_cast<uint64_t*>(p); p += 8;
+    s.act_full = reinterpret_cast<uint64_t*>(p); p += 8;
     s.tslot = reinterpret_cast<uint32_t*>(p); p += 64;
     s.sch = reinterpret_cast<Sched*>(p); p += sizeof(Sched);
     s.red = reinterpret_cast<float*>(((uintptr_t)p + 15) & ~(uintptr_t)15);
@@ -63,14 +76,17 @@ __device__ __forceinline__ uint32_t tc_setup(TcSmem& s, const TcArgs& a) {
     for (int i = tid; i < a.nA.vec_floats; i += TC_THREADS) s.vecA[i] = a.vecA ? a.vecA[i] : 0.f;
     for (int i = tid; i < a.nV.vec_floats; i += TC_THREADS) s.vecV[i] = a.vecV ? a.vecV[i] : 0.f;
     for (int i = tid; i < a.nG.vec_floats; i += TC_THREADS) s.vecG[i] = a.vecG ? a.vecG[i] : 0.f;
+    for (int i = tid; i < 2 * a.actdz_bytes / 4; i += TC_THREADS) reinterpret_cast<uint32_t*>(s.act)[i] = 0u;
     if (tid == 0) {
-        for (int i = 0; i < NSLOT; ++i) { mbar_init(&s.full[i], 1); mbar_init(&s.empty[i], 1); }
+        for (int i = 0; i < MAX_NSLOT; ++i) { mbar_init(&s.full[i], 1); mbar_init(&s.empty[i], 1); }
         mbar_init(s.acc_full, 1);
         mbar_init(s.a_ready, TC_PATHS);
+        mbar_init(s.act_full, 1);
         s.sch->nops = 0;
         fence_barrier_init();
     }
     if (warp == 4) tmem_alloc(s.tslot, 512);
+    fence_proxy_async();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -123,34 +139,69 @@ __device__ __forceinline__ void path_dw(const TcArgs& a, long long gpath_local, 
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// role contexts shared by both kernels
+struct Roles {
+    Ctrl C;
+    PathCtx P;
+    bool is_path, is_ctrl;
+    int row;
+};
+__device__ __forceinline__ void roles_init(Roles& r, const TcSmem& S, const TcArgs& a, uint32_t tmem) {
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    r.is_path = warp < 4;
+    r.is_ctrl = (warp == 4 && lane == 0);
+    r.row = tid & 127;
+    Ctrl& C = r.C;
+    C.ring = S.ring; C.full = S.full; C.empty = S.empty; C.acc_full = S.acc_full; C.a_ready = S.a_ready; C.sch = S.sch;
+    C.pf_op = 0; C.pf_ch = 0; C.n_loaded = 0; C.n_consumed = 0; C.op_count = 0; C.tmem = tmem;
+    C.act_full = S.act_full; C.act_count = 0; C.nslot = a.nslot; C.slot_bytes = a.slot_bytes; C.act = S.act; C.dz = S.dz;
+    r.P.tl = tmem + ((uint32_t)(warp * 32) << 16);
+    r.P.acc_full = S.acc_full; r.P.a_ready = S.a_ready; r.P.op_count = 0;
+}
+
+// sum over the 128 path threads of per-thread accumulators acc[0..n) -> atomicAdd into dst (kernel end)
+__device__ __forceinline__ void reduce_rows_to(float* dst, const float* acc, int n, bool is_path) {
+    for (int k = 0; k < n; ++k) {
+        float v = is_path ? acc[k] : 0.f;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (is_path && (threadIdx.x & 31) == 0) atomicAdd(dst + k, v);
+    }
+}
+
 // ================================================================================== critic (tensor)
 __global__ void __launch_bounds__(TC_THREADS, 1) critic_tc_kernel(const TcArgs a) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     TcSmem S;
-    tc_carve(S, smem_raw, a.nA.vec_floats, a.nV.vec_floats, a.nG.vec_floats);
+    tc_carve(S, smem_raw, a);
     const uint32_t tmem = tc_setup(S, a);
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const bool is_path = warp < 4;
-    const bool is_ctrl = (warp == 4 && lane == 0);
+    Roles R;
+    roles_init(R, S, a, tmem);
+    Ctrl& C = R.C;
+    PathCtx& P = R.P;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const bool is_path = R.is_path, is_ctrl = R.is_ctrl;
+    const int row = R.row;
     const Eq<float> E(a.eq);
-    const int d = E.d, N = a.N;
+    const int d = E.d, N = a.N, sr = a.sr;
     const bool cheat = a.flags & F_CHEAT_CONTROL, prop_only = a.flags & F_PROPAGATE_ONLY;
+    const bool need_grad = (a.flags & F_NEED_GRAD) && !prop_only;
     const bool td1 = (E.td == 1) && !prop_only;
     const float scale = 100.f * a.invB;
     const float fill = 0.5f * E.R / sqrtf((float)d);
-
-    Ctrl C;
-    C.ring = S.ring; C.full = S.full; C.empty = S.empty; C.acc_full = S.acc_full; C.a_ready = S.a_ready; C.sch = S.sch;
-    C.pf_op = 0; C.pf_ch = 0; C.n_loaded = 0; C.n_consumed = 0; C.op_count = 0; C.tmem = tmem;
-    PathCtx P;
-    P.tl = tmem + ((uint32_t)(warp * 32) << 16);
-    P.acc_full = S.acc_full; P.a_ready = S.a_ready; P.op_count = 0;
+    float* traj = a.scratch + (size_t)blockIdx.x * a.scratch_per_cta;               // [N][2*sr][128]
+    unsigned char* copies = a.copies ? a.copies + (size_t)blockIdx.x * a.copies_per_cta : nullptr;
+    float* gsV = a.slabV ? a.slabV + (size_t)blockIdx.x * a.gV.gtotal : nullptr;
+    float* gsG = a.slabG ? a.slabG + (size_t)blockIdx.x * a.gG.gtotal : nullptr;
+    float sxV[32], s0V[32], sxG[32], s0G[32];
+    for (int k = 0; k < 32; ++k) { sxV[k] = 0.f; s0V[k] = 0.f; sxG[k] = 0.f; s0G[k] = 0.f; }
 
     float loss0 = 0.f, loss1 = 0.f;
     const long long ntiles = (a.B_local + TC_PATHS - 1) / TC_PATHS;
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const long long base = tile * TC_PATHS;
-        const long long gp = base + tid;                          // local path index of this thread
+        const long long gp = base + row;                          // local path index of this thread
         const bool valid = is_path && gp < a.B_local;
         float x[32], u[32], dwv[32], sdw[32], g[32], raw[32];
         int flag = 0, nacc = 0;
@@ -187,6 +238,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) critic_tc_kernel(const TcArgs a
                     else for (int j = 0; j < E.m; ++j) u[j] = raw[j];
                 }
                 if (td1) path_net_forward(P, a.nG, S.vecG, x, g);
+                float* tr = traj + (size_t)t * 2 * sr * TC_PATHS;
+                if (need_grad && td1)
+                    for (int k = 0; k < d; ++k) tr[k * TC_PATHS + row] = x[k];
                 float w = 0.f;
                 if (!prop_only) w = eq_w(E, x, u, 1, 0);
                 const int coef = fwd_move(E, x, u, dwv, dt, sqdt, xn, flag, sdw, 1, 0);
@@ -197,6 +251,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) critic_tc_kernel(const TcArgs a
                     for (int k = 0; k < d; ++k) dif = dif + sdw[k] * g[k];        // solver.py:177-182
                     dif = dif * disc;
                     y = y - dif * cf * sqdt;                                      // solver.py:184
+                    if (need_grad) {
+                        const float q = disc * cf * sqdt;
+                        for (int k = 0; k < d; ++k) tr[(sr + k) * TC_PATHS + row] = sdw[k] * q;
+                    }
                 }
                 disc = disc * expf(-E.gamma * dt * cf);                          // solver.py:187
                 nacc += coef;
@@ -218,19 +276,46 @@ __global__ void __launch_bounds__(TC_THREADS, 1) critic_tc_kernel(const TcArgs a
             if (a.o_exit) a.o_exit[gp] = nacc;
         }
         if (prop_only) continue;
-        // ------------------------------------------------------------------ NN_value at x_N, x_0, x_bdry
-        float rho_v = 0.f, rho_b = 0.f;
+        // ------------------------------------------------------------------ NN_value at x_0, x_N, x_bdry
+        float rho_v = 0.f, rho_b = 0.f, rhog = 0.f;
         if (is_ctrl) {
             ctrl_flush(C);
-            sched_add_fwd(C.sch, a.nV, a.imgV, a.nV.L);
-            for (int i = 0; i < 3; ++i) ctrl_net_forward(C, a.nV, a.nV.L);
+            if (!need_grad) {
+                sched_add_fwd(C.sch, a.nV, a.imgV, a.nV.L);
+                for (int i = 0; i < 3; ++i) ctrl_net_forward(C, a.nV, a.nV.L);
+            } else {
+                sched_add_fwd(C.sch, a.nV, a.imgV, a.nV.L);                       // V(x_0), forward only
+                for (int i = 0; i < 3; ++i) { sched_add_fwd(C.sch, a.nV, a.imgV, a.nV.L); sched_add_bwd(C.sch, a.nV, a.imgV); }
+                ctrl_net_forward(C, a.nV, a.nV.L);
+                for (int i = 0; i < 3; ++i) { ctrl_net_forward(C, a.nV, a.nV.L); ctrl_net_backward(C, a.nV, true, copies); }
+            }
         } else if (is_path) {
-            float vN[1], v0[1], vb[1], x0v[32], xbv[32];
-            path_net_forward(P, a.nV, S.vecV, x, vN);
+            float vN[1], v0[1], vb[1], x0v[32], xbv[32], dy0[32], cot[1];
             for (int k = 0; k < d; ++k) x0v[k] = valid ? a.x0[gp * d + k] : fill;
-            path_net_forward(P, a.nV, S.vecV, x0v, v0);
             for (int k = 0; k < d; ++k) xbv[k] = valid ? a.xb[gp * d + k] : fill;
-            path_net_forward(P, a.nV, S.vecV, xbv, vb);
+            if (!need_grad) {
+                path_net_forward(P, a.nV, S.vecV, x0v, v0);
+                path_net_forward(P, a.nV, S.vecV, x, vN);
+                path_net_forward(P, a.nV, S.vecV, xbv, vb);
+            } else {
+                Masks mk;
+                path_net_forward(P, a.nV, S.vecV, x0v, v0);
+                path_net_forward_keep(P, a.nV, S.vecV, x, vN, mk, copies, S.act, row, false);
+                const float delta = v0[0] - y - vN[0] * disc;
+                rhog = valid ? rho_grad(delta, 50.f) * scale : 0.f;
+                cot[0] = -rhog * disc;
+                path_net_backward(P, a.nV, a.gV, mk, cot, true, gsV, S.dz, row, dy0);
+                for (int k = 0; k < d; ++k) { sxV[k] += x[k] * dy0[k]; s0V[k] += dy0[k]; }
+                path_net_forward_keep(P, a.nV, S.vecV, x0v, v0, mk, copies, S.act, row, false);
+                cot[0] = rhog;
+                path_net_backward(P, a.nV, a.gV, mk, cot, true, gsV, S.dz, row, dy0);
+                for (int k = 0; k < d; ++k) { sxV[k] += x0v[k] * dy0[k]; s0V[k] += dy0[k]; }
+                path_net_forward_keep(P, a.nV, S.vecV, xbv, vb, mk, copies, S.act, row, false);
+                const float dbb = vb[0] - eq_Z(E, xbv, 1, 0);
+                cot[0] = valid ? rho_grad(dbb, 50.f) * scale : 0.f;
+                path_net_backward(P, a.nV, a.gV, mk, cot, true, gsV, S.dz, row, dy0);
+                for (int k = 0; k < d; ++k) { sxV[k] += xbv[k] * dy0[k]; s0V[k] += dy0[k]; }
+            }
             const float delta = v0[0] - y - vN[0] * disc;                         // solver.py:189
             const float db = vb[0] - eq_Z(E, xbv, 1, 0);                          // solver.py:190
             if (valid) {
@@ -242,9 +327,38 @@ __global__ void __launch_bounds__(TC_THREADS, 1) critic_tc_kernel(const TcArgs a
         }
         loss0 += tc_block_sum(rho_v, S.red);
         loss1 += tc_block_sum(rho_b, S.red);
-        (void)scale;
+        // ------------------------------------------------------------------ sweep 2: NN_value_grad backward
+        if (need_grad && td1) {
+            if (is_ctrl) {
+                ctrl_flush(C);
+                sched_add_fwd(C.sch, a.nG, a.imgG, a.nG.L - 1);
+                sched_add_bwd(C.sch, a.nG, a.imgG);
+                for (int t = 0; t < tlive; ++t) {
+                    ctrl_net_forward(C, a.nG, a.nG.L - 1);
+                    ctrl_net_backward(C, a.nG, true, copies);
+                }
+            } else if (is_path) {
+                Masks mk;
+                float xt[32], cot[32], dy0[32];
+                for (int t = 0; t < tlive; ++t) {
+                    const float* tr = traj + (size_t)t * 2 * sr * TC_PATHS;
+                    for (int k = 0; k < d; ++k) { xt[k] = tr[k * TC_PATHS + row]; cot[k] = tr[(sr + k) * TC_PATHS + row] * rhog; }
+                    path_net_forward_keep(P, a.nG, S.vecG, xt, (float*)nullptr, mk, copies, S.act, row, true);
+                    path_net_backward(P, a.nG, a.gG, mk, cot, true, gsG, S.dz, row, dy0);
+                    for (int k = 0; k < d; ++k) { sxG[k] += xt[k] * dy0[k]; s0G[k] += dy0[k]; }
+                }
+            }
+        }
     }
     if (is_ctrl) ctrl_flush(C);
+    if (need_grad) {
+        reduce_rows_to(gsV + a.gV.gX, sxV, d, is_path);
+        reduce_rows_to(gsV + a.gV.g0, s0V, d, is_path);
+        if (td1) {
+            reduce_rows_to(gsG + a.gG.gX, sxG, d, is_path);
+            reduce_rows_to(gsG + a.gG.g0, s0G, d, is_path);
+        }
+    }
     if (tid == 0 && a.loss_part) {
         a.loss_part[blockIdx.x * 2] = loss0;
         a.loss_part[blockIdx.x * 2 + 1] = loss1;
@@ -258,28 +372,32 @@ __global__ void __launch_bounds__(TC_THREADS, 1) critic_tc_kernel(const TcArgs a
 __global__ void __launch_bounds__(TC_THREADS, 1) actor_tc_kernel(const TcArgs a) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     TcSmem S;
-    tc_carve(S, smem_raw, a.nA.vec_floats, a.nV.vec_floats, a.nG.vec_floats);
+    tc_carve(S, smem_raw, a);
     const uint32_t tmem = tc_setup(S, a);
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const bool is_path = warp < 4;
-    const bool is_ctrl = (warp == 4 && lane == 0);
+    Roles R;
+    roles_init(R, S, a, tmem);
+    Ctrl& C = R.C;
+    PathCtx& P = R.P;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const bool is_path = R.is_path, is_ctrl = R.is_ctrl;
+    const int row = R.row;
     const Eq<float> E(a.eq);
-    const int d = E.d, N = a.N;
+    const int d = E.d, m = E.m, N = a.N, sr = a.sr;
     const bool cheat = a.flags & F_CHEAT_CONTROL, cheat_v = a.flags & F_CHEAT_VALUE;
+    const bool need_grad = (a.flags & F_NEED_GRAD) && !cheat;
     const float fill = 0.5f * E.R / sqrtf((float)d);
-
-    Ctrl C;
-    C.ring = S.ring; C.full = S.full; C.empty = S.empty; C.acc_full = S.acc_full; C.a_ready = S.a_ready; C.sch = S.sch;
-    C.pf_op = 0; C.pf_ch = 0; C.n_loaded = 0; C.n_consumed = 0; C.op_count = 0; C.tmem = tmem;
-    PathCtx P;
-    P.tl = tmem + ((uint32_t)(warp * 32) << 16);
-    P.acc_full = S.acc_full; P.a_ready = S.a_ready; P.op_count = 0;
+    const int trs = 2 * sr + A_NSCAL;
+    float* traj = a.scratch + (size_t)blockIdx.x * a.scratch_per_cta;               // [N][2*sr + A_NSCAL][128]
+    unsigned char* copies = a.copies ? a.copies + (size_t)blockIdx.x * a.copies_per_cta : nullptr;
+    float* gsA = a.slabA ? a.slabA + (size_t)blockIdx.x * a.gA.gtotal : nullptr;
+    float sxA[32], s0A[32];
+    for (int k = 0; k < 32; ++k) { sxA[k] = 0.f; s0A[k] = 0.f; }
 
     float loss0 = 0.f;
     const long long ntiles = (a.B_local + TC_PATHS - 1) / TC_PATHS;
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const long long base = tile * TC_PATHS;
-        const long long gp = base + tid;
+        const long long gp = base + row;
         const bool valid = is_path && gp < a.B_local;
         float x[32], u[32], dwv[32], raw[32];
         int flag = 0, nacc = 0;
@@ -294,6 +412,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) actor_tc_kernel(const TcArgs a)
             ctrl_flush(C);
             if (!cheat) sched_add_fwd(C.sch, a.nA, a.imgA, a.nA.L);
         }
+        // ------------------------------------------------------------------ forward rollout
         int tlive = 0;
         for (int t = 0; t < N; ++t) {
             const int alive = __syncthreads_or(valid && flag > 0);
@@ -310,11 +429,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) actor_tc_kernel(const TcArgs a)
                 } else {
                     path_net_forward(P, a.nA, S.vecA, x, raw);
                     if (a.nA.ekn_head) ekn_head_fwd(raw, u, a.nA.mctrl, 1, 0);
-                    else for (int j = 0; j < E.m; ++j) u[j] = raw[j];
+                    else for (int j = 0; j < m; ++j) u[j] = raw[j];
                 }
+                float* tr = traj + (size_t)t * trs * TC_PATHS;
+                if (need_grad)
+                    for (int k = 0; k < d; ++k) { tr[k * TC_PATHS + row] = x[k]; tr[(sr + k) * TC_PATHS + row] = dwv[k]; }
                 const float w = eq_w(E, x, u, 1, 0);
                 const int coef = fwd_move(E, x, u, dwv, dt, sqdt, xn, flag, (float*)nullptr, 1, 0);
                 const float cf = (float)coef;
+                if (need_grad) {
+                    float* sc = tr + (size_t)2 * sr * TC_PATHS;
+                    sc[A_DT * TC_PATHS + row] = dt; sc[A_SQDT * TC_PATHS + row] = sqdt; sc[A_COEF * TC_PATHS + row] = valid ? cf : 0.f;
+                    sc[A_DISC * TC_PATHS + row] = disc; sc[A_XN * TC_PATHS + row] = xn; sc[A_DTG * TC_PATHS + row] = (float)dtg;
+                }
                 y = y + cf * w * dt * disc;                                       // solver.py:218
                 disc = disc * expf(-E.gamma * dt * cf);                          // solver.py:219
                 nacc += coef;
@@ -335,17 +462,39 @@ __global__ void __launch_bounds__(TC_THREADS, 1) actor_tc_kernel(const TcArgs a)
             }
             if (a.o_exit) a.o_exit[gp] = nacc;
         }
+        // ------------------------------------------------------------------ terminal value (+ its input gradient)
         float yv = 0.f;
+        float lam[32];
+        float Dbar = 0.f;
         if (is_ctrl) {
             ctrl_flush(C);
             if (!cheat_v) {
                 sched_add_fwd(C.sch, a.nV, a.imgV, a.nV.L);
+                if (need_grad) sched_add_bwd(C.sch, a.nV, a.imgV);
                 ctrl_net_forward(C, a.nV, a.nV.L);
+                if (need_grad) ctrl_net_backward(C, a.nV, false, nullptr);
             }
         } else if (is_path) {
             float vN[1];
-            if (cheat_v) vN[0] = eq_V_true(E, x, 1, 0);                           // solver.py:223
-            else path_net_forward(P, a.nV, S.vecV, x, vN);                        // solver.py:221
+            const float seed = valid ? disc * a.invB : 0.f;
+            if (cheat_v) {
+                vN[0] = eq_V_true(E, x, 1, 0);                                    // solver.py:223
+                if (need_grad) {
+                    eq_V_grad_true(E, x, lam, 1, 0);
+                    for (int k = 0; k < d; ++k) lam[k] = lam[k] * seed;
+                }
+            } else if (!need_grad) {
+                path_net_forward(P, a.nV, S.vecV, x, vN);                         // solver.py:221
+            } else {
+                Masks mk;
+                float cot[1], dy0[32];
+                path_net_forward_keep(P, a.nV, S.vecV, x, vN, mk, nullptr, nullptr, row, false);
+                cot[0] = seed;
+                path_net_backward(P, a.nV, a.gV, mk, cot, false, nullptr, nullptr, row, dy0);
+                const float* g0c = S.vecV + a.nV.vec_g0;
+                for (int k = 0; k < d; ++k) lam[k] = dy0[k] * g0c[k];
+            }
+            Dbar = valid ? vN[0] * a.invB : 0.f;
             y = y + vN[0] * disc;
             if (valid) {
                 yv = y;
@@ -353,8 +502,51 @@ __global__ void __launch_bounds__(TC_THREADS, 1) actor_tc_kernel(const TcArgs a)
             }
         }
         loss0 += tc_block_sum(yv, S.red);
+        if (!need_grad) continue;
+        // ------------------------------------------------------------------ reverse sweep
+        if (is_ctrl) {
+            ctrl_flush(C);
+            sched_add_fwd(C.sch, a.nA, a.imgA, a.nA.L);
+            sched_add_bwd(C.sch, a.nA, a.imgA);
+        }
+        for (int t = tlive - 1; t >= 0; --t) {
+            const float* tr = traj + (size_t)t * trs * TC_PATHS;
+            const float* sc = tr + (size_t)2 * sr * TC_PATHS;
+            const int any = __syncthreads_or(valid && sc[A_COEF * TC_PATHS + row] > 0.f);
+            if (!any) continue;
+            if (is_ctrl) {
+                ctrl_net_forward(C, a.nA, a.nA.L);
+                ctrl_net_backward(C, a.nA, true, copies);
+            } else if (is_path) {
+                Masks mk;
+                float xt[32], ubar[32], cot[32], dy0[32];
+                for (int k = 0; k < d; ++k) { xt[k] = tr[k * TC_PATHS + row]; dwv[k] = tr[(sr + k) * TC_PATHS + row]; }
+                path_net_forward_keep(P, a.nA, S.vecA, xt, raw, mk, copies, S.act, row, false);
+                if (a.nA.ekn_head) ekn_head_fwd(raw, u, a.nA.mctrl, 1, 0);
+                else for (int j = 0; j < m; ++j) u[j] = raw[j];
+                const int coef = (valid && sc[A_COEF * TC_PATHS + row] > 0.f) ? 1 : 0;
+                adj_step(E, xt, u, dwv, sc[A_DT * TC_PATHS + row], sc[A_SQDT * TC_PATHS + row], coef, (int)sc[A_DTG * TC_PATHS + row],
+                         sc[A_XN * TC_PATHS + row], sc[A_DISC * TC_PATHS + row], a.invB, lam, Dbar, ubar, 1, 0);
+                if (a.nA.ekn_head) {
+                    if (coef) ekn_head_bwd(raw, ubar, cot, m, 1, 0);
+                    else for (int j = 0; j <= m; ++j) cot[j] = 0.f;
+                } else {
+                    for (int j = 0; j < m; ++j) cot[j] = ubar[j];
+                }
+                path_net_backward(P, a.nA, a.gA, mk, cot, true, gsA, S.dz, row, dy0);
+                const float* g0c = S.vecA + a.nA.vec_g0;
+                for (int k = 0; k < d; ++k) {
+                    sxA[k] += xt[k] * dy0[k]; s0A[k] += dy0[k];
+                    lam[k] = lam[k] + dy0[k] * g0c[k];
+                }
+            }
+        }
     }
     if (is_ctrl) ctrl_flush(C);
+    if (need_grad) {
+        reduce_rows_to(gsA + a.gA.gX, sxA, d, is_path);
+        reduce_rows_to(gsA + a.gA.g0, s0A, d, is_path);
+    }
     if (tid == 0 && a.loss_part) {
         a.loss_part[blockIdx.x * 2] = loss0;
         a.loss_part[blockIdx.x * 2 + 1] = 0.f;

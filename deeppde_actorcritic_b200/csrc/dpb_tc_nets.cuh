@@ -12,7 +12,7 @@
 //     A operand (tcgen05.mma with A in tensor memory).
 //   * Weights: the pack kernel turns the flat FP32 parameters into bf16 hi/lo operand images (layout in
 //     dpb_tc.cuh), cut into 16-wide contraction chunks of N16*64 bytes.  The control thread streams the
-//     chunks L2 -> shared memory through a ring of NSLOT slots with 1-D bulk copies (cp.async.bulk,
+//     chunks L2 -> shared memory through a ring of slots with 1-D bulk copies (cp.async.bulk,
 //     completion on an mbarrier); a slot is released by the tcgen05.commit of the MMAs that read it.
 //     The chunk sequence of a phase is a cyclic schedule known in advance, so the stream runs ahead of
 //     the MMAs across layers, networks and time steps.
@@ -26,8 +26,7 @@ namespace tc {
 
 constexpr int TC_PATHS = 128;
 constexpr int TC_THREADS = 160;                 // 4 path warps + 1 control warp
-constexpr int NSLOT = 12;
-constexpr int SLOT_BYTES = 256 * 64;            // one 16-wide contraction chunk of <= 256 rows, hi + lo planes
+constexpr int MAX_NSLOT = 16;                   // ring slots (runtime count: whatever shared memory is left)
 constexpr uint32_t COL_ACC = 0, COL_AHI = 256, COL_ALO = 384;
 constexpr int MAXOPS = 40;
 
@@ -136,20 +135,22 @@ struct Sched {                       // cyclic chunk schedule of the current pha
 
 struct Ctrl {
     unsigned char* ring;
-    uint64_t *full, *empty, *acc_full, *a_ready;
+    uint64_t *full, *empty, *acc_full, *a_ready, *act_full;
     Sched* sch;
     int pf_op, pf_ch;
-    uint32_t n_loaded, n_consumed, op_count, tmem;
+    uint32_t nslot, slot_bytes;
+    uint32_t n_loaded, n_consumed, op_count, act_count, tmem;
+    unsigned char *act, *dz;         // shared-memory operand images of the dW products (128 paths x K16 features, bf16)
 };
 
 __device__ __forceinline__ void ctrl_prefetch(Ctrl& c) {
     if (c.sch->nops == 0) return;
-    while (c.n_loaded - c.n_consumed < (uint32_t)NSLOT) {
-        const uint32_t slot = c.n_loaded % NSLOT, use = c.n_loaded / NSLOT;
+    while (c.n_loaded - c.n_consumed < c.nslot) {
+        const uint32_t slot = c.n_loaded % c.nslot, use = c.n_loaded / c.nslot;
         if (use > 0) mbar_wait(&c.empty[slot], (use - 1) & 1);
         const uint32_t bytes = (uint32_t)c.sch->cb[c.pf_op];
         mbar_arrive_expect_tx(&c.full[slot], bytes);
-        bulk_g2s(c.ring + (size_t)slot * SLOT_BYTES, c.sch->ptr[c.pf_op] + (size_t)c.pf_ch * bytes, bytes, &c.full[slot]);
+        bulk_g2s(c.ring + (size_t)slot * c.slot_bytes, c.sch->ptr[c.pf_op] + (size_t)c.pf_ch * bytes, bytes, &c.full[slot]);
         if (++c.pf_ch == c.sch->nch[c.pf_op]) {
             c.pf_ch = 0;
             if (++c.pf_op == c.sch->nops) c.pf_op = 0;
@@ -161,7 +162,7 @@ __device__ __forceinline__ void ctrl_prefetch(Ctrl& c) {
 // drop every chunk that was streamed ahead but will not be used (end of a phase / dead tile)
 __device__ __forceinline__ void ctrl_flush(Ctrl& c) {
     while (c.n_consumed != c.n_loaded) {
-        const uint32_t slot = c.n_consumed % NSLOT, use = c.n_consumed / NSLOT;
+        const uint32_t slot = c.n_consumed % c.nslot, use = c.n_consumed / c.nslot;
         mbar_wait(&c.full[slot], use & 1);
         mbar_arrive(&c.empty[slot]);
         ++c.n_consumed;
@@ -184,9 +185,9 @@ __device__ __forceinline__ void ctrl_gemm_ts(Ctrl& c, int nchunks, int R) {
     mbar_wait(c.a_ready, c.op_count & 1);
     tc_fence_after();
     for (int s = 0; s < nchunks; ++s) {
-        const uint32_t slot = c.n_consumed % NSLOT, use = c.n_consumed / NSLOT;
+        const uint32_t slot = c.n_consumed % c.nslot, use = c.n_consumed / c.nslot;
         mbar_wait(&c.full[slot], use & 1);
-        const uint32_t sb = smem_u32(c.ring + (size_t)slot * SLOT_BYTES);
+        const uint32_t sb = smem_u32(c.ring + (size_t)slot * c.slot_bytes);
         const uint64_t bhi = smem_desc(sb, (R >> 3) * 128, 128), blo = smem_desc(sb + R * 32, (R >> 3) * 128, 128);
         const uint32_t ahi = c.tmem + COL_AHI + s * 8, alo = c.tmem + COL_ALO + s * 8;
         mma_ts(c.tmem + COL_ACC, ahi, bhi, idesc, s > 0);
@@ -296,6 +297,258 @@ __device__ __forceinline__ void path_net_forward(PathCtx& p, const TcNet& t, con
     path_write_y0(p, t, vec, x);
     for (int l = 0; l < t.L; ++l) path_epi_hidden(p, vec + t.ly[l].vec, t.ly[l].N16);
     path_epi_last(p, vec + t.ly[t.L].vec, t.ly[t.L].N16, t.ly[t.L].nl, out);
+}
+
+
+// ===================================================================================== backward pass
+// Gradient slab of one network on the tensor path (per CTA, FP32):
+//   layer l: (kl + 1) x nl, row-major; rows 0..kl-1 = G_l = a_l^T dz_l, row kl = column sums of dz_l
+//   (the activation copies carry a constant 1 in feature kl), then SX[in] = sum x*dy0, S0[in] = sum dy0.
+struct TcSlab { long long gW[MAXLIN], gX, g0, gtotal; };
+inline void tcslab_init(TcSlab& g, const TcNet& t) {
+    long long o = 0;
+    for (int l = 0; l <= t.L; ++l) { g.gW[l] = o; o += ((long long)(t.ly[l].kl + 1) * t.ly[l].nl + 3) & ~3LL; }
+    g.gX = o; o += (t.in + 3) & ~3; g.g0 = o; o += (t.in + 3) & ~3;
+    g.gtotal = o;
+}
+// byte offset of the bf16 copy of activation a_l (l = 0..L-1) inside the per-CTA copy scratch
+inline __host__ __device__ long long tc_copy_off(const TcNet& t, int l) {
+    long long o = 0;
+    for (int i = 0; i < l; ++i) o += (long long)TC_PATHS * t.ly[i].K16 * 2;
+    return o;
+}
+inline __host__ __device__ long long tc_copy_bytes(const TcNet& t) { return tc_copy_off(t, t.L); }
+
+// raw slab -> flat gradient (same formulas as finalize_grad_kernel of the exact path)
+__global__ void tc_finalize_grad_kernel(TcNet t, TcSlab g, const float* __restrict__ th, const float* __restrict__ raw, float* __restrict__ grad, float c) {
+    const NetDev& nd = t.flat;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const long long t0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    for (long long i = t0; i < t.in; i += stride) {
+        grad[nd.fg0 + i] = c * raw[g.gX + i];
+        grad[nd.fb0 + i] = raw[g.g0 + i];
+    }
+    for (int l = 0; l <= t.L; ++l) {
+        const int kl = t.ly[l].kl, nl = t.ly[l].nl;
+        for (long long i = t0; i < (long long)kl * nl; i += stride) {
+            int n = (int)(i % nl);
+            grad[nd.fW[l] + i] = raw[g.gW[l] + i] * (th[nd.fg[l] + n] * c);
+        }
+        for (long long n = t0; n < nl; n += stride) {
+            float s = 0.f;
+            for (int k = 0; k < kl; ++k) s = fmaf(th[nd.fW[l] + (long long)k * nl + n], raw[g.gW[l] + (long long)k * nl + n], s);
+            const float C = raw[g.gW[l] + (long long)kl * nl + n];
+            if (l == t.L) {
+                s = s + th[nd.fbias + n] * C;
+                grad[nd.fbias + n] = (th[nd.fg[l] + n] * c) * C;
+            }
+            grad[nd.fg[l] + n] = c * s;
+            grad[nd.fb[l] + n] = C;
+        }
+    }
+}
+
+// ---- control thread ----------------------------------------------------------------------------------
+__device__ __forceinline__ void sched_add_bwd(Sched* s, const TcNet& t, const unsigned char* img) {
+    for (int l = t.L; l >= 0; --l) sched_add(s, img + t.ly[l].img_b, t.ly[l].N16 / 16, t.ly[l].K16 * 64);
+}
+
+// global copy scratch -> ACT (bulk copy; waits until it has landed)
+__device__ __forceinline__ void ctrl_act_load(Ctrl& c, const unsigned char* src, uint32_t bytes) {
+    mbar_arrive_expect_tx(c.act_full, bytes);
+    bulk_g2s(c.act, src, bytes, c.act_full);
+}
+__device__ __forceinline__ void ctrl_act_wait(Ctrl& c) {
+    mbar_wait(c.act_full, c.act_count & 1);
+    ++c.act_count;
+}
+
+// D[acc] (rows = features 128*blk .. of ACT, cols = N16 features of DZ) = ACT^T DZ over the 128 paths
+__device__ __forceinline__ void ctrl_gemm_dw(Ctrl& c, int blk, int N16) {
+    const uint32_t idesc = idesc_bf16(128, N16, 1, 1);
+    mbar_wait(c.a_ready, c.op_count & 1);
+    tc_fence_after();
+    const uint32_t a0 = smem_u32(c.act) + blk * 16 * 2048, b0 = smem_u32(c.dz);
+#pragma unroll
+    for (int s = 0; s < TC_PATHS / 16; ++s) {
+        const uint64_t ad = smem_desc(a0 + s * 256, 128, 2048), bd = smem_desc(b0 + s * 256, 128, 2048);
+        mma_ss(c.tmem + COL_ACC, ad, bd, idesc, s > 0);
+    }
+    tc_commit(c.acc_full);
+    ++c.op_count;
+}
+
+// backward of one network evaluation.  need_w: dW products (+ drains on the path side);
+// copies: per-CTA global scratch holding the bf16 copies of a_0..a_{L-1} (a_L is already in ACT).
+__device__ __forceinline__ void ctrl_net_backward(Ctrl& c, const TcNet& t, bool need_w, const unsigned char* copies) {
+    for (int l = t.L; l >= 0; --l) {
+        if (need_w) {
+            if (l < t.L) ctrl_act_wait(c);
+            const int nblk = (t.ly[l].kl + 1 + 127) >> 7;
+            for (int b = 0; b < nblk; ++b) ctrl_gemm_dw(c, b, t.ly[l].N16);
+            if (l > 0) {
+                mbar_wait(c.acc_full, (c.op_count - 1) & 1);           // the MMAs reading ACT are done
+                ctrl_act_load(c, copies + tc_copy_off(t, l - 1), (uint32_t)(TC_PATHS * t.ly[l - 1].K16 * 2));
+            }
+        }
+        ctrl_gemm_ts(c, t.ly[l].N16 / 16, t.ly[l].K16);                  // dA_l = dz_l x (W_l gamma c)^T
+    }
+}
+
+// ---- path threads ------------------------------------------------------------------------------------
+struct Masks { uint32_t m[MAXLIN][8]; };     // m[l] bit k: a_l[k] > 0  (l = 1..L), K16 <= 256
+
+// 16 features 16c.. of this thread's row -> bf16 image (R = 128 rows) at `img` (shared or global)
+__device__ __forceinline__ void copy16(unsigned char* img, int row, int c, const float* v, int one_at /* feature index set to 1, or -1 */) {
+    uint32_t w[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        float a = v[2 * j], b = v[2 * j + 1];
+        if (16 * c + 2 * j == one_at) a = 1.f;
+        if (16 * c + 2 * j + 1 == one_at) b = 1.f;
+        w[j] = pack2(__float2bfloat16_rn(a), __float2bfloat16_rn(b));
+    }
+    unsigned char* p = img + (size_t)(2 * c) * 2048 + (row >> 3) * 128 + (row & 7) * 16;
+    *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+    *reinterpret_cast<uint4*>(p + 2048) = make_uint4(w[4], w[5], w[6], w[7]);
+}
+
+// forward keeping what the backward needs: relu masks (registers), bf16 copies of a_0..a_{L-1} (global
+// scratch `copies`, NULL: none) and of a_L (shared ACT image, NULL: none).  skip_last: stop after the
+// last hidden layer (the raw output is not needed) -- then the caller must write dz_L and publish.
+__device__ __forceinline__ void path_net_forward_keep(PathCtx& p, const TcNet& t, const float* vec, const float* x, float* out, Masks& mk,
+                                                      unsigned char* copies, unsigned char* act, int row, bool skip_last) {
+    {
+        const int K0 = t.ly[0].K16;
+        const float* g0c = vec + t.vec_g0;
+        const float* b0 = g0c + K0;
+        for (int c = 0; c < K0 / 16; ++c) {
+            float v[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const int k = 16 * c + j;
+                v[j] = (k < t.in) ? x[k] * g0c[k] + b0[k] : 0.f;
+            }
+            put16(p.tl, c, v);
+            if (copies) copy16(copies, row, c, v, t.ly[0].kl);
+        }
+        if (copies) fence_proxy_async_all();
+        path_publish(p);
+    }
+    for (int l = 0; l < t.L; ++l) {
+        const int N16 = t.ly[l].N16;
+        const float* gc = vec + t.ly[l].vec;
+        const float* bb = gc + N16;
+        const bool last_hidden = (l == t.L - 1);
+        unsigned char* dst = last_hidden ? act : (copies ? copies + tc_copy_off(t, l + 1) : nullptr);
+        path_wait_acc(p);
+        for (int c = 0; c < N16 / 16; ++c) {
+            uint32_t r[16];
+            tmem_ld16(p.tl + COL_ACC + 16 * c, r);
+            tmem_ld_wait();
+            float v[16];
+            uint32_t bits = 0;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const float z = __uint_as_float(r[j]) * gc[16 * c + j] + bb[16 * c + j];
+                v[j] = z + fmaxf(z, 0.f);
+                bits |= (z > 0.f ? 1u : 0u) << j;
+            }
+            if (c & 1) mk.m[l + 1][c >> 1] |= bits << 16; else mk.m[l + 1][c >> 1] = bits;
+            put16(p.tl, c, v);
+            if (dst) copy16(dst, row, c, v, t.ly[l + 1].kl);
+        }
+        if (dst) fence_proxy_async_all();
+        if (!(last_hidden && skip_last)) path_publish(p);
+    }
+    if (!skip_last) path_epi_last(p, vec + t.ly[t.L].vec, t.ly[t.L].N16, t.ly[t.L].nl, out);
+}
+
+// this thread's row of a dW block -> RED into the slab:  rows f = 128*blk + row (f <= kl), cols n < nl
+__device__ __forceinline__ void path_drain(PathCtx& p, int blk, int row, int kl, int nl, int N16, float* slab) {
+    path_wait_acc(p);
+    const int f = 128 * blk + row;
+    float* dst = slab + (long long)f * nl;
+    const bool rowok = f <= kl;
+    const bool vec4 = (nl & 3) == 0;
+    for (int c = 0; c < N16 / 16; ++c) {
+        uint32_t r[16];
+        tmem_ld16(p.tl + COL_ACC + 16 * c, r);
+        tmem_ld_wait();
+        if (!rowok) continue;
+        if (vec4) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int n = 16 * c + 4 * q;
+                if (n < nl) red_add_v4(dst + n, __uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]), __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3]));
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const int n = 16 * c + j;
+                if (n < nl) atomicAdd(dst + n, __uint_as_float(r[j]));
+            }
+        }
+    }
+    tc_fence_before();
+    mbar_arrive(p.a_ready);                    // accumulator drained
+}
+
+// cotangent row (N16 values, zero beyond nl) -> planes (+ DZ image)
+__device__ __forceinline__ void path_write_dz(PathCtx& p, const float* dz, int N16, unsigned char* dzimg, int row) {
+    for (int c = 0; c < N16 / 16; ++c) {
+        put16(p.tl, c, dz + 16 * c);
+        if (dzimg) copy16(dzimg, row, c, dz + 16 * c, -1);
+    }
+    if (dzimg) fence_proxy_async();
+    path_publish(p);
+}
+
+// backward of one network evaluation on the path side.  dout: cotangent of the raw output (nl_L values).
+// slab: this CTA's gradient slab of the network (need_w) ; dy0 receives the cotangent of y0 (in values).
+__device__ __forceinline__ void path_net_backward(PathCtx& p, const TcNet& t, const TcSlab& g, const Masks& mk, const float* dout, bool need_w,
+                                                  float* slab, unsigned char* dzimg, int row, float* dy0) {
+    {
+        float v[32];
+        const int N16 = t.ly[t.L].N16;
+        for (int n = 0; n < N16; ++n) v[n] = (n < t.ly[t.L].nl) ? dout[n] : 0.f;
+        path_write_dz(p, v, N16, need_w ? dzimg : nullptr, row);
+    }
+    for (int l = t.L; l >= 0; --l) {
+        if (need_w) {
+            const int nblk = (t.ly[l].kl + 1 + 127) >> 7;
+            for (int b = 0; b < nblk; ++b) path_drain(p, b, row, t.ly[l].kl, t.ly[l].nl, t.ly[l].N16, slab + g.gW[l]);
+        }
+        path_wait_acc(p);                                                // dA_l in the accumulator (K16_l columns)
+        const int K16 = t.ly[l].K16;
+        if (l > 0) {
+            for (int c = 0; c < K16 / 16; ++c) {
+                uint32_t r[16];
+                tmem_ld16(p.tl + COL_ACC + 16 * c, r);
+                tmem_ld_wait();
+                const uint32_t bits = mk.m[l][c >> 1] >> ((c & 1) * 16);
+                float v[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const float a = __uint_as_float(r[j]);
+                    v[j] = ((bits >> j) & 1u) ? 2.f * a : a;                 // d(z + relu z)
+                }
+                put16(p.tl, c, v);
+                if (need_w) copy16(dzimg, row, c, v, -1);
+            }
+            if (need_w) fence_proxy_async();
+            path_publish(p);
+        } else {
+            for (int c = 0; c < K16 / 16; ++c) {
+                uint32_t r[16];
+                tmem_ld16(p.tl + COL_ACC + 16 * c, r);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                    if (16 * c + j < t.in) dy0[16 * c + j] = __uint_as_float(r[j]);
+            }
+        }
+    }
 }
 
 }  // namespace tc

@@ -119,3 +119,74 @@ def test_tensor_forward_vs_exact_d20_3x200():
     yb = tn.actor_step(th["actor"], th["critic"], x0, None, N, T, want=("delta", "coef"), **kw)
     same = (ya["coef"] == yb["coef"]).all(1).cpu().numpy()
     np.testing.assert_allclose(_npy(yb["delta"])[same], _npy(ya["delta"])[same], **VTOL)
+
+
+GTOL_TENSOR = 1e-2      # stated tolerance of the tensor path: gradients, relative to the gradient's max-norm
+                        # (the dW contraction uses bf16 operands; forward / dX products are bf16x3)
+
+
+def _gerr(got, ref):
+    ref = np.asarray(ref, dtype=np.float64)
+    scale = np.abs(ref).max()
+    if scale == 0:
+        return float(np.abs(got).max())
+    return float(np.abs(got - ref).max() / scale)
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_tensor_gradients_vs_golden(name):
+    z, cfg = _load(name)
+    eng = Engine(cfg["eqn_config"], cfg["net_config"], cfg["train_config"], dtype="float32", impl="tensor")
+    x0, dw, xb = (eng.tensor(z[k]) for k in ("x0", "dw", "xb"))
+    thA, thV, thG = (eng.tensor(z[k]) for k in ("theta_actor", "theta_critic", "theta_critic_grad"))
+    ec = cfg["eqn_config"]
+    N, T = ec["num_time_interval_critic"], ec["total_time_critic"]
+    errs = {}
+    for cheat in (False, True):
+        tag = "cheat" if cheat else "nn"
+        r = eng.critic_step(thA, thV, thG, x0, dw, xb, N, T, cheat_control=cheat, need_grad=True, want=("delta", "coef"))
+        same = (_npy(r["coef"]) == z[f"prop_{tag}_coef"]).all(1)
+        np.testing.assert_allclose(_npy(r["delta"])[same], z[f"critic_{tag}_delta"][same], **VTOL)
+        if same.all():
+            errs[f"gV_{tag}"] = _gerr(_npy(r["grad_V"]), z[f"critic_{tag}_grad_V"])
+            errs[f"gG_{tag}"] = _gerr(_npy(r["grad_G"]), z[f"critic_{tag}_grad_G"])
+    for cheat_v in (False, True):
+        tag = "cheatV" if cheat_v else "nn"
+        r = eng.actor_step(thA, thV, x0, dw, N, T, cheat_value=cheat_v, need_grad=True, want=("delta", "coef"))
+        same = (_npy(r["coef"]) == z["prop_nn_coef"]).all(1)
+        np.testing.assert_allclose(_npy(r["delta"])[same], z[f"actor_{tag}_y"][same], **VTOL)
+        if same.all():
+            errs[f"gA_{tag}"] = _gerr(_npy(r["grad_actor"]), z[f"actor_{tag}_grad"])
+    print(name, {k: f"{v:.2e}" for k, v in errs.items()})
+    for k, v in errs.items():
+        assert v < GTOL_TENSOR, (k, v)
+
+
+def test_tensor_gradients_vs_exact_d20_3x200():
+    e = {"eqn_name": "LQR_var", "discount": 1.0, "q": 1.0, "beta": 1.0, "epsilon": 0.05, "R": 1.0, "dim": 20, "control_dim": 20,
+         "total_time_critic": 0.2, "total_time_actor": 0.2, "num_time_interval_critic": 25, "num_time_interval_actor": 25}
+    net = {"num_hiddens_actor": [200, 200, 200], "num_hiddens_critic": [200, 200, 200]}
+    tr = {"scheme": "adaptive", "TD_type": "TD1"}
+    ex = Engine(e, net, tr, dtype="float32", impl="exact")
+    tn = Engine(e, net, tr, dtype="float32", impl="tensor")
+    from oracle import ref_solver as RS
+    rng = np.random.RandomState(12)
+    cfg = {"eqn_config": e, "net_config": net, "train_config": tr}
+    th = {}
+    for k in ("actor", "critic", "critic_grad"):
+        i, h, o, _ = RS.net_dims(cfg, k)
+        th[k] = ex.tensor(RS.init_params(i, h, o, rng))
+    B, N, T = 1000, 25, 0.2
+    x0, xb = ex.sample_x(5, 1, 0, B)
+    kw = dict(dw_mode=1, seed=5, stream_id=3)
+    a = ex.critic_step(th["actor"], th["critic"], th["critic_grad"], x0, None, xb, N, T, need_grad=True, **kw)
+    b = tn.critic_step(th["actor"], th["critic"], th["critic_grad"], x0, None, xb, N, T, need_grad=True, **kw)
+    ya = ex.actor_step(th["actor"], th["critic"], x0, None, N, T, need_grad=True, **kw)
+    yb = tn.actor_step(th["actor"], th["critic"], x0, None, N, T, need_grad=True, **kw)
+    errs = {"gV": _gerr(_npy(b["grad_V"]), _npy(a["grad_V"])), "gG": _gerr(_npy(b["grad_G"]), _npy(a["grad_G"])),
+            "gA": _gerr(_npy(yb["grad_actor"]), _npy(ya["grad_actor"])),
+            "loss_c": abs(float(b["loss"].sum() - a["loss"].sum())) / abs(float(a["loss"].sum())),
+            "loss_a": abs(float(yb["loss"][0] - ya["loss"][0]))}
+    print("tensor vs exact gradients (max-norm relative):", {k: f"{v:.2e}" for k, v in errs.items()})
+    assert errs["gV"] < GTOL_TENSOR and errs["gG"] < GTOL_TENSOR and errs["gA"] < GTOL_TENSOR
+    assert errs["loss_c"] < 1e-4 and errs["loss_a"] < 1e-4
