@@ -62,7 +62,7 @@ static const double BN_C = 1.0 / sqrt(1.0 + 1e-6);       // solver.py:242 (epsil
 struct Layout {
     int grid;
     size_t pkA, pkV, pkG, loss_part, loss_out, scratch, slabs, raw, total;
-    size_t imgA, imgV, imgG, vecA, vecV, vecG, copies;      // tensor path: operand images, vector blocks, activation copies
+    size_t imgA, imgV, imgG, vecA, vecV, vecG, copies, stats;      // tensor path: operand images, vector blocks, activation copies, counters
     long long scratch_per_cta, copies_per_cta;
 };
 
@@ -90,13 +90,14 @@ static Layout make_layout(const dpb_handle* h, long long B_local, int N) {
     L.loss_out = o; o += 256;
     L.scratch_per_cta = (long long)N * (2 * h->sr + A_NSCAL) * P;
     L.scratch = o; o += a256((size_t)L.grid * L.scratch_per_cta * es);
-    L.copies = 0; L.copies_per_cta = 0;
+    L.copies = 0; L.copies_per_cta = 0; L.stats = 0;
     if (tensor) {
         long long cb = tc::tc_copy_bytes(h->tA);
         if (tc::tc_copy_bytes(h->tV) > cb) cb = tc::tc_copy_bytes(h->tV);
         if (tc::tc_copy_bytes(h->tG) > cb) cb = tc::tc_copy_bytes(h->tG);
         L.copies_per_cta = (long long)a256((size_t)cb);
         L.copies = o; o += a256((size_t)L.grid * L.copies_per_cta);
+        L.stats = o; o += a256((size_t)L.grid * 16 * 8);
     }
     const long long gc = tensor ? h->sV.gtotal + h->sG.gtotal : h->nV.gtotal + h->nG.gtotal, ga = tensor ? h->sA.gtotal : h->nA.gtotal;
     const long long gmax = gc > ga ? gc : ga;
@@ -407,6 +408,7 @@ static void tc_fill(dpb_handle* h, tc::TcArgs& a, const Layout& L, char* ws, con
     a.scratch_per_cta = L.scratch_per_cta;
     a.copies = (unsigned char*)(ws + L.copies);
     a.copies_per_cta = L.copies_per_cta;
+    a.stats = (long long*)(ws + L.stats);
     a.sr = h->sr;
     if (outs) {
         a.o_x = (float*)outs->x_smp; a.o_dt = (float*)outs->dt; a.o_coef = (float*)outs->coef;
@@ -706,5 +708,12 @@ extern "C" int dpb_tc_selftest(const float* A, const float* B, float* D, int K, 
     DPB_CUDA(nullptr, cudaFuncSetAttribute(tc::tc_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     tc::tc_selftest_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(A, B, D, K);
     DPB_CUDA(nullptr, cudaGetLastError());
+    return DPB_OK;
+}
+
+extern "C" int dpb_tc_stats(dpb_handle* h, const void* workspace, int64_t B_local, int32_t N, int64_t* out_host) {
+    if (!h || !workspace || !out_host || h->cfg.impl != DPB_IMPL_TENSOR) return fail(h, DPB_ERR_ARG, "dpb_tc_stats: tensor-path handle and workspace required");
+    const Layout L = make_layout(h, B_local, N);
+    DPB_CUDA(h, cudaMemcpy(out_host, (const char*)workspace + L.stats, 16 * 8, cudaMemcpyDeviceToHost));
     return DPB_OK;
 }

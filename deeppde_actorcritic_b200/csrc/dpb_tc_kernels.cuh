@@ -31,6 +31,7 @@ struct TcArgs {
     int nslot, slot_bytes, actdz_bytes;   // ring geometry; bytes of each of the ACT / DZ images (0: no gradients)
     float *o_x, *o_dt, *o_coef, *o_delta, *o_delta_b;
     int* o_exit;
+    long long* stats;               // [grid][16] cycle counters (diagnostics), may be NULL
 };
 
 struct TcSmem {
@@ -41,11 +42,13 @@ struct TcSmem {
     uint32_t* tslot;
     Sched* sch;
     float* red;
+    TcNet *nA, *nV, *nG;             // shared-memory copies of the network descriptors
+    TcSlab *gA, *gV, *gG;
 };
 
 // everything except the ring
 __host__ __device__ inline size_t tc_smem_fixed(int vfA, int vfV, int vfG, int actdz_bytes) {
-    return 2 * (size_t)actdz_bytes + (size_t)(vfA + vfV + vfG) * 4 + (2 * MAX_NSLOT + 3) * 8 + 64 + sizeof(Sched) + 64 + 1024;
+    return 2 * (size_t)actdz_bytes + (size_t)(vfA + vfV + vfG) * 4 + (2 * MAX_NSLOT + 3) * 8 + 64 + sizeof(Sched) + 64 + 3 * sizeof(TcNet) + 3 * sizeof(TcSlab) + 64 + 1024;
 }
 __host__ __device__ inline size_t tc_smem_bytes(int vfA, int vfV, int vfG, int actdz_bytes, int nslot, int slot_bytes) {
     return tc_smem_fixed(vfA, vfV, vfG, actdz_bytes) + (size_t)nslot * slot_bytes;
@@ -68,6 +71,13 @@ __device__ __forceinline__ void tc_carve(TcSmem& s, unsigned char* base, const T
     s.tslot = reinterpret_cast<uint32_t*>(p); p += 64;
     s.sch = reinterpret_cast<Sched*>(p); p += sizeof(Sched);
     s.red = reinterpret_cast<float*>(((uintptr_t)p + 15) & ~(uintptr_t)15);
+    p = reinterpret_cast<unsigned char*>(s.red) + 64;
+    s.nA = reinterpret_cast<TcNet*>(p); p += sizeof(TcNet);
+    s.nV = reinterpret_cast<TcNet*>(p); p += sizeof(TcNet);
+    s.nG = reinterpret_cast<TcNet*>(p); p += sizeof(TcNet);
+    s.gA = reinterpret_cast<TcSlab*>(p); p += sizeof(TcSlab);
+    s.gV = reinterpret_cast<TcSlab*>(p); p += sizeof(TcSlab);
+    s.gG = reinterpret_cast<TcSlab*>(p);
 }
 
 // common prologue: barriers, TMEM, vector blocks -> shared memory.  Returns the TMEM base.
@@ -77,6 +87,7 @@ __device__ __forceinline__ uint32_t tc_setup(TcSmem& s, const TcArgs& a) {
     for (int i = tid; i < a.nV.vec_floats; i += TC_THREADS) s.vecV[i] = a.vecV ? a.vecV[i] : 0.f;
     for (int i = tid; i < a.nG.vec_floats; i += TC_THREADS) s.vecG[i] = a.vecG ? a.vecG[i] : 0.f;
     for (int i = tid; i < 2 * a.actdz_bytes / 4; i += TC_THREADS) reinterpret_cast<uint32_t*>(s.act)[i] = 0u;
+    if (tid == 0) { *s.nA = a.nA; *s.nV = a.nV; *s.nG = a.nG; *s.gA = a.gA; *s.gV = a.gV; *s.gG = a.gG; }
     if (tid == 0) {
         for (int i = 0; i < MAX_NSLOT; ++i) { mbar_init(&s.full[i], 1); mbar_init(&s.empty[i], 1); }
         mbar_init(s.acc_full, 1);
@@ -106,7 +117,7 @@ __device__ __forceinline__ float tc_block_sum(float v, float* red) {
 }
 
 // increments of step t for one path (same generator and bits as load_dw of the exact path)
-__device__ __forceinline__ void path_dw(const TcArgs& a, long long gpath_local, bool valid, int t, float* dw) {
+__device__ __noinline__ void path_dw(const TcArgs& a, long long gpath_local, bool valid, int t, float* dw) {
     const int d = a.eq.d;
     if (a.dw_mode == DW_EXTERNAL) {
         for (int k = 0; k < d; ++k) dw[k] = valid ? a.dw[(gpath_local * d + k) * (long long)a.N + t] : 0.f;
@@ -158,6 +169,17 @@ __device__ __forceinline__ void roles_init(Roles& r, const TcSmem& S, const TcAr
     C.act_full = S.act_full; C.act_count = 0; C.nslot = a.nslot; C.slot_bytes = a.slot_bytes; C.act = S.act; C.dz = S.dz;
     r.P.tl = tmem + ((uint32_t)(warp * 32) << 16);
     r.P.acc_full = S.acc_full; r.P.a_ready = S.a_ready; r.P.op_count = 0;
+    r.P.t_accw = 0; r.P.t_epi = 0; r.P.t_mark = clock64();
+    C.t_aready = 0; C.t_full = 0; C.t_issue = 0; C.t_accw = 0; C.n_ops = 0;
+    C.ld_slot = 0; C.ld_use = 0; C.mm_slot = 0; C.mm_use = 0; C.nops = 0; C.cur_ptr = nullptr; C.cur_nch = 0; C.cur_cb = 0;
+}
+// stats row: [0] kernel cycles, ctrl: [1] waiting for the path threads, [2] waiting for weights, [3] ops;
+// path thread 0: [4] waiting for the tensor pipe, [5] epilogue (wake-up -> publish)
+__device__ __forceinline__ void roles_stats(const Roles& r, const TcArgs& a, long long t_start) {
+    if (!a.stats) return;
+    long long* st = a.stats + (size_t)blockIdx.x * 16;
+    if (r.is_ctrl) { st[0] = clock64() - t_start; st[1] = r.C.t_aready; st[2] = r.C.t_full; st[3] = r.C.n_ops; }
+    if (threadIdx.x == 0) { st[4] = r.P.t_accw; st[5] = r.P.t_epi; }
 }
 
 // sum over the 128 path threads of per-thread accumulators acc[0..n) -> atomicAdd into dst (kernel end)
@@ -178,8 +200,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) critic_tc_kernel(const TcArgs a
     const uint32_t tmem = tc_setup(S, a);
     Roles R;
     roles_init(R, S, a, tmem);
+    const long long t_start = clock64();
     Ctrl& C = R.C;
     PathCtx& P = R.P;
+    const TcNet& nA = *S.nA;
+    const TcNet& nV = *S.nV;
+    const TcNet& nG = *S.nG;
+    const TcSlab& gA = *S.gA;
+    const TcSlab& gV = *S.gV;
+    const TcSlab& gG = *S.gG;
+    (void)gA; (void)gV; (void)gG;
     const int tid = threadIdx.x, warp = tid >> 5;
     const bool is_path = R.is_path, is_ctrl = R.is_ctrl;
     const int row = R.row;
@@ -192,8 +222,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) critic_tc_kernel(const TcArgs a
     const float fill = 0.5f * E.R / sqrtf((float)d);
     float* traj = a.scratch + (size_t)blockIdx.x * a.scratch_per_cta;               // [N][2*sr][128]
     unsigned char* copies = a.copies ? a.copies + (size_t)blockIdx.x * a.copies_per_cta : nullptr;
-    float* gsV = a.slabV ? a.slabV + (size_t)blockIdx.x * a.gV.gtotal : nullptr;
-    float* gsG = a.slabG ? a.slabG + (size_t)blockIdx.x * a.gG.gtotal : nullptr;
+    float* gsV = a.slabV ? a.slabV + (size_t)blockIdx.x * gV.gtotal : nullptr;
+    float* gsG = a.slabG ? a.slabG + (size_t)blockIdx.x * gG.gtotal : nullptr;
     float sxV[32], s0V[32], sxG[32], s0G[32];
     for (int k = 0; k < 32; ++k) { sxV[k] = 0.f; s0V[k] = 0.f; sxG[k] = 0.f; s0G[k] = 0.f; }
 
@@ -214,8 +244,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) critic_tc_kernel(const TcArgs a
         }
         if (is_ctrl) {                                            // schedule of the rollout
             ctrl_flush(C);
-            if (!cheat) sched_add_fwd(C.sch, a.nA, a.imgA, a.nA.L);
-            if (td1) sched_add_fwd(C.sch, a.nG, a.imgG, a.nG.L);
+            if (!cheat) sched_add_fwd(C.sch, nA, a.imgA, nA.L);
+            if (td1) sched_add_fwd(C.sch, nG, a.imgG, nG.L);
+            ctrl_sched_ready(C);
         }
         // ------------------------------------------------------------------ sweep 1: rollout
         int tlive = 0;
@@ -224,8 +255,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) critic_tc_kernel(const TcArgs a
             if (!alive) break;
             tlive = t + 1;
             if (is_ctrl) {
-                if (!cheat) ctrl_net_forward(C, a.nA, a.nA.L);
-                if (td1) ctrl_net_forward(C, a.nG, a.nG.L);
+                if (!cheat) ctrl_net_forward(C, nA, nA.L);
+                if (td1) ctrl_net_forward(C, nG, nG.L);
             } else if (is_path) {
                 path_dw(a, gp, valid, t, dwv);
                 float dt, sqdt, xn; int dtg;
@@ -233,11 +264,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) critic_tc_kernel(const TcArgs a
                 if (cheat) {
                     eq_u_true(E, x, u, 1, 0);
                 } else {
-                    path_net_forward(P, a.nA, S.vecA, x, raw);
-                    if (a.nA.ekn_head) ekn_head_fwd(raw, u, a.nA.mctrl, 1, 0);
+                    path_net_forward(P, nA, S.vecA, x, raw);
+                    if (nA.ekn_head) ekn_head_fwd(raw, u, nA.mctrl, 1, 0);
                     else for (int j = 0; j < E.m; ++j) u[j] = raw[j];
                 }
-                if (td1) path_net_forward(P, a.nG, S.vecG, x, g);
+                if (td1) path_net_forward(P, nG, S.vecG, x, g);
                 float* tr = traj + (size_t)t * 2 * sr * TC_PATHS;
                 if (need_grad && td1)
                     for (int k = 0; k < d; ++k) tr[k * TC_PATHS + row] = x[k];
@@ -281,39 +312,41 @@ __global__ void __launch_bounds__(TC_THREADS, 1) critic_tc_kernel(const TcArgs a
         if (is_ctrl) {
             ctrl_flush(C);
             if (!need_grad) {
-                sched_add_fwd(C.sch, a.nV, a.imgV, a.nV.L);
-                for (int i = 0; i < 3; ++i) ctrl_net_forward(C, a.nV, a.nV.L);
+                sched_add_fwd(C.sch, nV, a.imgV, nV.L);
+                ctrl_sched_ready(C);
+                for (int i = 0; i < 3; ++i) ctrl_net_forward(C, nV, nV.L);
             } else {
-                sched_add_fwd(C.sch, a.nV, a.imgV, a.nV.L);                       // V(x_0), forward only
-                for (int i = 0; i < 3; ++i) { sched_add_fwd(C.sch, a.nV, a.imgV, a.nV.L); sched_add_bwd(C.sch, a.nV, a.imgV); }
-                ctrl_net_forward(C, a.nV, a.nV.L);
-                for (int i = 0; i < 3; ++i) { ctrl_net_forward(C, a.nV, a.nV.L); ctrl_net_backward(C, a.nV, true, copies); }
+                sched_add_fwd(C.sch, nV, a.imgV, nV.L);                       // V(x_0), forward only
+                for (int i = 0; i < 3; ++i) { sched_add_fwd(C.sch, nV, a.imgV, nV.L); sched_add_bwd(C.sch, nV, a.imgV); }
+                ctrl_sched_ready(C);
+                ctrl_net_forward(C, nV, nV.L);
+                for (int i = 0; i < 3; ++i) { ctrl_net_forward(C, nV, nV.L); ctrl_net_backward(C, nV, true, copies); }
             }
         } else if (is_path) {
             float vN[1], v0[1], vb[1], x0v[32], xbv[32], dy0[32], cot[1];
             for (int k = 0; k < d; ++k) x0v[k] = valid ? a.x0[gp * d + k] : fill;
             for (int k = 0; k < d; ++k) xbv[k] = valid ? a.xb[gp * d + k] : fill;
             if (!need_grad) {
-                path_net_forward(P, a.nV, S.vecV, x0v, v0);
-                path_net_forward(P, a.nV, S.vecV, x, vN);
-                path_net_forward(P, a.nV, S.vecV, xbv, vb);
+                path_net_forward(P, nV, S.vecV, x0v, v0);
+                path_net_forward(P, nV, S.vecV, x, vN);
+                path_net_forward(P, nV, S.vecV, xbv, vb);
             } else {
                 Masks mk;
-                path_net_forward(P, a.nV, S.vecV, x0v, v0);
-                path_net_forward_keep(P, a.nV, S.vecV, x, vN, mk, copies, S.act, row, false);
+                path_net_forward(P, nV, S.vecV, x0v, v0);
+                path_net_forward_keep(P, nV, S.vecV, x, vN, mk, copies, S.act, row, false);
                 const float delta = v0[0] - y - vN[0] * disc;
                 rhog = valid ? rho_grad(delta, 50.f) * scale : 0.f;
                 cot[0] = -rhog * disc;
-                path_net_backward(P, a.nV, a.gV, mk, cot, true, gsV, S.dz, row, dy0);
+                path_net_backward(P, nV, gV, mk, cot, true, gsV, S.dz, row, dy0);
                 for (int k = 0; k < d; ++k) { sxV[k] += x[k] * dy0[k]; s0V[k] += dy0[k]; }
-                path_net_forward_keep(P, a.nV, S.vecV, x0v, v0, mk, copies, S.act, row, false);
+                path_net_forward_keep(P, nV, S.vecV, x0v, v0, mk, copies, S.act, row, false);
                 cot[0] = rhog;
-                path_net_backward(P, a.nV, a.gV, mk, cot, true, gsV, S.dz, row, dy0);
+                path_net_backward(P, nV, gV, mk, cot, true, gsV, S.dz, row, dy0);
                 for (int k = 0; k < d; ++k) { sxV[k] += x0v[k] * dy0[k]; s0V[k] += dy0[k]; }
-                path_net_forward_keep(P, a.nV, S.vecV, xbv, vb, mk, copies, S.act, row, false);
+                path_net_forward_keep(P, nV, S.vecV, xbv, vb, mk, copies, S.act, row, false);
                 const float dbb = vb[0] - eq_Z(E, xbv, 1, 0);
                 cot[0] = valid ? rho_grad(dbb, 50.f) * scale : 0.f;
-                path_net_backward(P, a.nV, a.gV, mk, cot, true, gsV, S.dz, row, dy0);
+                path_net_backward(P, nV, gV, mk, cot, true, gsV, S.dz, row, dy0);
                 for (int k = 0; k < d; ++k) { sxV[k] += xbv[k] * dy0[k]; s0V[k] += dy0[k]; }
             }
             const float delta = v0[0] - y - vN[0] * disc;                         // solver.py:189
@@ -331,11 +364,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) critic_tc_kernel(const TcArgs a
         if (need_grad && td1) {
             if (is_ctrl) {
                 ctrl_flush(C);
-                sched_add_fwd(C.sch, a.nG, a.imgG, a.nG.L - 1);
-                sched_add_bwd(C.sch, a.nG, a.imgG);
+                sched_add_fwd(C.sch, nG, a.imgG, nG.L - 1);
+                sched_add_bwd(C.sch, nG, a.imgG);
+                ctrl_sched_ready(C);
                 for (int t = 0; t < tlive; ++t) {
-                    ctrl_net_forward(C, a.nG, a.nG.L - 1);
-                    ctrl_net_backward(C, a.nG, true, copies);
+                    ctrl_net_forward(C, nG, nG.L - 1);
+                    ctrl_net_backward(C, nG, true, copies);
                 }
             } else if (is_path) {
                 Masks mk;
@@ -343,8 +377,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) critic_tc_kernel(const TcArgs a
                 for (int t = 0; t < tlive; ++t) {
                     const float* tr = traj + (size_t)t * 2 * sr * TC_PATHS;
                     for (int k = 0; k < d; ++k) { xt[k] = tr[k * TC_PATHS + row]; cot[k] = tr[(sr + k) * TC_PATHS + row] * rhog; }
-                    path_net_forward_keep(P, a.nG, S.vecG, xt, (float*)nullptr, mk, copies, S.act, row, true);
-                    path_net_backward(P, a.nG, a.gG, mk, cot, true, gsG, S.dz, row, dy0);
+                    path_net_forward_keep(P, nG, S.vecG, xt, (float*)nullptr, mk, copies, S.act, row, true);
+                    path_net_backward(P, nG, gG, mk, cot, true, gsG, S.dz, row, dy0);
                     for (int k = 0; k < d; ++k) { sxG[k] += xt[k] * dy0[k]; s0G[k] += dy0[k]; }
                 }
             }
@@ -352,17 +386,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) critic_tc_kernel(const TcArgs a
     }
     if (is_ctrl) ctrl_flush(C);
     if (need_grad) {
-        reduce_rows_to(gsV + a.gV.gX, sxV, d, is_path);
-        reduce_rows_to(gsV + a.gV.g0, s0V, d, is_path);
+        reduce_rows_to(gsV + gV.gX, sxV, d, is_path);
+        reduce_rows_to(gsV + gV.g0, s0V, d, is_path);
         if (td1) {
-            reduce_rows_to(gsG + a.gG.gX, sxG, d, is_path);
-            reduce_rows_to(gsG + a.gG.g0, s0G, d, is_path);
+            reduce_rows_to(gsG + gG.gX, sxG, d, is_path);
+            reduce_rows_to(gsG + gG.g0, s0G, d, is_path);
         }
     }
     if (tid == 0 && a.loss_part) {
         a.loss_part[blockIdx.x * 2] = loss0;
         a.loss_part[blockIdx.x * 2 + 1] = loss1;
     }
+    roles_stats(R, a, t_start);
     tc_fence_before();
     __syncthreads();
     if (warp == 4) tmem_dealloc(tmem, 512);
@@ -376,8 +411,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) actor_tc_kernel(const TcArgs a)
     const uint32_t tmem = tc_setup(S, a);
     Roles R;
     roles_init(R, S, a, tmem);
+    const long long t_start = clock64();
     Ctrl& C = R.C;
     PathCtx& P = R.P;
+    const TcNet& nA = *S.nA;
+    const TcNet& nV = *S.nV;
+    const TcNet& nG = *S.nG;
+    const TcSlab& gA = *S.gA;
+    const TcSlab& gV = *S.gV;
+    const TcSlab& gG = *S.gG;
+    (void)gA; (void)gV; (void)gG;
     const int tid = threadIdx.x, warp = tid >> 5;
     const bool is_path = R.is_path, is_ctrl = R.is_ctrl;
     const int row = R.row;
@@ -389,7 +432,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) actor_tc_kernel(const TcArgs a)
     const int trs = 2 * sr + A_NSCAL;
     float* traj = a.scratch + (size_t)blockIdx.x * a.scratch_per_cta;               // [N][2*sr + A_NSCAL][128]
     unsigned char* copies = a.copies ? a.copies + (size_t)blockIdx.x * a.copies_per_cta : nullptr;
-    float* gsA = a.slabA ? a.slabA + (size_t)blockIdx.x * a.gA.gtotal : nullptr;
+    float* gsA = a.slabA ? a.slabA + (size_t)blockIdx.x * gA.gtotal : nullptr;
     float sxA[32], s0A[32];
     for (int k = 0; k < 32; ++k) { sxA[k] = 0.f; s0A[k] = 0.f; }
 
@@ -410,7 +453,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) actor_tc_kernel(const TcArgs a)
         }
         if (is_ctrl) {
             ctrl_flush(C);
-            if (!cheat) sched_add_fwd(C.sch, a.nA, a.imgA, a.nA.L);
+            if (!cheat) sched_add_fwd(C.sch, nA, a.imgA, nA.L);
+            ctrl_sched_ready(C);
         }
         // ------------------------------------------------------------------ forward rollout
         int tlive = 0;
@@ -419,7 +463,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) actor_tc_kernel(const TcArgs a)
             if (!alive) break;
             tlive = t + 1;
             if (is_ctrl) {
-                if (!cheat) ctrl_net_forward(C, a.nA, a.nA.L);
+                if (!cheat) ctrl_net_forward(C, nA, nA.L);
             } else if (is_path) {
                 path_dw(a, gp, valid, t, dwv);
                 float dt, sqdt, xn; int dtg;
@@ -427,8 +471,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) actor_tc_kernel(const TcArgs a)
                 if (cheat) {
                     eq_u_true(E, x, u, 1, 0);
                 } else {
-                    path_net_forward(P, a.nA, S.vecA, x, raw);
-                    if (a.nA.ekn_head) ekn_head_fwd(raw, u, a.nA.mctrl, 1, 0);
+                    path_net_forward(P, nA, S.vecA, x, raw);
+                    if (nA.ekn_head) ekn_head_fwd(raw, u, nA.mctrl, 1, 0);
                     else for (int j = 0; j < m; ++j) u[j] = raw[j];
                 }
                 float* tr = traj + (size_t)t * trs * TC_PATHS;
@@ -469,10 +513,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) actor_tc_kernel(const TcArgs a)
         if (is_ctrl) {
             ctrl_flush(C);
             if (!cheat_v) {
-                sched_add_fwd(C.sch, a.nV, a.imgV, a.nV.L);
-                if (need_grad) sched_add_bwd(C.sch, a.nV, a.imgV);
-                ctrl_net_forward(C, a.nV, a.nV.L);
-                if (need_grad) ctrl_net_backward(C, a.nV, false, nullptr);
+                sched_add_fwd(C.sch, nV, a.imgV, nV.L);
+                if (need_grad) sched_add_bwd(C.sch, nV, a.imgV);
+                ctrl_sched_ready(C);
+                ctrl_net_forward(C, nV, nV.L);
+                if (need_grad) ctrl_net_backward(C, nV, false, nullptr);
             }
         } else if (is_path) {
             float vN[1];
@@ -484,14 +529,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) actor_tc_kernel(const TcArgs a)
                     for (int k = 0; k < d; ++k) lam[k] = lam[k] * seed;
                 }
             } else if (!need_grad) {
-                path_net_forward(P, a.nV, S.vecV, x, vN);                         // solver.py:221
+                path_net_forward(P, nV, S.vecV, x, vN);                         // solver.py:221
             } else {
                 Masks mk;
                 float cot[1], dy0[32];
-                path_net_forward_keep(P, a.nV, S.vecV, x, vN, mk, nullptr, nullptr, row, false);
+                path_net_forward_keep(P, nV, S.vecV, x, vN, mk, nullptr, nullptr, row, false);
                 cot[0] = seed;
-                path_net_backward(P, a.nV, a.gV, mk, cot, false, nullptr, nullptr, row, dy0);
-                const float* g0c = S.vecV + a.nV.vec_g0;
+                path_net_backward(P, nV, gV, mk, cot, false, nullptr, nullptr, row, dy0);
+                const float* g0c = S.vecV + nV.vec_g0;
                 for (int k = 0; k < d; ++k) lam[k] = dy0[k] * g0c[k];
             }
             Dbar = valid ? vN[0] * a.invB : 0.f;
@@ -506,8 +551,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) actor_tc_kernel(const TcArgs a)
         // ------------------------------------------------------------------ reverse sweep
         if (is_ctrl) {
             ctrl_flush(C);
-            sched_add_fwd(C.sch, a.nA, a.imgA, a.nA.L);
-            sched_add_bwd(C.sch, a.nA, a.imgA);
+            sched_add_fwd(C.sch, nA, a.imgA, nA.L);
+            sched_add_bwd(C.sch, nA, a.imgA);
+            ctrl_sched_ready(C);
         }
         for (int t = tlive - 1; t >= 0; --t) {
             const float* tr = traj + (size_t)t * trs * TC_PATHS;
@@ -515,26 +561,26 @@ __global__ void __launch_bounds__(TC_THREADS, 1) actor_tc_kernel(const TcArgs a)
             const int any = __syncthreads_or(valid && sc[A_COEF * TC_PATHS + row] > 0.f);
             if (!any) continue;
             if (is_ctrl) {
-                ctrl_net_forward(C, a.nA, a.nA.L);
-                ctrl_net_backward(C, a.nA, true, copies);
+                ctrl_net_forward(C, nA, nA.L);
+                ctrl_net_backward(C, nA, true, copies);
             } else if (is_path) {
                 Masks mk;
                 float xt[32], ubar[32], cot[32], dy0[32];
                 for (int k = 0; k < d; ++k) { xt[k] = tr[k * TC_PATHS + row]; dwv[k] = tr[(sr + k) * TC_PATHS + row]; }
-                path_net_forward_keep(P, a.nA, S.vecA, xt, raw, mk, copies, S.act, row, false);
-                if (a.nA.ekn_head) ekn_head_fwd(raw, u, a.nA.mctrl, 1, 0);
+                path_net_forward_keep(P, nA, S.vecA, xt, raw, mk, copies, S.act, row, false);
+                if (nA.ekn_head) ekn_head_fwd(raw, u, nA.mctrl, 1, 0);
                 else for (int j = 0; j < m; ++j) u[j] = raw[j];
                 const int coef = (valid && sc[A_COEF * TC_PATHS + row] > 0.f) ? 1 : 0;
                 adj_step(E, xt, u, dwv, sc[A_DT * TC_PATHS + row], sc[A_SQDT * TC_PATHS + row], coef, (int)sc[A_DTG * TC_PATHS + row],
                          sc[A_XN * TC_PATHS + row], sc[A_DISC * TC_PATHS + row], a.invB, lam, Dbar, ubar, 1, 0);
-                if (a.nA.ekn_head) {
+                if (nA.ekn_head) {
                     if (coef) ekn_head_bwd(raw, ubar, cot, m, 1, 0);
                     else for (int j = 0; j <= m; ++j) cot[j] = 0.f;
                 } else {
                     for (int j = 0; j < m; ++j) cot[j] = ubar[j];
                 }
-                path_net_backward(P, a.nA, a.gA, mk, cot, true, gsA, S.dz, row, dy0);
-                const float* g0c = S.vecA + a.nA.vec_g0;
+                path_net_backward(P, nA, gA, mk, cot, true, gsA, S.dz, row, dy0);
+                const float* g0c = S.vecA + nA.vec_g0;
                 for (int k = 0; k < d; ++k) {
                     sxA[k] += xt[k] * dy0[k]; s0A[k] += dy0[k];
                     lam[k] = lam[k] + dy0[k] * g0c[k];
@@ -544,13 +590,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) actor_tc_kernel(const TcArgs a)
     }
     if (is_ctrl) ctrl_flush(C);
     if (need_grad) {
-        reduce_rows_to(gsA + a.gA.gX, sxA, d, is_path);
-        reduce_rows_to(gsA + a.gA.g0, s0A, d, is_path);
+        reduce_rows_to(gsA + gA.gX, sxA, d, is_path);
+        reduce_rows_to(gsA + gA.g0, s0A, d, is_path);
     }
     if (tid == 0 && a.loss_part) {
         a.loss_part[blockIdx.x * 2] = loss0;
         a.loss_part[blockIdx.x * 2 + 1] = 0.f;
     }
+    roles_stats(R, a, t_start);
     tc_fence_before();
     __syncthreads();
     if (warp == 4) tmem_dealloc(tmem, 512);

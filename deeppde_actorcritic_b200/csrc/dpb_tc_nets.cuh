@@ -140,35 +140,48 @@ struct Ctrl {
     int pf_op, pf_ch;
     uint32_t nslot, slot_bytes;
     uint32_t n_loaded, n_consumed, op_count, act_count, tmem;
+    uint32_t ld_slot, ld_use, mm_slot, mm_use;      // ring cursors (slot index, wrap count) of the loader and of the MMA issuer
+    const unsigned char* cur_ptr; int cur_nch, cur_cb, nops;   // schedule entry under the prefetch cursor (registers)
     unsigned char *act, *dz;         // shared-memory operand images of the dW products (128 paths x K16 features, bf16)
+    long long t_aready, t_full, t_issue, t_accw, n_ops;   // cycle counters (diagnostics)
 };
 
+// Top the ring up.  Never blocks: a slot whose previous occupant is still being read by the tensor
+// pipe is left for the next call (blocking here would serialise MMA issue with MMA completion).
 __device__ __forceinline__ void ctrl_prefetch(Ctrl& c) {
-    if (c.sch->nops == 0) return;
+    if (c.nops == 0) return;
     while (c.n_loaded - c.n_consumed < c.nslot) {
-        const uint32_t slot = c.n_loaded % c.nslot, use = c.n_loaded / c.nslot;
-        if (use > 0) mbar_wait(&c.empty[slot], (use - 1) & 1);
-        const uint32_t bytes = (uint32_t)c.sch->cb[c.pf_op];
+        const uint32_t slot = c.ld_slot, use = c.ld_use;
+        if (use > 0 && !mbar_try(&c.empty[slot], (use - 1) & 1)) return;
+        const uint32_t bytes = (uint32_t)c.cur_cb;
         mbar_arrive_expect_tx(&c.full[slot], bytes);
-        bulk_g2s(c.ring + (size_t)slot * c.slot_bytes, c.sch->ptr[c.pf_op] + (size_t)c.pf_ch * bytes, bytes, &c.full[slot]);
-        if (++c.pf_ch == c.sch->nch[c.pf_op]) {
+        bulk_g2s(c.ring + (size_t)slot * c.slot_bytes, c.cur_ptr + (size_t)c.pf_ch * bytes, bytes, &c.full[slot]);
+        if (++c.pf_ch == c.cur_nch) {
             c.pf_ch = 0;
-            if (++c.pf_op == c.sch->nops) c.pf_op = 0;
+            if (++c.pf_op == c.nops) c.pf_op = 0;
+            c.cur_ptr = c.sch->ptr[c.pf_op]; c.cur_nch = c.sch->nch[c.pf_op]; c.cur_cb = c.sch->cb[c.pf_op];
         }
         ++c.n_loaded;
+        if (++c.ld_slot == c.nslot) { c.ld_slot = 0; ++c.ld_use; }
     }
+}
+// call after the schedule of a phase has been written
+__device__ __forceinline__ void ctrl_sched_ready(Ctrl& c) {
+    c.nops = c.sch->nops; c.pf_op = 0; c.pf_ch = 0;
+    if (c.nops > 0) { c.cur_ptr = c.sch->ptr[0]; c.cur_nch = c.sch->nch[0]; c.cur_cb = c.sch->cb[0]; }
 }
 
 // drop every chunk that was streamed ahead but will not be used (end of a phase / dead tile)
 __device__ __forceinline__ void ctrl_flush(Ctrl& c) {
     while (c.n_consumed != c.n_loaded) {
-        const uint32_t slot = c.n_consumed % c.nslot, use = c.n_consumed / c.nslot;
-        mbar_wait(&c.full[slot], use & 1);
-        mbar_arrive(&c.empty[slot]);
+        mbar_wait(&c.full[c.mm_slot], c.mm_use & 1);
+        mbar_arrive(&c.empty[c.mm_slot]);
         ++c.n_consumed;
+        if (++c.mm_slot == c.nslot) { c.mm_slot = 0; ++c.mm_use; }
     }
     c.pf_op = 0; c.pf_ch = 0;
     c.sch->nops = 0;
+    c.nops = 0;
 }
 
 __device__ __forceinline__ void sched_add(Sched* s, const unsigned char* p, int nch, int cb) {
@@ -179,29 +192,38 @@ __device__ __forceinline__ void sched_add_fwd(Sched* s, const TcNet& t, const un
 }
 
 // D[acc] = A(planes in TMEM) x B(streamed image with R rows): nchunks contraction chunks, 3 split products
-__device__ __forceinline__ void ctrl_gemm_ts(Ctrl& c, int nchunks, int R) {
+__device__ __forceinline__ void ctrl_gemm_ts(Ctrl& cref, int nchunks, int R) {
+    Ctrl c = cref;                                                       // registers for the issue loop
     const uint32_t idesc = idesc_bf16(128, R, 0, 0);
-    ctrl_prefetch(c);
-    mbar_wait(c.a_ready, c.op_count & 1);
+    const long long t0 = clock64();
+    while (!mbar_try(c.a_ready, c.op_count & 1)) ctrl_prefetch(c);       // stream ahead while the path threads work
+    c.t_aready += clock64() - t0;
+    ++c.n_ops;
     tc_fence_after();
+    const uint32_t lbo = (R >> 3) * 128;
+    const uint64_t dlo = ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) | ((uint64_t)(128 >> 4) << 32) | (1ull << 46);
+    const uint32_t ring0 = smem_u32(c.ring);
     for (int s = 0; s < nchunks; ++s) {
-        const uint32_t slot = c.n_consumed % c.nslot, use = c.n_consumed / c.nslot;
-        mbar_wait(&c.full[slot], use & 1);
-        const uint32_t sb = smem_u32(c.ring + (size_t)slot * c.slot_bytes);
-        const uint64_t bhi = smem_desc(sb, (R >> 3) * 128, 128), blo = smem_desc(sb + R * 32, (R >> 3) * 128, 128);
+        ctrl_prefetch(c);
+        const uint32_t slot = c.mm_slot;
+        while (c.n_loaded == c.n_consumed) ctrl_prefetch(c);             // nothing in flight: this chunk must be loaded now
+        mbar_wait(&c.full[slot], c.mm_use & 1);
+        const uint32_t sb = ring0 + slot * c.slot_bytes;
+        const uint64_t bhi = dlo | (uint64_t)((sb >> 4) & 0x3FFF), blo = dlo | (uint64_t)(((sb + R * 32) >> 4) & 0x3FFF);
         const uint32_t ahi = c.tmem + COL_AHI + s * 8, alo = c.tmem + COL_ALO + s * 8;
         mma_ts(c.tmem + COL_ACC, ahi, bhi, idesc, s > 0);
         mma_ts(c.tmem + COL_ACC, ahi, blo, idesc, 1);
         mma_ts(c.tmem + COL_ACC, alo, bhi, idesc, 1);
         tc_commit(&c.empty[slot]);
         ++c.n_consumed;
-        ctrl_prefetch(c);
+        if (++c.mm_slot == c.nslot) { c.mm_slot = 0; ++c.mm_use; }
     }
     tc_commit(c.acc_full);
     ++c.op_count;
+    cref = c;
 }
 
-__device__ __forceinline__ void ctrl_net_forward(Ctrl& c, const TcNet& t, int upto) {
+__device__ __noinline__ void ctrl_net_forward(Ctrl& c, const TcNet& t, int upto) {
     for (int l = 0; l <= upto; ++l) ctrl_gemm_ts(c, t.ly[l].K16 / 16, t.ly[l].N16);
 }
 
@@ -210,32 +232,81 @@ struct PathCtx {
     uint32_t tl;                   // TMEM address of this thread's lane (column 0)
     uint64_t *acc_full, *a_ready;
     uint32_t op_count;
+    long long t_accw, t_mark;      // cycles spent waiting for the tensor pipe; time of the last wake-up (diagnostics)
+    long long t_epi;
 };
 
 __device__ __forceinline__ void path_publish(PathCtx& p) {   // A planes written and accumulator drained
     tmem_st_wait();
     tc_fence_before();
     mbar_arrive(p.a_ready);
+    p.t_epi += clock64() - p.t_mark;
 }
 __device__ __forceinline__ void path_wait_acc(PathCtx& p) {
+    const long long t0 = clock64();
     mbar_wait(p.acc_full, p.op_count & 1);
+    p.t_mark = clock64();
+    p.t_accw += p.t_mark - t0;
     tc_fence_after();
     ++p.op_count;
 }
 
+// 16 floats -> 8 packed hi words + 8 packed lo words (hi = bf16(x), lo = bf16(x - hi); element 2j in bits 0..15)
+__device__ __forceinline__ void split16(const float* v, uint32_t* h, uint32_t* l) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const __nv_bfloat162 hh = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+        const uint32_t hb = *reinterpret_cast<const uint32_t*>(&hh);
+        const float r0 = v[2 * j] - __uint_as_float(hb << 16);
+        const float r1 = v[2 * j + 1] - __uint_as_float(hb & 0xffff0000u);
+        const __nv_bfloat162 ll = __floats2bfloat162_rn(r0, r1);
+        h[j] = hb;
+        l[j] = *reinterpret_cast<const uint32_t*>(&ll);
+    }
+}
 // features 16c .. 16c+15 of this thread's row -> hi / lo planes
 __device__ __forceinline__ void put16(uint32_t tl, int c, const float* v) {
     uint32_t h[8], l[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        __nv_bfloat16 h0, l0, h1, l1;
-        split_bf16(v[2 * j], h0, l0);
-        split_bf16(v[2 * j + 1], h1, l1);
-        h[j] = pack2(h0, h1);
-        l[j] = pack2(l0, l1);
-    }
+    split16(v, h, l);
     tmem_st8(tl + COL_AHI + c * 8, h);
     tmem_st8(tl + COL_ALO + c * 8, l);
+}
+// same, also returning the hi words (for the bf16 copies)
+__device__ __forceinline__ void put16h(uint32_t tl, int c, const float* v, uint32_t* h) {
+    uint32_t l[8];
+    split16(v, h, l);
+    tmem_st8(tl + COL_AHI + c * 8, h);
+    tmem_st8(tl + COL_ALO + c * 8, l);
+}
+
+// accumulator columns [0, 16*nchunks) of this thread's lane, 16 at a time, the TMEM load of chunk c+1 in
+// flight while chunk c is processed:  f(c, const uint32_t r[16])
+template <class F>
+__device__ __forceinline__ void for_acc_chunks(uint32_t tl, int nchunks, F f) {
+    uint32_t ra[16], rb[16];
+    tmem_ld16(tl + COL_ACC, ra);
+    for (int c = 0; c < nchunks; c += 2) {
+        tmem_ld_wait();
+        if (c + 1 < nchunks) tmem_ld16(tl + COL_ACC + 16 * (c + 1), rb);
+        f(c, ra);
+        if (c + 1 < nchunks) {
+            tmem_ld_wait();
+            if (c + 2 < nchunks) tmem_ld16(tl + COL_ACC + 16 * (c + 2), ra);
+            f(c + 1, rb);
+        }
+    }
+}
+
+// z = acc * gc + bb for 16 features (gc, bb: 16-byte aligned shared memory)
+__device__ __forceinline__ void affine16(const uint32_t* r, const float* gc, const float* bb, float* z) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const float4 g = reinterpret_cast<const float4*>(gc)[q], b = reinterpret_cast<const float4*>(bb)[q];
+        z[4 * q] = fmaf(__uint_as_float(r[4 * q]), g.x, b.x);
+        z[4 * q + 1] = fmaf(__uint_as_float(r[4 * q + 1]), g.y, b.y);
+        z[4 * q + 2] = fmaf(__uint_as_float(r[4 * q + 2]), g.z, b.z);
+        z[4 * q + 3] = fmaf(__uint_as_float(r[4 * q + 3]), g.w, b.w);
+    }
 }
 
 // y0 = x * g0c + b0 (solver.py:265) -> planes; x: this thread's point (in values)
@@ -260,18 +331,13 @@ __device__ __forceinline__ void path_epi_hidden(PathCtx& p, const float* gcbb, i
     path_wait_acc(p);
     const float* gc = gcbb;
     const float* bb = gcbb + N16;
-    for (int c = 0; c < N16 / 16; ++c) {
-        uint32_t r[16];
-        tmem_ld16(p.tl + COL_ACC + 16 * c, r);
-        tmem_ld_wait();
+    for_acc_chunks(p.tl, N16 / 16, [&](int c, const uint32_t* r) {
         float v[16];
+        affine16(r, gc + 16 * c, bb + 16 * c, v);
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-            const float z = __uint_as_float(r[j]) * gc[16 * c + j] + bb[16 * c + j];
-            v[j] = z + fmaxf(z, 0.f);
-        }
+        for (int j = 0; j < 16; ++j) v[j] = v[j] + fmaxf(v[j], 0.f);
         put16(p.tl, c, v);
-    }
+    });
     path_publish(p);
 }
 
@@ -293,7 +359,7 @@ __device__ __forceinline__ void path_epi_last(PathCtx& p, const float* gcbb, int
 }
 
 // whole network, forward only: x -> raw output (before the ekn head)
-__device__ __forceinline__ void path_net_forward(PathCtx& p, const TcNet& t, const float* vec, const float* x, float* out) {
+__device__ __noinline__ void path_net_forward(PathCtx& p, const TcNet& t, const float* vec, const float* x, float* out) {
     path_write_y0(p, t, vec, x);
     for (int l = 0; l < t.L; ++l) path_epi_hidden(p, vec + t.ly[l].vec, t.ly[l].N16);
     path_epi_last(p, vec + t.ly[t.L].vec, t.ly[t.L].N16, t.ly[t.L].nl, out);
@@ -380,7 +446,7 @@ __device__ __forceinline__ void ctrl_gemm_dw(Ctrl& c, int blk, int N16) {
 
 // backward of one network evaluation.  need_w: dW products (+ drains on the path side);
 // copies: per-CTA global scratch holding the bf16 copies of a_0..a_{L-1} (a_L is already in ACT).
-__device__ __forceinline__ void ctrl_net_backward(Ctrl& c, const TcNet& t, bool need_w, const unsigned char* copies) {
+__device__ __noinline__ void ctrl_net_backward(Ctrl& c, const TcNet& t, bool need_w, const unsigned char* copies) {
     for (int l = t.L; l >= 0; --l) {
         if (need_w) {
             if (l < t.L) ctrl_act_wait(c);
@@ -398,15 +464,15 @@ __device__ __forceinline__ void ctrl_net_backward(Ctrl& c, const TcNet& t, bool 
 // ---- path threads ------------------------------------------------------------------------------------
 struct Masks { uint32_t m[MAXLIN][8]; };     // m[l] bit k: a_l[k] > 0  (l = 1..L), K16 <= 256
 
-// 16 features 16c.. of this thread's row -> bf16 image (R = 128 rows) at `img` (shared or global)
-__device__ __forceinline__ void copy16(unsigned char* img, int row, int c, const float* v, int one_at /* feature index set to 1, or -1 */) {
-    uint32_t w[8];
+// 16 features 16c.. of this thread's row (packed bf16 hi words) -> image (R = 128 rows) at `img` (shared or global)
+__device__ __forceinline__ void copy16h(unsigned char* img, int row, int c, uint32_t* w, int one_at /* feature index set to 1, or -1 */) {
+    const int o = one_at - 16 * c;
+    if (o >= 0 && o < 16) {                                          // bf16(1.0) = 0x3F80
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        float a = v[2 * j], b = v[2 * j + 1];
-        if (16 * c + 2 * j == one_at) a = 1.f;
-        if (16 * c + 2 * j + 1 == one_at) b = 1.f;
-        w[j] = pack2(__float2bfloat16_rn(a), __float2bfloat16_rn(b));
+        for (int j = 0; j < 8; ++j) {
+            if (o == 2 * j) w[j] = (w[j] & 0xffff0000u) | 0x3F80u;
+            if (o == 2 * j + 1) w[j] = (w[j] & 0x0000ffffu) | 0x3F800000u;
+        }
     }
     unsigned char* p = img + (size_t)(2 * c) * 2048 + (row >> 3) * 128 + (row & 7) * 16;
     *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
@@ -416,7 +482,7 @@ __device__ __forceinline__ void copy16(unsigned char* img, int row, int c, const
 // forward keeping what the backward needs: relu masks (registers), bf16 copies of a_0..a_{L-1} (global
 // scratch `copies`, NULL: none) and of a_L (shared ACT image, NULL: none).  skip_last: stop after the
 // last hidden layer (the raw output is not needed) -- then the caller must write dz_L and publish.
-__device__ __forceinline__ void path_net_forward_keep(PathCtx& p, const TcNet& t, const float* vec, const float* x, float* out, Masks& mk,
+__device__ __noinline__ void path_net_forward_keep(PathCtx& p, const TcNet& t, const float* vec, const float* x, float* out, Masks& mk,
                                                       unsigned char* copies, unsigned char* act, int row, bool skip_last) {
     {
         const int K0 = t.ly[0].K16;
@@ -424,13 +490,14 @@ __device__ __forceinline__ void path_net_forward_keep(PathCtx& p, const TcNet& t
         const float* b0 = g0c + K0;
         for (int c = 0; c < K0 / 16; ++c) {
             float v[16];
+            uint32_t h[8];
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
                 const int k = 16 * c + j;
                 v[j] = (k < t.in) ? x[k] * g0c[k] + b0[k] : 0.f;
             }
-            put16(p.tl, c, v);
-            if (copies) copy16(copies, row, c, v, t.ly[0].kl);
+            put16h(p.tl, c, v, h);
+            if (copies) copy16h(copies, row, c, h, t.ly[0].kl);
         }
         if (copies) fence_proxy_async_all();
         path_publish(p);
@@ -441,23 +508,22 @@ __device__ __forceinline__ void path_net_forward_keep(PathCtx& p, const TcNet& t
         const float* bb = gc + N16;
         const bool last_hidden = (l == t.L - 1);
         unsigned char* dst = last_hidden ? act : (copies ? copies + tc_copy_off(t, l + 1) : nullptr);
+        const int one_at = t.ly[l + 1].kl;
         path_wait_acc(p);
-        for (int c = 0; c < N16 / 16; ++c) {
-            uint32_t r[16];
-            tmem_ld16(p.tl + COL_ACC + 16 * c, r);
-            tmem_ld_wait();
+        for_acc_chunks(p.tl, N16 / 16, [&](int c, const uint32_t* r) {
             float v[16];
+            uint32_t h[8];
+            affine16(r, gc + 16 * c, bb + 16 * c, v);
             uint32_t bits = 0;
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
-                const float z = __uint_as_float(r[j]) * gc[16 * c + j] + bb[16 * c + j];
-                v[j] = z + fmaxf(z, 0.f);
-                bits |= (z > 0.f ? 1u : 0u) << j;
+                bits |= (v[j] > 0.f ? 1u : 0u) << j;
+                v[j] = v[j] + fmaxf(v[j], 0.f);
             }
             if (c & 1) mk.m[l + 1][c >> 1] |= bits << 16; else mk.m[l + 1][c >> 1] = bits;
-            put16(p.tl, c, v);
-            if (dst) copy16(dst, row, c, v, t.ly[l + 1].kl);
-        }
+            put16h(p.tl, c, v, h);
+            if (dst) copy16h(dst, row, c, h, one_at);
+        });
         if (dst) fence_proxy_async_all();
         if (!(last_hidden && skip_last)) path_publish(p);
     }
@@ -497,8 +563,9 @@ __device__ __forceinline__ void path_drain(PathCtx& p, int blk, int row, int kl,
 // cotangent row (N16 values, zero beyond nl) -> planes (+ DZ image)
 __device__ __forceinline__ void path_write_dz(PathCtx& p, const float* dz, int N16, unsigned char* dzimg, int row) {
     for (int c = 0; c < N16 / 16; ++c) {
-        put16(p.tl, c, dz + 16 * c);
-        if (dzimg) copy16(dzimg, row, c, dz + 16 * c, -1);
+        uint32_t h[8];
+        put16h(p.tl, c, dz + 16 * c, h);
+        if (dzimg) copy16h(dzimg, row, c, h, -1);
     }
     if (dzimg) fence_proxy_async();
     path_publish(p);
@@ -506,7 +573,7 @@ __device__ __forceinline__ void path_write_dz(PathCtx& p, const float* dz, int N
 
 // backward of one network evaluation on the path side.  dout: cotangent of the raw output (nl_L values).
 // slab: this CTA's gradient slab of the network (need_w) ; dy0 receives the cotangent of y0 (in values).
-__device__ __forceinline__ void path_net_backward(PathCtx& p, const TcNet& t, const TcSlab& g, const Masks& mk, const float* dout, bool need_w,
+__device__ __noinline__ void path_net_backward(PathCtx& p, const TcNet& t, const TcSlab& g, const Masks& mk, const float* dout, bool need_w,
                                                   float* slab, unsigned char* dzimg, int row, float* dy0) {
     {
         float v[32];
@@ -522,20 +589,18 @@ __device__ __forceinline__ void path_net_backward(PathCtx& p, const TcNet& t, co
         path_wait_acc(p);                                                // dA_l in the accumulator (K16_l columns)
         const int K16 = t.ly[l].K16;
         if (l > 0) {
-            for (int c = 0; c < K16 / 16; ++c) {
-                uint32_t r[16];
-                tmem_ld16(p.tl + COL_ACC + 16 * c, r);
-                tmem_ld_wait();
+            for_acc_chunks(p.tl, K16 / 16, [&](int c, const uint32_t* r) {
                 const uint32_t bits = mk.m[l][c >> 1] >> ((c & 1) * 16);
                 float v[16];
+                uint32_t h[8];
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
                     const float a = __uint_as_float(r[j]);
                     v[j] = ((bits >> j) & 1u) ? 2.f * a : a;                 // d(z + relu z)
                 }
-                put16(p.tl, c, v);
-                if (need_w) copy16(dzimg, row, c, v, -1);
-            }
+                put16h(p.tl, c, v, h);
+                if (need_w) copy16h(dzimg, row, c, h, -1);
+            });
             if (need_w) fence_proxy_async();
             path_publish(p);
         } else {

@@ -209,6 +209,13 @@ class Engine:
         self._chk(rc)
         return dict(loss=loss_h, grad_actor=gA)
 
+    def tc_stats(self, B, N):
+        """cycle counters of CTA 0 of the last tensor-path launch (diagnostics)"""
+        import numpy as np
+        out = np.zeros(16, dtype=np.int64)
+        self._chk(self.lib.dpb_tc_stats(self.handle, C.c_void_p(self._ws.data_ptr()), B, N, out.ctypes.data_as(C.c_void_p)))
+        return out
+
     def last_kernel_ms(self):
         """device time of the most recent critic/actor kernel launch (CUDA events recorded by the library)"""
         return float(self.lib.dpb_last_kernel_ms(self.handle))
