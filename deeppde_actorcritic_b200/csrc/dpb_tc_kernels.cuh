@@ -91,12 +91,12 @@ __device__ __forceinline__ uint32_t tc_setup(TcSmem& s, const TcArgs& a) {
     if (tid == 0) {
         for (int i = 0; i < MAX_NSLOT; ++i) { mbar_init(&s.full[i], 1); mbar_init(&s.empty[i], 1); }
         mbar_init(s.acc_full, 1);
-        mbar_init(s.a_ready, TC_PATHS);
+        mbar_init(s.a_ready, TC_PATH_THREADS);
         mbar_init(s.act_full, 1);
         s.sch->nops = 0;
         fence_barrier_init();
     }
-    if (warp == 4) tmem_alloc(s.tslot, 512);
+    if (warp == TC_CTRL_WARP) tmem_alloc(s.tslot, 512);
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
@@ -155,21 +155,23 @@ __device__ __noinline__ void path_dw(const TcArgs& a, long long gpath_local, boo
 struct Roles {
     Ctrl C;
     PathCtx P;
-    bool is_path, is_ctrl;
+    bool is_path, is_ctrl, primary;      // primary: the path thread of group 0 (does the global stores of its path)
     int row;
 };
 __device__ __forceinline__ void roles_init(Roles& r, const TcSmem& S, const TcArgs& a, uint32_t tmem) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    r.is_path = warp < 4;
-    r.is_ctrl = (warp == 4 && lane == 0);
+    r.is_path = warp < TC_CTRL_WARP;
+    r.is_ctrl = (warp == TC_CTRL_WARP && lane == 0);
+    r.primary = warp < 4;
     r.row = tid & 127;
     Ctrl& C = r.C;
     C.ring = S.ring; C.full = S.full; C.empty = S.empty; C.acc_full = S.acc_full; C.a_ready = S.a_ready; C.sch = S.sch;
     C.pf_op = 0; C.pf_ch = 0; C.n_loaded = 0; C.n_consumed = 0; C.op_count = 0; C.tmem = tmem;
     C.act_full = S.act_full; C.act_count = 0; C.nslot = a.nslot; C.slot_bytes = a.slot_bytes; C.act = S.act; C.dz = S.dz;
-    r.P.tl = tmem + ((uint32_t)(warp * 32) << 16);
+    r.P.tl = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+    r.P.grp = (warp >> 2) & 1;
     r.P.acc_full = S.acc_full; r.P.a_ready = S.a_ready; r.P.op_count = 0;
-    r.P.t_accw = 0; r.P.t_epi = 0; r.P.t_mark = clock64();
+    r.P.t_accw = 0; r.P.t_epi = 0; r.P.t_hid = 0; r.P.t_mark = clock64();
     C.t_aready = 0; C.t_full = 0; C.t_issue = 0; C.t_accw = 0; C.n_ops = 0;
     C.ld_slot = 0; C.ld_use = 0; C.mm_slot = 0; C.mm_use = 0; C.nops = 0; C.cur_ptr = nullptr; C.cur_nch = 0; C.cur_cb = 0;
 }
@@ -178,17 +180,17 @@ __device__ __forceinline__ void roles_init(Roles& r, const TcSmem& S, const TcAr
 __device__ __forceinline__ void roles_stats(const Roles& r, const TcArgs& a, long long t_start) {
     if (!a.stats) return;
     long long* st = a.stats + (size_t)blockIdx.x * 16;
-    if (r.is_ctrl) { st[0] = clock64() - t_start; st[1] = r.C.t_aready; st[2] = r.C.t_full; st[3] = r.C.n_ops; }
-    if (threadIdx.x == 0) { st[4] = r.P.t_accw; st[5] = r.P.t_epi; }
+    if (r.is_ctrl) { st[0] = clock64() - t_start; st[1] = r.C.t_aready; st[2] = r.C.t_full; st[3] = r.C.n_ops; st[7] = r.C.t_issue; st[8] = r.C.t_accw; }
+    if (threadIdx.x == 0) { st[4] = r.P.t_accw; st[5] = r.P.t_epi; st[6] = r.P.t_hid; }
 }
 
 // sum over the 128 path threads of per-thread accumulators acc[0..n) -> atomicAdd into dst (kernel end)
-__device__ __forceinline__ void reduce_rows_to(float* dst, const float* acc, int n, bool is_path) {
+__device__ __forceinline__ void reduce_rows_to(float* dst, const float* acc, int n, bool primary) {
     for (int k = 0; k < n; ++k) {
-        float v = is_path ? acc[k] : 0.f;
+        float v = primary ? acc[k] : 0.f;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        if (is_path && (threadIdx.x & 31) == 0) atomicAdd(dst + k, v);
+        if (primary && (threadIdx.x & 31) == 0) atomicAdd(dst + k, v);
     }
 }
 
@@ -211,7 +213,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) critic_tc_kernel(const TcArgs a
     const TcSlab& gG = *S.gG;
     (void)gA; (void)gV; (void)gG;
     const int tid = threadIdx.x, warp = tid >> 5;
-    const bool is_path = R.is_path, is_ctrl = R.is_ctrl;
+    const bool is_path = R.is_path, is_ctrl = R.is_ctrl, primary = R.primary;
     const int row = R.row;
     const Eq<float> E(a.eq);
     const int d = E.d, N = a.N, sr = a.sr;
@@ -233,13 +235,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) critic_tc_kernel(const TcArgs a
         const long long base = tile * TC_PATHS;
         const long long gp = base + row;                          // local path index of this thread
         const bool valid = is_path && gp < a.B_local;
+        const bool wr = valid && primary;               // this thread does the global stores of its path
         float x[32], u[32], dwv[32], sdw[32], g[32], raw[32];
         int flag = 0, nacc = 0;
         float disc = 1.f, y = 0.f;
         if (is_path) {
             for (int k = 0; k < d; ++k) x[k] = valid ? a.x0[gp * d + k] : fill;
             flag = fwd_initial_flag(E, x, 1, 0);
-            if (a.o_x && valid)
+            if (a.o_x && wr)
                 for (int k = 0; k < d; ++k) a.o_x[(gp * d + k) * (long long)(N + 1)] = x[k];
         }
         if (is_ctrl) {                                            // schedule of the rollout
@@ -258,38 +261,41 @@ __global__ void __launch_bounds__(TC_THREADS, 1) critic_tc_kernel(const TcArgs a
                 if (!cheat) ctrl_net_forward(C, nA, nA.L);
                 if (td1) ctrl_net_forward(C, nG, nG.L);
             } else if (is_path) {
+                // per-path arithmetic is placed where the tensor pipe is busy with a first layer
+                if (!cheat) path_net_begin(P, nA, S.vecA, x);
                 path_dw(a, gp, valid, t, dwv);
                 float dt, sqdt, xn; int dtg;
                 fwd_dt(E, x, flag, 1, 0, dt, sqdt, xn, dtg);
                 if (cheat) {
                     eq_u_true(E, x, u, 1, 0);
                 } else {
-                    path_net_forward(P, nA, S.vecA, x, raw);
+                    path_net_finish(P, nA, S.vecA, raw);
                     if (nA.ekn_head) ekn_head_fwd(raw, u, nA.mctrl, 1, 0);
                     else for (int j = 0; j < E.m; ++j) u[j] = raw[j];
                 }
-                if (td1) path_net_forward(P, nG, S.vecG, x, g);
+                if (td1) path_net_begin(P, nG, S.vecG, x);                        // NN_value_grad at x_t (before the move)
                 float* tr = traj + (size_t)t * 2 * sr * TC_PATHS;
-                if (need_grad && td1)
+                if (need_grad && td1 && primary)
                     for (int k = 0; k < d; ++k) tr[k * TC_PATHS + row] = x[k];
                 float w = 0.f;
                 if (!prop_only) w = eq_w(E, x, u, 1, 0);
                 const int coef = fwd_move(E, x, u, dwv, dt, sqdt, xn, flag, sdw, 1, 0);
                 const float cf = (float)coef;
+                if (td1) path_net_finish(P, nG, S.vecG, g);
                 y = y + w * disc * cf * dt;                                       // solver.py:170-174
                 if (td1) {
                     float dif = 0.f;
                     for (int k = 0; k < d; ++k) dif = dif + sdw[k] * g[k];        // solver.py:177-182
                     dif = dif * disc;
                     y = y - dif * cf * sqdt;                                      // solver.py:184
-                    if (need_grad) {
+                    if (need_grad && primary) {
                         const float q = disc * cf * sqdt;
                         for (int k = 0; k < d; ++k) tr[(sr + k) * TC_PATHS + row] = sdw[k] * q;
                     }
                 }
                 disc = disc * expf(-E.gamma * dt * cf);                          // solver.py:187
                 nacc += coef;
-                if (valid) {
+                if (wr) {
                     if (a.o_dt) a.o_dt[gp * N + t] = dt;
                     if (a.o_coef) a.o_coef[gp * N + t] = cf;
                     if (a.o_x)
@@ -297,7 +303,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) critic_tc_kernel(const TcArgs a
                 }
             }
         }
-        if (valid) {
+        if (wr) {
             for (int t = tlive; t < N; ++t) {
                 if (a.o_dt) a.o_dt[gp * N + t] = E.delta_t;
                 if (a.o_coef) a.o_coef[gp * N + t] = 0.f;
@@ -351,7 +357,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) critic_tc_kernel(const TcArgs a
             }
             const float delta = v0[0] - y - vN[0] * disc;                         // solver.py:189
             const float db = vb[0] - eq_Z(E, xbv, 1, 0);                          // solver.py:190
-            if (valid) {
+            if (wr) {
                 rho_v = rho(delta, 50.f);
                 rho_b = rho(db, 50.f);
                 if (a.o_delta) a.o_delta[gp] = delta;
@@ -386,11 +392,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) critic_tc_kernel(const TcArgs a
     }
     if (is_ctrl) ctrl_flush(C);
     if (need_grad) {
-        reduce_rows_to(gsV + gV.gX, sxV, d, is_path);
-        reduce_rows_to(gsV + gV.g0, s0V, d, is_path);
+        reduce_rows_to(gsV + gV.gX, sxV, d, primary);
+        reduce_rows_to(gsV + gV.g0, s0V, d, primary);
         if (td1) {
-            reduce_rows_to(gsG + gG.gX, sxG, d, is_path);
-            reduce_rows_to(gsG + gG.g0, s0G, d, is_path);
+            reduce_rows_to(gsG + gG.gX, sxG, d, primary);
+            reduce_rows_to(gsG + gG.g0, s0G, d, primary);
         }
     }
     if (tid == 0 && a.loss_part) {
@@ -400,7 +406,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) critic_tc_kernel(const TcArgs a
     roles_stats(R, a, t_start);
     tc_fence_before();
     __syncthreads();
-    if (warp == 4) tmem_dealloc(tmem, 512);
+    if (warp == TC_CTRL_WARP) tmem_dealloc(tmem, 512);
 }
 
 // =================================================================================== actor (tensor)
@@ -422,7 +428,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) actor_tc_kernel(const TcArgs a)
     const TcSlab& gG = *S.gG;
     (void)gA; (void)gV; (void)gG;
     const int tid = threadIdx.x, warp = tid >> 5;
-    const bool is_path = R.is_path, is_ctrl = R.is_ctrl;
+    const bool is_path = R.is_path, is_ctrl = R.is_ctrl, primary = R.primary;
     const int row = R.row;
     const Eq<float> E(a.eq);
     const int d = E.d, m = E.m, N = a.N, sr = a.sr;
@@ -442,13 +448,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) actor_tc_kernel(const TcArgs a)
         const long long base = tile * TC_PATHS;
         const long long gp = base + row;
         const bool valid = is_path && gp < a.B_local;
+        const bool wr = valid && primary;               // this thread does the global stores of its path
         float x[32], u[32], dwv[32], raw[32];
         int flag = 0, nacc = 0;
         float disc = 1.f, y = 0.f;
         if (is_path) {
             for (int k = 0; k < d; ++k) x[k] = valid ? a.x0[gp * d + k] : fill;
             flag = fwd_initial_flag(E, x, 1, 0);
-            if (a.o_x && valid)
+            if (a.o_x && wr)
                 for (int k = 0; k < d; ++k) a.o_x[(gp * d + k) * (long long)(N + 1)] = x[k];
         }
         if (is_ctrl) {
@@ -465,23 +472,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1) actor_tc_kernel(const TcArgs a)
             if (is_ctrl) {
                 if (!cheat) ctrl_net_forward(C, nA, nA.L);
             } else if (is_path) {
+                if (!cheat) path_net_begin(P, nA, S.vecA, x);
                 path_dw(a, gp, valid, t, dwv);
                 float dt, sqdt, xn; int dtg;
                 fwd_dt(E, x, flag, 1, 0, dt, sqdt, xn, dtg);
                 if (cheat) {
                     eq_u_true(E, x, u, 1, 0);
                 } else {
-                    path_net_forward(P, nA, S.vecA, x, raw);
+                    path_net_finish(P, nA, S.vecA, raw);
                     if (nA.ekn_head) ekn_head_fwd(raw, u, nA.mctrl, 1, 0);
                     else for (int j = 0; j < m; ++j) u[j] = raw[j];
                 }
                 float* tr = traj + (size_t)t * trs * TC_PATHS;
-                if (need_grad)
+                if (need_grad && primary)
                     for (int k = 0; k < d; ++k) { tr[k * TC_PATHS + row] = x[k]; tr[(sr + k) * TC_PATHS + row] = dwv[k]; }
                 const float w = eq_w(E, x, u, 1, 0);
                 const int coef = fwd_move(E, x, u, dwv, dt, sqdt, xn, flag, (float*)nullptr, 1, 0);
                 const float cf = (float)coef;
-                if (need_grad) {
+                if (need_grad && primary) {
                     float* sc = tr + (size_t)2 * sr * TC_PATHS;
                     sc[A_DT * TC_PATHS + row] = dt; sc[A_SQDT * TC_PATHS + row] = sqdt; sc[A_COEF * TC_PATHS + row] = valid ? cf : 0.f;
                     sc[A_DISC * TC_PATHS + row] = disc; sc[A_XN * TC_PATHS + row] = xn; sc[A_DTG * TC_PATHS + row] = (float)dtg;
@@ -489,7 +497,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) actor_tc_kernel(const TcArgs a)
                 y = y + cf * w * dt * disc;                                       // solver.py:218
                 disc = disc * expf(-E.gamma * dt * cf);                          // solver.py:219
                 nacc += coef;
-                if (valid) {
+                if (wr) {
                     if (a.o_dt) a.o_dt[gp * N + t] = dt;
                     if (a.o_coef) a.o_coef[gp * N + t] = cf;
                     if (a.o_x)
@@ -497,7 +505,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) actor_tc_kernel(const TcArgs a)
                 }
             }
         }
-        if (valid) {
+        if (wr) {
             for (int t = tlive; t < N; ++t) {
                 if (a.o_dt) a.o_dt[gp * N + t] = E.delta_t;
                 if (a.o_coef) a.o_coef[gp * N + t] = 0.f;
@@ -541,7 +549,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) actor_tc_kernel(const TcArgs a)
             }
             Dbar = valid ? vN[0] * a.invB : 0.f;
             y = y + vN[0] * disc;
-            if (valid) {
+            if (wr) {
                 yv = y;
                 if (a.o_delta) a.o_delta[gp] = y;
             }
@@ -590,8 +598,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) actor_tc_kernel(const TcArgs a)
     }
     if (is_ctrl) ctrl_flush(C);
     if (need_grad) {
-        reduce_rows_to(gsA + gA.gX, sxA, d, is_path);
-        reduce_rows_to(gsA + gA.g0, s0A, d, is_path);
+        reduce_rows_to(gsA + gA.gX, sxA, d, primary);
+        reduce_rows_to(gsA + gA.g0, s0A, d, primary);
     }
     if (tid == 0 && a.loss_part) {
         a.loss_part[blockIdx.x * 2] = loss0;
@@ -600,7 +608,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) actor_tc_kernel(const TcArgs a)
     roles_stats(R, a, t_start);
     tc_fence_before();
     __syncthreads();
-    if (warp == 4) tmem_dealloc(tmem, 512);
+    if (warp == TC_CTRL_WARP) tmem_dealloc(tmem, 512);
 }
 
 }  // namespace tc

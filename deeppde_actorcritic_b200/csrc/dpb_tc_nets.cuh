@@ -1,7 +1,9 @@
 // dpb_tc_nets.cuh -- DeepNN (reference solver.py:227-278) on the 5th-generation tensor cores.
 //
-// One CTA owns a tile of 128 paths; thread t of warps 0-3 ("path threads") owns path t = TMEM lane t;
-// lane 0 of warp 4 (the "control thread") streams the weights and issues every tcgen05.mma.
+// One CTA owns a tile of 128 paths; path t = TMEM lane t is owned by TWO "path threads", t (warps 0-3) and
+// t+128 (warps 4-7): both carry the identical per-path state in registers and each handles every other
+// 16-column chunk of the epilogues; lane 0 of warp 8 (the "control thread") streams the weights and
+// issues every tcgen05.mma.
 //
 //   * Precision: FP32 emulated with bf16 pairs.  Every operand x is carried as hi = bf16(x) and
 //     lo = bf16(x - hi) and a product a*w is formed as ah*wh + ah*wl + al*wh with FP32 accumulation in
@@ -25,7 +27,10 @@ namespace dpb {
 namespace tc {
 
 constexpr int TC_PATHS = 128;
-constexpr int TC_THREADS = 160;                 // 4 path warps + 1 control warp
+constexpr int TC_PATH_THREADS = 256;            // two groups of 4 path warps: thread t and t+128 own the same path (TMEM lane)
+                                                // and split the 16-column chunks of every epilogue between them
+constexpr int TC_CTRL_WARP = 8;
+constexpr int TC_THREADS = 288;                 // 8 path warps + 1 control warp
 constexpr int MAX_NSLOT = 16;                   // ring slots (runtime count: whatever shared memory is left)
 constexpr uint32_t COL_ACC = 0, COL_AHI = 256, COL_ALO = 384;
 constexpr int MAXOPS = 40;
@@ -200,14 +205,19 @@ __device__ __forceinline__ void ctrl_gemm_ts(Ctrl& cref, int nchunks, int R) {
     c.t_aready += clock64() - t0;
     ++c.n_ops;
     tc_fence_after();
+    const long long ti0 = clock64();
     const uint32_t lbo = (R >> 3) * 128;
     const uint64_t dlo = ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) | ((uint64_t)(128 >> 4) << 32) | (1ull << 46);
     const uint32_t ring0 = smem_u32(c.ring);
     for (int s = 0; s < nchunks; ++s) {
-        ctrl_prefetch(c);
+        if ((s & 3) == 0) ctrl_prefetch(c);
         const uint32_t slot = c.mm_slot;
         while (c.n_loaded == c.n_consumed) ctrl_prefetch(c);             // nothing in flight: this chunk must be loaded now
-        mbar_wait(&c.full[slot], c.mm_use & 1);
+        if (!mbar_try(&c.full[slot], c.mm_use & 1)) {
+            const long long tw = clock64();
+            mbar_wait(&c.full[slot], c.mm_use & 1);
+            c.t_full += clock64() - tw;
+        }
         const uint32_t sb = ring0 + slot * c.slot_bytes;
         const uint64_t bhi = dlo | (uint64_t)((sb >> 4) & 0x3FFF), blo = dlo | (uint64_t)(((sb + R * 32) >> 4) & 0x3FFF);
         const uint32_t ahi = c.tmem + COL_AHI + s * 8, alo = c.tmem + COL_ALO + s * 8;
@@ -219,6 +229,10 @@ __device__ __forceinline__ void ctrl_gemm_ts(Ctrl& cref, int nchunks, int R) {
         if (++c.mm_slot == c.nslot) { c.mm_slot = 0; ++c.mm_use; }
     }
     tc_commit(c.acc_full);
+    const long long ti1 = clock64();
+    c.t_issue += ti1 - ti0;
+    mbar_wait(c.acc_full, c.op_count & 1);                               // diagnostics: tail = last issue -> all MMAs complete
+    c.t_accw += clock64() - ti1;
     ++c.op_count;
     cref = c;
 }
@@ -232,8 +246,9 @@ struct PathCtx {
     uint32_t tl;                   // TMEM address of this thread's lane (column 0)
     uint64_t *acc_full, *a_ready;
     uint32_t op_count;
+    int grp;                       // 0: threads 0..127, 1: threads 128..255 (chunk parity this thread handles)
     long long t_accw, t_mark;      // cycles spent waiting for the tensor pipe; time of the last wake-up (diagnostics)
-    long long t_epi;
+    long long t_epi, t_hid;        // t_hid: cycles inside hidden-layer epilogues only
 };
 
 __device__ __forceinline__ void path_publish(PathCtx& p) {   // A planes written and accumulator drained
@@ -282,17 +297,18 @@ __device__ __forceinline__ void put16h(uint32_t tl, int c, const float* v, uint3
 // accumulator columns [0, 16*nchunks) of this thread's lane, 16 at a time, the TMEM load of chunk c+1 in
 // flight while chunk c is processed:  f(c, const uint32_t r[16])
 template <class F>
-__device__ __forceinline__ void for_acc_chunks(uint32_t tl, int nchunks, F f) {
+__device__ __forceinline__ void for_acc_chunks(uint32_t tl, int first, int nchunks, F f) {
     uint32_t ra[16], rb[16];
-    tmem_ld16(tl + COL_ACC, ra);
-    for (int c = 0; c < nchunks; c += 2) {
+    if (first >= nchunks) return;
+    tmem_ld16(tl + COL_ACC + 16 * first, ra);
+    for (int c = first; c < nchunks; c += 4) {
         tmem_ld_wait();
-        if (c + 1 < nchunks) tmem_ld16(tl + COL_ACC + 16 * (c + 1), rb);
+        if (c + 2 < nchunks) tmem_ld16(tl + COL_ACC + 16 * (c + 2), rb);
         f(c, ra);
-        if (c + 1 < nchunks) {
+        if (c + 2 < nchunks) {
             tmem_ld_wait();
-            if (c + 2 < nchunks) tmem_ld16(tl + COL_ACC + 16 * (c + 2), ra);
-            f(c + 1, rb);
+            if (c + 4 < nchunks) tmem_ld16(tl + COL_ACC + 16 * (c + 4), ra);
+            f(c + 2, rb);
         }
     }
 }
@@ -314,7 +330,7 @@ __device__ __forceinline__ void path_write_y0(PathCtx& p, const TcNet& t, const 
     const int K0 = t.ly[0].K16;
     const float* g0c = vec + t.vec_g0;
     const float* b0 = g0c + K0;
-    for (int c = 0; c < K0 / 16; ++c) {
+    for (int c = p.grp; c < K0 / 16; c += 2) {
         float v[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
@@ -329,9 +345,10 @@ __device__ __forceinline__ void path_write_y0(PathCtx& p, const TcNet& t, const 
 // hidden layer epilogue: a = z + relu(z), z = acc * gc + bb (solver.py:267-269) -> planes
 __device__ __forceinline__ void path_epi_hidden(PathCtx& p, const float* gcbb, int N16) {
     path_wait_acc(p);
+    const long long th0 = clock64();
     const float* gc = gcbb;
     const float* bb = gcbb + N16;
-    for_acc_chunks(p.tl, N16 / 16, [&](int c, const uint32_t* r) {
+    for_acc_chunks(p.tl, p.grp, N16 / 16, [&](int c, const uint32_t* r) {
         float v[16];
         affine16(r, gc + 16 * c, bb + 16 * c, v);
 #pragma unroll
@@ -339,6 +356,7 @@ __device__ __forceinline__ void path_epi_hidden(PathCtx& p, const float* gcbb, i
         put16(p.tl, c, v);
     });
     path_publish(p);
+    p.t_hid += clock64() - th0;
 }
 
 // last layer: out[n] = acc * gc + bb (solver.py:270-271), n < nl
@@ -358,13 +376,26 @@ __device__ __forceinline__ void path_epi_last(PathCtx& p, const float* gcbb, int
     }
 }
 
-// whole network, forward only: x -> raw output (before the ekn head)
+// whole network, forward only: x -> raw output (before the ekn head).  Split in two so that the caller can
+// put per-path arithmetic that does not need the output between begin and finish (it then runs while the
+// tensor pipe works on the first layer).
+__device__ __forceinline__ void path_net_begin(PathCtx& p, const TcNet& t, const float* vec, const float* x) {
+    path_write_y0(p, t, vec, x);
+}
+__device__ __noinline__ void path_net_finish(PathCtx& p, const TcNet& t, const float* vec, float* out) {
+    for (int l = 0; l < t.L; ++l) path_epi_hidden(p, vec + t.ly[l].vec, t.ly[l].N16);
+    path_epi_last(p, vec + t.ly[t.L].vec, t.ly[t.L].N16, t.ly[t.L].nl, out);
+}
 __device__ __noinline__ void path_net_forward(PathCtx& p, const TcNet& t, const float* vec, const float* x, float* out) {
     path_write_y0(p, t, vec, x);
     for (int l = 0; l < t.L; ++l) path_epi_hidden(p, vec + t.ly[l].vec, t.ly[l].N16);
     path_epi_last(p, vec + t.ly[t.L].vec, t.ly[t.L].N16, t.ly[t.L].nl, out);
 }
 
+}  // namespace tc
+}  // namespace dpb
+namespace dpb {
+namespace tc {
 
 // ===================================================================================== backward pass
 // Gradient slab of one network on the tensor path (per CTA, FP32):
@@ -484,11 +515,14 @@ __device__ __forceinline__ void copy16h(unsigned char* img, int row, int c, uint
 // last hidden layer (the raw output is not needed) -- then the caller must write dz_L and publish.
 __device__ __noinline__ void path_net_forward_keep(PathCtx& p, const TcNet& t, const float* vec, const float* x, float* out, Masks& mk,
                                                       unsigned char* copies, unsigned char* act, int row, bool skip_last) {
+    for (int l = 0; l <= t.L; ++l)
+#pragma unroll
+        for (int w = 0; w < 8; ++w) mk.m[l][w] = 0u;
     {
         const int K0 = t.ly[0].K16;
         const float* g0c = vec + t.vec_g0;
         const float* b0 = g0c + K0;
-        for (int c = 0; c < K0 / 16; ++c) {
+        for (int c = p.grp; c < K0 / 16; c += 2) {
             float v[16];
             uint32_t h[8];
 #pragma unroll
@@ -510,7 +544,7 @@ __device__ __noinline__ void path_net_forward_keep(PathCtx& p, const TcNet& t, c
         unsigned char* dst = last_hidden ? act : (copies ? copies + tc_copy_off(t, l + 1) : nullptr);
         const int one_at = t.ly[l + 1].kl;
         path_wait_acc(p);
-        for_acc_chunks(p.tl, N16 / 16, [&](int c, const uint32_t* r) {
+        for_acc_chunks(p.tl, p.grp, N16 / 16, [&](int c, const uint32_t* r) {
             float v[16];
             uint32_t h[8];
             affine16(r, gc + 16 * c, bb + 16 * c, v);
@@ -520,7 +554,7 @@ __device__ __noinline__ void path_net_forward_keep(PathCtx& p, const TcNet& t, c
                 bits |= (v[j] > 0.f ? 1u : 0u) << j;
                 v[j] = v[j] + fmaxf(v[j], 0.f);
             }
-            if (c & 1) mk.m[l + 1][c >> 1] |= bits << 16; else mk.m[l + 1][c >> 1] = bits;
+            mk.m[l + 1][c >> 1] |= (c & 1) ? (bits << 16) : bits;
             put16h(p.tl, c, v, h);
             if (dst) copy16h(dst, row, c, h, one_at);
         });
@@ -537,7 +571,7 @@ __device__ __forceinline__ void path_drain(PathCtx& p, int blk, int row, int kl,
     float* dst = slab + (long long)f * nl;
     const bool rowok = f <= kl;
     const bool vec4 = (nl & 3) == 0;
-    for (int c = 0; c < N16 / 16; ++c) {
+    for (int c = p.grp; c < N16 / 16; c += 2) {
         uint32_t r[16];
         tmem_ld16(p.tl + COL_ACC + 16 * c, r);
         tmem_ld_wait();
@@ -562,7 +596,7 @@ __device__ __forceinline__ void path_drain(PathCtx& p, int blk, int row, int kl,
 
 // cotangent row (N16 values, zero beyond nl) -> planes (+ DZ image)
 __device__ __forceinline__ void path_write_dz(PathCtx& p, const float* dz, int N16, unsigned char* dzimg, int row) {
-    for (int c = 0; c < N16 / 16; ++c) {
+    for (int c = p.grp; c < N16 / 16; c += 2) {
         uint32_t h[8];
         put16h(p.tl, c, dz + 16 * c, h);
         if (dzimg) copy16h(dzimg, row, c, h, -1);
@@ -589,7 +623,7 @@ __device__ __noinline__ void path_net_backward(PathCtx& p, const TcNet& t, const
         path_wait_acc(p);                                                // dA_l in the accumulator (K16_l columns)
         const int K16 = t.ly[l].K16;
         if (l > 0) {
-            for_acc_chunks(p.tl, K16 / 16, [&](int c, const uint32_t* r) {
+            for_acc_chunks(p.tl, p.grp, K16 / 16, [&](int c, const uint32_t* r) {
                 const uint32_t bits = mk.m[l][c >> 1] >> ((c & 1) * 16);
                 float v[16];
                 uint32_t h[8];
