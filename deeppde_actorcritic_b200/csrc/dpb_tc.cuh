@@ -61,6 +61,15 @@ __device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity) {
     return done != 0;
 }
 
+// CTA barriers over the first `nthreads` threads only (named barrier 1): the producer warp never joins them
+__device__ __forceinline__ void bar_work_sync(int nthreads) { asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory"); }
+__device__ __forceinline__ int bar_work_or(int pred, int nthreads) {
+    int r;
+    asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.s32 p, %1, 0;\n\tbar.red.or.pred q, 1, %2, p;\n\tselp.s32 %0, 1, 0, q;\n\t}"
+                 : "=r"(r) : "r"(pred), "r"(nthreads) : "memory");
+    return r;
+}
+
 // ------------------------------------------------------------------------------- bulk copy (TMA 1-D)
 // global -> shared, completion counted in bytes on an mbarrier.  16-byte aligned, size % 16 == 0.
 __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {

@@ -41,6 +41,7 @@ struct TcSmem {
     uint64_t *full, *empty, *acc_full, *a_ready, *act_full;
     uint32_t* tslot;
     Sched* sch;
+    ProdCtl* pc;
     float* red;
     TcNet *nA, *nV, *nG;             // shared-memory copies of the network descriptors
     TcSlab *gA, *gV, *gG;
@@ -48,7 +49,7 @@ struct TcSmem {
 
 // everything except the ring
 __host__ __device__ inline size_t tc_smem_fixed(int vfA, int vfV, int vfG, int actdz_bytes) {
-    return 2 * (size_t)actdz_bytes + (size_t)(vfA + vfV + vfG) * 4 + (2 * MAX_NSLOT + 3) * 8 + 64 + sizeof(Sched) + 64 + 3 * sizeof(TcNet) + 3 * sizeof(TcSlab) + 64 + 1024;
+    return 2 * (size_t)actdz_bytes + (size_t)(vfA + vfV + vfG) * 4 + (2 * MAX_NSLOT + 3) * 8 + 64 + sizeof(Sched) + 64 + 64 + 3 * sizeof(TcNet) + 3 * sizeof(TcSlab) + 64 + 1024;
 }
 __host__ __device__ inline size_t tc_smem_bytes(int vfA, int vfV, int vfG, int actdz_bytes, int nslot, int slot_bytes) {
     return tc_smem_fixed(vfA, vfV, vfG, actdz_bytes) + (size_t)nslot * slot_bytes;
@@ -70,6 +71,7 @@ __device__ __forceinline__ void tc_carve(TcSmem& s, unsigned char* base, const T
     s.act_full = reinterpret_cast<uint64_t*>(p); p += 8;
     s.tslot = reinterpret_cast<uint32_t*>(p); p += 64;
     s.sch = reinterpret_cast<Sched*>(p); p += sizeof(Sched);
+    s.pc = reinterpret_cast<ProdCtl*>(p); p += 64;
     s.red = reinterpret_cast<float*>(((uintptr_t)p + 15) & ~(uintptr_t)15);
     p = reinterpret_cast<unsigned char*>(s.red) + 64;
     s.nA = reinterpret_cast<TcNet*>(p); p += sizeof(TcNet);
@@ -94,6 +96,7 @@ __device__ __forceinline__ uint32_t tc_setup(TcSmem& s, const TcArgs& a) {
         mbar_init(s.a_ready, TC_PATH_THREADS);
         mbar_init(s.act_full, 1);
         s.sch->nops = 0;
+        s.pc->req = 0; s.pc->gen = 0; s.pc->quit = 0;
         fence_barrier_init();
     }
     if (warp == TC_CTRL_WARP) tmem_alloc(s.tslot, 512);
@@ -104,15 +107,16 @@ __device__ __forceinline__ uint32_t tc_setup(TcSmem& s, const TcArgs& a) {
     return *s.tslot;
 }
 
+// sum over the work threads (warps 0..8); result valid in thread 0
 __device__ __forceinline__ float tc_block_sum(float v, float* red) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    __syncthreads();
+    bar_work_sync(TC_WORK_THREADS);
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
-    __syncthreads();
+    bar_work_sync(TC_WORK_THREADS);
     float s = 0.f;
     if (threadIdx.x == 0)
-        for (int i = 0; i < TC_THREADS / 32; ++i) s += red[i];
+        for (int i = 0; i < TC_WORK_THREADS / 32; ++i) s += red[i];
     return s;
 }
 
@@ -166,14 +170,14 @@ __device__ __forceinline__ void roles_init(Roles& r, const TcSmem& S, const TcAr
     r.row = tid & 127;
     Ctrl& C = r.C;
     C.ring = S.ring; C.full = S.full; C.empty = S.empty; C.acc_full = S.acc_full; C.a_ready = S.a_ready; C.sch = S.sch;
-    C.pf_op = 0; C.pf_ch = 0; C.n_loaded = 0; C.n_consumed = 0; C.op_count = 0; C.tmem = tmem;
+    C.pc = S.pc; C.n_req = 0; C.n_consumed = 0; C.op_count = 0; C.tmem = tmem;
     C.act_full = S.act_full; C.act_count = 0; C.nslot = a.nslot; C.slot_bytes = a.slot_bytes; C.act = S.act; C.dz = S.dz;
     r.P.tl = tmem + ((uint32_t)((warp & 3) * 32) << 16);
     r.P.grp = (warp >> 2) & 1;
     r.P.acc_full = S.acc_full; r.P.a_ready = S.a_ready; r.P.op_count = 0;
     r.P.t_accw = 0; r.P.t_epi = 0; r.P.t_hid = 0; r.P.t_mark = clock64();
     C.t_aready = 0; C.t_full = 0; C.t_issue = 0; C.t_accw = 0; C.n_ops = 0;
-    C.ld_slot = 0; C.ld_use = 0; C.mm_slot = 0; C.mm_use = 0; C.nops = 0; C.cur_ptr = nullptr; C.cur_nch = 0; C.cur_cb = 0;
+    C.mm_slot = 0; C.mm_use = 0;
 }
 // stats row: [0] kernel cycles, ctrl: [1] waiting for the path threads, [2] waiting for weights, [3] ops;
 // path thread 0: [4] waiting for the tensor pipe, [5] epilogue (wake-up -> publish)
@@ -203,6 +207,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) critic_tc_kernel(const TcArgs a
     Roles R;
     roles_init(R, S, a, tmem);
     const long long t_start = clock64();
+    if ((threadIdx.x >> 5) == TC_PROD_WARP) {                       // producer warp: lane 0 streams weights until told to quit
+        if ((threadIdx.x & 31) == 0) producer_loop(S.ring, S.full, S.empty, S.sch, S.pc, a.nslot, a.slot_bytes);
+        tc_fence_before();
+        __syncthreads();
+        return;
+    }
     Ctrl& C = R.C;
     PathCtx& P = R.P;
     const TcNet& nA = *S.nA;
@@ -254,7 +264,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) critic_tc_kernel(const TcArgs a
         // ------------------------------------------------------------------ sweep 1: rollout
         int tlive = 0;
         for (int t = 0; t < N; ++t) {
-            const int alive = __syncthreads_or(valid && flag > 0);
+            const int alive = bar_work_or(valid && flag > 0, TC_WORK_THREADS);
             if (!alive) break;
             tlive = t + 1;
             if (is_ctrl) {
@@ -390,7 +400,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) critic_tc_kernel(const TcArgs a
             }
         }
     }
-    if (is_ctrl) ctrl_flush(C);
+    if (is_ctrl) { ctrl_flush(C); C.pc->quit = 1; }
     if (need_grad) {
         reduce_rows_to(gsV + gV.gX, sxV, d, primary);
         reduce_rows_to(gsV + gV.g0, s0V, d, primary);
@@ -418,6 +428,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) actor_tc_kernel(const TcArgs a)
     Roles R;
     roles_init(R, S, a, tmem);
     const long long t_start = clock64();
+    if ((threadIdx.x >> 5) == TC_PROD_WARP) {                       // producer warp: lane 0 streams weights until told to quit
+        if ((threadIdx.x & 31) == 0) producer_loop(S.ring, S.full, S.empty, S.sch, S.pc, a.nslot, a.slot_bytes);
+        tc_fence_before();
+        __syncthreads();
+        return;
+    }
     Ctrl& C = R.C;
     PathCtx& P = R.P;
     const TcNet& nA = *S.nA;
@@ -466,7 +482,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) actor_tc_kernel(const TcArgs a)
         // ------------------------------------------------------------------ forward rollout
         int tlive = 0;
         for (int t = 0; t < N; ++t) {
-            const int alive = __syncthreads_or(valid && flag > 0);
+            const int alive = bar_work_or(valid && flag > 0, TC_WORK_THREADS);
             if (!alive) break;
             tlive = t + 1;
             if (is_ctrl) {
@@ -566,7 +582,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) actor_tc_kernel(const TcArgs a)
         for (int t = tlive - 1; t >= 0; --t) {
             const float* tr = traj + (size_t)t * trs * TC_PATHS;
             const float* sc = tr + (size_t)2 * sr * TC_PATHS;
-            const int any = __syncthreads_or(valid && sc[A_COEF * TC_PATHS + row] > 0.f);
+            const int any = bar_work_or(valid && sc[A_COEF * TC_PATHS + row] > 0.f, TC_WORK_THREADS);
             if (!any) continue;
             if (is_ctrl) {
                 ctrl_net_forward(C, nA, nA.L);
@@ -596,7 +612,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) actor_tc_kernel(const TcArgs a)
             }
         }
     }
-    if (is_ctrl) ctrl_flush(C);
+    if (is_ctrl) { ctrl_flush(C); C.pc->quit = 1; }
     if (need_grad) {
         reduce_rows_to(gsA + gA.gX, sxA, d, primary);
         reduce_rows_to(gsA + gA.g0, s0A, d, primary);

@@ -29,8 +29,10 @@ namespace tc {
 constexpr int TC_PATHS = 128;
 constexpr int TC_PATH_THREADS = 256;            // two groups of 4 path warps: thread t and t+128 own the same path (TMEM lane)
                                                 // and split the 16-column chunks of every epilogue between them
-constexpr int TC_CTRL_WARP = 8;
-constexpr int TC_THREADS = 288;                 // 8 path warps + 1 control warp
+constexpr int TC_CTRL_WARP = 8;                 // lane 0: waits for operands, issues every tcgen05.mma
+constexpr int TC_PROD_WARP = 9;                 // lane 0: streams the weight chunks (bulk copies) on its own
+constexpr int TC_WORK_THREADS = 288;            // warps 0..8 take part in the in-loop CTA barriers (named barrier 1)
+constexpr int TC_THREADS = 320;
 constexpr int MAX_NSLOT = 16;                   // ring slots (runtime count: whatever shared memory is left)
 constexpr uint32_t COL_ACC = 0, COL_AHI = 256, COL_ALO = 384;
 constexpr int MAXOPS = 40;
@@ -138,55 +140,81 @@ struct Sched {                       // cyclic chunk schedule of the current pha
     int nops;
 };
 
+// mailbox between the control thread and the producer thread (shared memory)
+struct ProdCtl {
+    volatile uint32_t req;       // chunks requested so far (monotone); the producer loads until loaded == req
+    volatile uint32_t gen;       // bumped whenever a new schedule has been written (the producer restarts its cursor)
+    volatile uint32_t quit;
+};
+
 struct Ctrl {
     unsigned char* ring;
     uint64_t *full, *empty, *acc_full, *a_ready, *act_full;
     Sched* sch;
-    int pf_op, pf_ch;
+    ProdCtl* pc;
     uint32_t nslot, slot_bytes;
-    uint32_t n_loaded, n_consumed, op_count, act_count, tmem;
-    uint32_t ld_slot, ld_use, mm_slot, mm_use;      // ring cursors (slot index, wrap count) of the loader and of the MMA issuer
-    const unsigned char* cur_ptr; int cur_nch, cur_cb, nops;   // schedule entry under the prefetch cursor (registers)
+    uint32_t n_req, n_consumed, op_count, act_count, tmem;
+    uint32_t mm_slot, mm_use;        // ring cursor (slot index, wrap count) of the MMA issuer
     unsigned char *act, *dz;         // shared-memory operand images of the dW products (128 paths x K16 features, bf16)
     long long t_aready, t_full, t_issue, t_accw, n_ops;   // cycle counters (diagnostics)
 };
 
-// Top the ring up.  Never blocks: a slot whose previous occupant is still being read by the tensor
-// pipe is left for the next call (blocking here would serialise MMA issue with MMA completion).
-__device__ __forceinline__ void ctrl_prefetch(Ctrl& c) {
-    if (c.nops == 0) return;
-    while (c.n_loaded - c.n_consumed < c.nslot) {
-        const uint32_t slot = c.ld_slot, use = c.ld_use;
-        if (use > 0 && !mbar_try(&c.empty[slot], (use - 1) & 1)) return;
-        const uint32_t bytes = (uint32_t)c.cur_cb;
-        mbar_arrive_expect_tx(&c.full[slot], bytes);
-        bulk_g2s(c.ring + (size_t)slot * c.slot_bytes, c.cur_ptr + (size_t)c.pf_ch * bytes, bytes, &c.full[slot]);
-        if (++c.pf_ch == c.cur_nch) {
-            c.pf_ch = 0;
-            if (++c.pf_op == c.nops) c.pf_op = 0;
-            c.cur_ptr = c.sch->ptr[c.pf_op]; c.cur_nch = c.sch->nch[c.pf_op]; c.cur_cb = c.sch->cb[c.pf_op];
-        }
-        ++c.n_loaded;
-        if (++c.ld_slot == c.nslot) { c.ld_slot = 0; ++c.ld_use; }
-    }
-}
-// call after the schedule of a phase has been written
-__device__ __forceinline__ void ctrl_sched_ready(Ctrl& c) {
-    c.nops = c.sch->nops; c.pf_op = 0; c.pf_ch = 0;
-    if (c.nops > 0) { c.cur_ptr = c.sch->ptr[0]; c.cur_nch = c.sch->nch[0]; c.cur_cb = c.sch->cb[0]; }
+// let the producer run up to nslot chunks ahead of the MMAs (one shared-memory store, never waits)
+__device__ __forceinline__ void ctrl_request(Ctrl& c) {
+    const uint32_t want = c.n_consumed + c.nslot;
+    if (want != c.n_req) { c.n_req = want; c.pc->req = want; }
 }
 
-// drop every chunk that was streamed ahead but will not be used (end of a phase / dead tile)
+// drop every chunk that was requested ahead but will not be used (end of a phase / dead tile)
 __device__ __forceinline__ void ctrl_flush(Ctrl& c) {
-    while (c.n_consumed != c.n_loaded) {
+    while (c.n_consumed != c.n_req) {
         mbar_wait(&c.full[c.mm_slot], c.mm_use & 1);
         mbar_arrive(&c.empty[c.mm_slot]);
         ++c.n_consumed;
         if (++c.mm_slot == c.nslot) { c.mm_slot = 0; ++c.mm_use; }
     }
-    c.pf_op = 0; c.pf_ch = 0;
     c.sch->nops = 0;
-    c.nops = 0;
+}
+// call after the schedule of a phase has been written (the producer is idle: everything requested was flushed)
+__device__ __forceinline__ void ctrl_sched_ready(Ctrl& c) {
+    __threadfence_block();
+    c.pc->gen = c.pc->gen + 1;
+    __threadfence_block();
+}
+
+// the producer thread: streams the cyclic chunk schedule through the ring as far as requested
+__device__ __forceinline__ void producer_loop(unsigned char* ring, uint64_t* full, uint64_t* empty, Sched* sch, ProdCtl* pc,
+                                              uint32_t nslot, uint32_t slot_bytes) {
+    uint32_t loaded = 0, my_gen = 0, slot = 0, use = 0;
+    int op = 0, ch = 0, nops = 0, cur_nch = 0;
+    uint32_t cur_cb = 0;
+    const unsigned char* cur_ptr = nullptr;
+    for (;;) {
+        const uint32_t r = pc->req;
+        if (loaded == r) {
+            if (pc->quit) break;
+            __nanosleep(32);
+            continue;
+        }
+        __threadfence_block();
+        const uint32_t g = pc->gen;
+        if (g != my_gen) {
+            my_gen = g; op = 0; ch = 0; nops = sch->nops;
+            cur_ptr = sch->ptr[0]; cur_nch = sch->nch[0]; cur_cb = (uint32_t)sch->cb[0];
+        }
+        while (loaded != r) {
+            if (use > 0) mbar_wait(&empty[slot], (use - 1) & 1);
+            mbar_arrive_expect_tx(&full[slot], cur_cb);
+            bulk_g2s(ring + (size_t)slot * slot_bytes, cur_ptr + (size_t)ch * cur_cb, cur_cb, &full[slot]);
+            if (++ch == cur_nch) {
+                ch = 0;
+                if (++op == nops) op = 0;
+                cur_ptr = sch->ptr[op]; cur_nch = sch->nch[op]; cur_cb = (uint32_t)sch->cb[op];
+            }
+            ++loaded;
+            if (++slot == nslot) { slot = 0; ++use; }
+        }
+    }
 }
 
 __device__ __forceinline__ void sched_add(Sched* s, const unsigned char* p, int nch, int cb) {
@@ -200,24 +228,19 @@ __device__ __forceinline__ void sched_add_fwd(Sched* s, const TcNet& t, const un
 __device__ __forceinline__ void ctrl_gemm_ts(Ctrl& cref, int nchunks, int R) {
     Ctrl c = cref;                                                       // registers for the issue loop
     const uint32_t idesc = idesc_bf16(128, R, 0, 0);
+    ctrl_request(c);
     const long long t0 = clock64();
-    while (!mbar_try(c.a_ready, c.op_count & 1)) ctrl_prefetch(c);       // stream ahead while the path threads work
-    c.t_aready += clock64() - t0;
+    mbar_wait(c.a_ready, c.op_count & 1);
+    const long long ti0 = clock64();
+    c.t_aready += ti0 - t0;
     ++c.n_ops;
     tc_fence_after();
-    const long long ti0 = clock64();
     const uint32_t lbo = (R >> 3) * 128;
     const uint64_t dlo = ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) | ((uint64_t)(128 >> 4) << 32) | (1ull << 46);
     const uint32_t ring0 = smem_u32(c.ring);
     for (int s = 0; s < nchunks; ++s) {
-        if ((s & 3) == 0) ctrl_prefetch(c);
         const uint32_t slot = c.mm_slot;
-        while (c.n_loaded == c.n_consumed) ctrl_prefetch(c);             // nothing in flight: this chunk must be loaded now
-        if (!mbar_try(&c.full[slot], c.mm_use & 1)) {
-            const long long tw = clock64();
-            mbar_wait(&c.full[slot], c.mm_use & 1);
-            c.t_full += clock64() - tw;
-        }
+        mbar_wait(&c.full[slot], c.mm_use & 1);
         const uint32_t sb = ring0 + slot * c.slot_bytes;
         const uint64_t bhi = dlo | (uint64_t)((sb >> 4) & 0x3FFF), blo = dlo | (uint64_t)(((sb + R * 32) >> 4) & 0x3FFF);
         const uint32_t ahi = c.tmem + COL_AHI + s * 8, alo = c.tmem + COL_ALO + s * 8;
@@ -227,12 +250,10 @@ __device__ __forceinline__ void ctrl_gemm_ts(Ctrl& cref, int nchunks, int R) {
         tc_commit(&c.empty[slot]);
         ++c.n_consumed;
         if (++c.mm_slot == c.nslot) { c.mm_slot = 0; ++c.mm_use; }
+        ctrl_request(c);
     }
     tc_commit(c.acc_full);
-    const long long ti1 = clock64();
-    c.t_issue += ti1 - ti0;
-    mbar_wait(c.acc_full, c.op_count & 1);                               // diagnostics: tail = last issue -> all MMAs complete
-    c.t_accw += clock64() - ti1;
+    c.t_issue += clock64() - ti0;
     ++c.op_count;
     cref = c;
 }
