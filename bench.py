@@ -274,12 +274,14 @@ def main():
         j = i % pool
         r = eng.critic_step_host(thA, thV, thG, hx0c[j], None, hxbc[j], solver.N_c, solver.T_c, B_global=B, path_offset=lo,
                                  dw_mode=solver._dw_mode, seed=solver.seed, stream_id=(10_000 + i) << 1)
-        gV, gG, _ = solver._allreduce([r["grad_V"], r["grad_G"], r["loss"].to(dev)])
+        gV, gG, lc = solver._allreduce([r["grad_V"], r["grad_G"], r["loss"].to(dev)])
         solver.optimizer_critic.apply_gradients([gV, gG])
         a = eng.actor_step_host(thA, thV, hx0a[j], None, solver.N_a, solver.T_a, B_global=B, path_offset=lo,
                                 dw_mode=solver._dw_mode, seed=solver.seed, stream_id=((10_000 + i) << 1) | 1)
-        gA, _ = solver._allreduce([a["grad_actor"], a["loss"].to(dev)])
+        gA, la = solver._allreduce([a["grad_actor"], a["loss"].to(dev)])
         solver.optimizer_actor.apply_gradients([gA])
+        if world > 1:                                                    # global losses (the per-rank ones are already on the host)
+            return float(lc.sum()), float(la[0])
         return float(r["loss"].sum()), float(a["loss"][0])
 
     for i in range(min(args.warmup, 2)):

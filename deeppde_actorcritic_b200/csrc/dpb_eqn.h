@@ -18,8 +18,10 @@
 
 #if defined(__CUDACC__)
 #define DPB_HD __host__ __device__ __forceinline__
+#define DPB_UNROLL _Pragma("unroll 4")
 #else
 #define DPB_HD inline
+#define DPB_UNROLL
 #endif
 
 namespace dpb {
@@ -77,6 +79,7 @@ DPB_HD double dpb_max(double a, double b) { return fmax(a, b); }
 template <typename real>
 DPB_HD real norm2_path(const real* x, int d, int ld, int p) {
     real s = (real)0;
+    DPB_UNROLL
     for (int k = 0; k < d; ++k) s = s + DPB_AT(x, k) * DPB_AT(x, k);
     return s;
 }
@@ -87,9 +90,11 @@ DPB_HD void eq_u_true(const Eq<real>& E, const real* x, real* u, int ld, int p) 
     const int d = E.d, m = E.m;
     switch (E.eqn) {
     case EQ_LQR:
+        DPB_UNROLL
         for (int k = 0; k < d; ++k) DPB_AT(u, k) = E.cu * DPB_AT(x, k);
         break;
     case EQ_VDP:
+        DPB_UNROLL
         for (int j = 0; j < m; ++j) {
             real x2 = DPB_AT(x, m + j);
             real px2 = DPB_AT(x, m + (j + 1 == m ? 0 : j + 1));
@@ -99,10 +104,12 @@ DPB_HD void eq_u_true(const Eq<real>& E, const real* x, real* u, int ld, int p) 
         break;
     case EQ_EKN: {
         real r = dpb_sqrt(norm2_path(x, d, ld, p));
+        DPB_UNROLL
         for (int k = 0; k < d; ++k) DPB_AT(u, k) = DPB_AT(x, k) / r;
         break;
     }
     default:
+        DPB_UNROLL
         for (int k = 0; k < d; ++k) {
             real xk = DPB_AT(x, k);
             DPB_AT(u, k) = -E.lv_un * xk / (E.lv_ud + E.lv_ue * xk * xk);
@@ -121,6 +128,7 @@ DPB_HD real eq_V_true(const Eq<real>& E, const real* x, int ld, int p) {
         return n2 * E.k;
     case EQ_VDP: {
         real s = (real)0;
+        DPB_UNROLL
         for (int j = 0; j < m; ++j) {
             int jn = (j + 1 == m ? 0 : j + 1);
             s = s + (DPB_AT(x, j) * DPB_AT(x, jn) + DPB_AT(x, m + j) * DPB_AT(x, m + jn));
@@ -148,9 +156,11 @@ DPB_HD void eq_V_grad_true(const Eq<real>& E, const real* x, real* g, int ld, in
     switch (E.eqn) {
     case EQ_LQR:
     case EQ_LQRVAR:
+        DPB_UNROLL
         for (int k = 0; k < d; ++k) DPB_AT(g, k) = (real)2 * E.k * DPB_AT(x, k);
         break;
     case EQ_VDP:
+        DPB_UNROLL
         for (int j = 0; j < m; ++j) {
             int jn = (j + 1 == m ? 0 : j + 1), jp = (j == 0 ? m - 1 : j - 1);
             DPB_AT(g, j) = (real)2 * E.a * DPB_AT(x, j) - E.eps * (DPB_AT(x, jn) + DPB_AT(x, jp));
@@ -160,6 +170,7 @@ DPB_HD void eq_V_grad_true(const Eq<real>& E, const real* x, real* g, int ld, in
     default: {
         real r = dpb_sqrt(norm2_path(x, d, ld, p));
         real c = (real)3 * E.a3 * r - (real)2 * E.a2;
+        DPB_UNROLL
         for (int k = 0; k < d; ++k) DPB_AT(g, k) = c * DPB_AT(x, k);
     }
     }
@@ -172,6 +183,7 @@ DPB_HD real eq_w(const Eq<real>& E, const real* x, const real* u, int ld, int p)
     switch (E.eqn) {
     case EQ_LQR: {
         real s1 = (real)0, s2 = (real)0;
+        DPB_UNROLL
         for (int k = 0; k < d; ++k) {
             s1 = s1 + E.p * (DPB_AT(x, k) * DPB_AT(x, k));
             s2 = s2 + E.q * (DPB_AT(u, k) * DPB_AT(u, k));
@@ -180,6 +192,7 @@ DPB_HD real eq_w(const Eq<real>& E, const real* x, const real* u, int ld, int p)
     }
     case EQ_VDP: {
         real s = (real)0, n2 = (real)0;
+        DPB_UNROLL
         for (int j = 0; j < m; ++j) {
             int jn = (j + 1 == m ? 0 : j + 1), jp = (j == 0 ? m - 1 : j - 1);
             real x1 = DPB_AT(x, j), x2 = DPB_AT(x, m + j);
@@ -198,6 +211,7 @@ DPB_HD real eq_w(const Eq<real>& E, const real* x, const real* u, int ld, int p)
         return (real)1;
     default: {
         real s1 = (real)0, s2 = (real)0;
+        DPB_UNROLL
         for (int k = 0; k < d; ++k) {
             real xk = DPB_AT(x, k), uk = DPB_AT(u, k);
             s1 = s1 + E.lv_num * (xk * xk) / (E.q + E.lv_den * (xk * xk));
@@ -295,6 +309,7 @@ DPB_HD int fwd_move(const Eq<real>& E, real* x, const real* u, const real* dw, r
     }
     real n2 = (real)0;
     real dx[32];
+    DPB_UNROLL
     for (int k = 0; k < d; ++k) {
         real sd = eq_sigma(E, x, u, k, ld, p) * DPB_AT(dw, k);
         if (sdw_out) DPB_AT(sdw_out, k) = sd;
@@ -314,6 +329,7 @@ DPB_HD int fwd_move(const Eq<real>& E, real* x, const real* u, const real* dw, r
         coef = (flag > 0 && newflag > 0) ? 1 : 0;           // sign(flag) * sign(new_flag)
     }
     if (coef) {
+        DPB_UNROLL
         for (int k = 0; k < d; ++k) DPB_AT(x, k) = DPB_AT(x, k) + dx[k];
     }
     flag = newflag;
@@ -330,6 +346,7 @@ DPB_HD void adj_step(const Eq<real>& E, const real* x, const real* u, const real
                      int dt_grad, real xnorm, real D_t, real invB, real* lam, real& Dbar, real* ubar, int ld, int p) {
     const int d = E.d, m = E.m;
     if (!coef) {                                            // identity step: contributes nothing
+        DPB_UNROLL
         for (int j = 0; j < m; ++j) DPB_AT(ubar, j) = (real)0;
         return;
     }
@@ -346,6 +363,7 @@ DPB_HD void adj_step(const Eq<real>& E, const real* x, const real* u, const real
     real hbar = (real)0;
     if (dt_grad) {
         real acc = (real)0;
+        DPB_UNROLL
         for (int k = 0; k < d; ++k) {
             real mu = eq_drift(E, cc, x, u, k, ld, p);
             real s = eq_sigma(E, x, u, k, ld, p);
@@ -358,15 +376,18 @@ DPB_HD void adj_step(const Eq<real>& E, const real* x, const real* u, const real
 
     // ubar and the direct part of xbar
     real xb[32];
+    DPB_UNROLL
     for (int k = 0; k < d; ++k) xb[k] = DPB_AT(lam, k);
     switch (E.eqn) {
     case EQ_LQR:
+        DPB_UNROLL
         for (int k = 0; k < d; ++k) {
             DPB_AT(ubar, k) = cw * ((real)2 * E.q * DPB_AT(u, k)) + dt * E.beta * DPB_AT(lam, k);
             xb[k] = xb[k] + cw * ((real)2 * E.p * DPB_AT(x, k));
         }
         break;
     case EQ_LQRVAR:
+        DPB_UNROLL
         for (int k = 0; k < d; ++k) {
             real xk = DPB_AT(x, k), uk = DPB_AT(u, k), lk = DPB_AT(lam, k), xi = DPB_AT(dw, k);
             real den = E.q + E.lv_den * xk * xk;
@@ -377,8 +398,10 @@ DPB_HD void adj_step(const Eq<real>& E, const real* x, const real* u, const real
         break;
     case EQ_EKN: {
         real lu = (real)0;
+        DPB_UNROLL
         for (int k = 0; k < d; ++k) lu = lu + DPB_AT(lam, k) * DPB_AT(u, k);
         real dc = cc * (real)3 * E.a3 / ((real)2 * E.a2 - (real)3 * E.a3 * r);      // dc/dr
+        DPB_UNROLL
         for (int k = 0; k < d; ++k) {
             DPB_AT(ubar, k) = dt * cc * DPB_AT(lam, k);
             xb[k] = xb[k] + dt * lu * dc * DPB_AT(x, k) / r;
@@ -387,6 +410,7 @@ DPB_HD void adj_step(const Eq<real>& E, const real* x, const real* u, const real
     }
     default: {                                              // VDP
         real dv1[16], dv2[16], f[16];
+        DPB_UNROLL
         for (int j = 0; j < m; ++j) {
             int jn = (j + 1 == m ? 0 : j + 1), jp = (j == 0 ? m - 1 : j - 1);
             real x1 = DPB_AT(x, j), x2 = DPB_AT(x, m + j);
@@ -394,6 +418,7 @@ DPB_HD void adj_step(const Eq<real>& E, const real* x, const real* u, const real
             dv2[j] = (real)2 * E.a * x2 - E.eps * (DPB_AT(x, m + jn) + DPB_AT(x, m + jp));
             f[j] = ((real)1 - x1 * x1) * x2 - x1;
         }
+        DPB_UNROLL
         for (int j = 0; j < m; ++j) {
             int jn = (j + 1 == m ? 0 : j + 1), jp = (j == 0 ? m - 1 : j - 1);
             real x1 = DPB_AT(x, j), x2 = DPB_AT(x, m + j);
@@ -413,8 +438,10 @@ DPB_HD void adj_step(const Eq<real>& E, const real* x, const real* u, const real
     if (dt_grad) {
         // dh/dx = -2 (R-|x|)/(3 d sigU^2) * x/|x|      (equation.py:85)
         real g = -(real)2 * (E.R - xnorm) / E.c3 / xnorm * hbar;
+        DPB_UNROLL
         for (int k = 0; k < d; ++k) xb[k] = xb[k] + g * DPB_AT(x, k);
     }
+    DPB_UNROLL
     for (int k = 0; k < d; ++k) DPB_AT(lam, k) = xb[k];
 }
 

@@ -124,6 +124,7 @@ __device__ __forceinline__ float tc_block_sum(float v, float* red) {
 __device__ __noinline__ void path_dw(const TcArgs& a, long long gpath_local, bool valid, int t, float* dw) {
     const int d = a.eq.d;
     if (a.dw_mode == DW_EXTERNAL) {
+        _Pragma("unroll 4")
         for (int k = 0; k < d; ++k) dw[k] = valid ? a.dw[(gpath_local * d + k) * (long long)a.N + t] : 0.f;
         return;
     }
@@ -250,9 +251,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) critic_tc_kernel(const TcArgs a
         int flag = 0, nacc = 0;
         float disc = 1.f, y = 0.f;
         if (is_path) {
+            _Pragma("unroll 4")
             for (int k = 0; k < d; ++k) x[k] = valid ? a.x0[gp * d + k] : fill;
             flag = fwd_initial_flag(E, x, 1, 0);
             if (a.o_x && wr)
+                _Pragma("unroll 4")
                 for (int k = 0; k < d; ++k) a.o_x[(gp * d + k) * (long long)(N + 1)] = x[k];
         }
         if (is_ctrl) {                                            // schedule of the rollout
@@ -286,6 +289,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) critic_tc_kernel(const TcArgs a
                 if (td1) path_net_begin(P, nG, S.vecG, x);                        // NN_value_grad at x_t (before the move)
                 float* tr = traj + (size_t)t * 2 * sr * TC_PATHS;
                 if (need_grad && td1 && primary)
+                    _Pragma("unroll 4")
                     for (int k = 0; k < d; ++k) tr[k * TC_PATHS + row] = x[k];
                 float w = 0.f;
                 if (!prop_only) w = eq_w(E, x, u, 1, 0);
@@ -295,11 +299,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) critic_tc_kernel(const TcArgs a
                 y = y + w * disc * cf * dt;                                       // solver.py:170-174
                 if (td1) {
                     float dif = 0.f;
+                    _Pragma("unroll 4")
                     for (int k = 0; k < d; ++k) dif = dif + sdw[k] * g[k];        // solver.py:177-182
                     dif = dif * disc;
                     y = y - dif * cf * sqdt;                                      // solver.py:184
                     if (need_grad && primary) {
                         const float q = disc * cf * sqdt;
+                        _Pragma("unroll 4")
                         for (int k = 0; k < d; ++k) tr[(sr + k) * TC_PATHS + row] = sdw[k] * q;
                     }
                 }
@@ -309,6 +315,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) critic_tc_kernel(const TcArgs a
                     if (a.o_dt) a.o_dt[gp * N + t] = dt;
                     if (a.o_coef) a.o_coef[gp * N + t] = cf;
                     if (a.o_x)
+                        _Pragma("unroll 4")
                         for (int k = 0; k < d; ++k) a.o_x[(gp * d + k) * (long long)(N + 1) + t + 1] = x[k];
                 }
             }
@@ -318,6 +325,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) critic_tc_kernel(const TcArgs a
                 if (a.o_dt) a.o_dt[gp * N + t] = E.delta_t;
                 if (a.o_coef) a.o_coef[gp * N + t] = 0.f;
                 if (a.o_x)
+                    _Pragma("unroll 4")
                     for (int k = 0; k < d; ++k) a.o_x[(gp * d + k) * (long long)(N + 1) + t + 1] = x[k];
             }
             if (a.o_exit) a.o_exit[gp] = nacc;
@@ -340,7 +348,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) critic_tc_kernel(const TcArgs a
             }
         } else if (is_path) {
             float vN[1], v0[1], vb[1], x0v[32], xbv[32], dy0[32], cot[1];
+            _Pragma("unroll 4")
             for (int k = 0; k < d; ++k) x0v[k] = valid ? a.x0[gp * d + k] : fill;
+            _Pragma("unroll 4")
             for (int k = 0; k < d; ++k) xbv[k] = valid ? a.xb[gp * d + k] : fill;
             if (!need_grad) {
                 path_net_forward(P, nV, S.vecV, x0v, v0);
@@ -354,15 +364,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) critic_tc_kernel(const TcArgs a
                 rhog = valid ? rho_grad(delta, 50.f) * scale : 0.f;
                 cot[0] = -rhog * disc;
                 path_net_backward(P, nV, gV, mk, cot, true, gsV, S.dz, row, dy0);
+                _Pragma("unroll 4")
                 for (int k = 0; k < d; ++k) { sxV[k] += x[k] * dy0[k]; s0V[k] += dy0[k]; }
                 path_net_forward_keep(P, nV, S.vecV, x0v, v0, mk, copies, S.act, row, false);
                 cot[0] = rhog;
                 path_net_backward(P, nV, gV, mk, cot, true, gsV, S.dz, row, dy0);
+                _Pragma("unroll 4")
                 for (int k = 0; k < d; ++k) { sxV[k] += x0v[k] * dy0[k]; s0V[k] += dy0[k]; }
                 path_net_forward_keep(P, nV, S.vecV, xbv, vb, mk, copies, S.act, row, false);
                 const float dbb = vb[0] - eq_Z(E, xbv, 1, 0);
                 cot[0] = valid ? rho_grad(dbb, 50.f) * scale : 0.f;
                 path_net_backward(P, nV, gV, mk, cot, true, gsV, S.dz, row, dy0);
+                _Pragma("unroll 4")
                 for (int k = 0; k < d; ++k) { sxV[k] += xbv[k] * dy0[k]; s0V[k] += dy0[k]; }
             }
             const float delta = v0[0] - y - vN[0] * disc;                         // solver.py:189
@@ -392,9 +405,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) critic_tc_kernel(const TcArgs a
                 float xt[32], cot[32], dy0[32];
                 for (int t = 0; t < tlive; ++t) {
                     const float* tr = traj + (size_t)t * 2 * sr * TC_PATHS;
+                    _Pragma("unroll 4")
                     for (int k = 0; k < d; ++k) { xt[k] = tr[k * TC_PATHS + row]; cot[k] = tr[(sr + k) * TC_PATHS + row] * rhog; }
                     path_net_forward_keep(P, nG, S.vecG, xt, (float*)nullptr, mk, copies, S.act, row, true);
                     path_net_backward(P, nG, gG, mk, cot, true, gsG, S.dz, row, dy0);
+                    _Pragma("unroll 4")
                     for (int k = 0; k < d; ++k) { sxG[k] += xt[k] * dy0[k]; s0G[k] += dy0[k]; }
                 }
             }
@@ -469,9 +484,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) actor_tc_kernel(const TcArgs a)
         int flag = 0, nacc = 0;
         float disc = 1.f, y = 0.f;
         if (is_path) {
+            _Pragma("unroll 4")
             for (int k = 0; k < d; ++k) x[k] = valid ? a.x0[gp * d + k] : fill;
             flag = fwd_initial_flag(E, x, 1, 0);
             if (a.o_x && wr)
+                _Pragma("unroll 4")
                 for (int k = 0; k < d; ++k) a.o_x[(gp * d + k) * (long long)(N + 1)] = x[k];
         }
         if (is_ctrl) {
@@ -501,6 +518,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) actor_tc_kernel(const TcArgs a)
                 }
                 float* tr = traj + (size_t)t * trs * TC_PATHS;
                 if (need_grad && primary)
+                    _Pragma("unroll 4")
                     for (int k = 0; k < d; ++k) { tr[k * TC_PATHS + row] = x[k]; tr[(sr + k) * TC_PATHS + row] = dwv[k]; }
                 const float w = eq_w(E, x, u, 1, 0);
                 const int coef = fwd_move(E, x, u, dwv, dt, sqdt, xn, flag, (float*)nullptr, 1, 0);
@@ -517,6 +535,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) actor_tc_kernel(const TcArgs a)
                     if (a.o_dt) a.o_dt[gp * N + t] = dt;
                     if (a.o_coef) a.o_coef[gp * N + t] = cf;
                     if (a.o_x)
+                        _Pragma("unroll 4")
                         for (int k = 0; k < d; ++k) a.o_x[(gp * d + k) * (long long)(N + 1) + t + 1] = x[k];
                 }
             }
@@ -526,6 +545,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) actor_tc_kernel(const TcArgs a)
                 if (a.o_dt) a.o_dt[gp * N + t] = E.delta_t;
                 if (a.o_coef) a.o_coef[gp * N + t] = 0.f;
                 if (a.o_x)
+                    _Pragma("unroll 4")
                     for (int k = 0; k < d; ++k) a.o_x[(gp * d + k) * (long long)(N + 1) + t + 1] = x[k];
             }
             if (a.o_exit) a.o_exit[gp] = nacc;
@@ -550,6 +570,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) actor_tc_kernel(const TcArgs a)
                 vN[0] = eq_V_true(E, x, 1, 0);                                    // solver.py:223
                 if (need_grad) {
                     eq_V_grad_true(E, x, lam, 1, 0);
+                    _Pragma("unroll 4")
                     for (int k = 0; k < d; ++k) lam[k] = lam[k] * seed;
                 }
             } else if (!need_grad) {
@@ -561,6 +582,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) actor_tc_kernel(const TcArgs a)
                 cot[0] = seed;
                 path_net_backward(P, nV, gV, mk, cot, false, nullptr, nullptr, row, dy0);
                 const float* g0c = S.vecV + nV.vec_g0;
+                _Pragma("unroll 4")
                 for (int k = 0; k < d; ++k) lam[k] = dy0[k] * g0c[k];
             }
             Dbar = valid ? vN[0] * a.invB : 0.f;
@@ -590,6 +612,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) actor_tc_kernel(const TcArgs a)
             } else if (is_path) {
                 Masks mk;
                 float xt[32], ubar[32], cot[32], dy0[32];
+                _Pragma("unroll 4")
                 for (int k = 0; k < d; ++k) { xt[k] = tr[k * TC_PATHS + row]; dwv[k] = tr[(sr + k) * TC_PATHS + row]; }
                 path_net_forward_keep(P, nA, S.vecA, xt, raw, mk, copies, S.act, row, false);
                 if (nA.ekn_head) ekn_head_fwd(raw, u, nA.mctrl, 1, 0);
@@ -605,6 +628,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) actor_tc_kernel(const TcArgs a)
                 }
                 path_net_backward(P, nA, gA, mk, cot, true, gsA, S.dz, row, dy0);
                 const float* g0c = S.vecA + nA.vec_g0;
+                _Pragma("unroll 4")
                 for (int k = 0; k < d; ++k) {
                     sxA[k] += xt[k] * dy0[k]; s0A[k] += dy0[k];
                     lam[k] = lam[k] + dy0[k] * g0c[k];
