@@ -5,6 +5,7 @@
 #include <math.h>
 #include <stdio.h>
 #include <string.h>
+#include <stdlib.h>
 #include <string>
 #include "../../include/deeppde_b200.h"
 #include "dpb_host.h"
@@ -61,6 +62,7 @@ static const double BN_C = 1.0 / sqrt(1.0 + 1e-6);       // solver.py:242 (epsil
 
 struct Layout {
     int grid;
+    int nslab;              // gradient slabs: one per CTA on the exact path (deterministic), <= 16 shared ones on the tensor path
     size_t pkA, pkV, pkG, loss_part, loss_out, scratch, slabs, raw, total;
     size_t imgA, imgV, imgG, vecA, vecV, vecG, copies, stats;      // tensor path: operand images, vector blocks, activation copies, counters
     long long scratch_per_cta, copies_per_cta;
@@ -73,6 +75,7 @@ static Layout make_layout(const dpb_handle* h, long long B_local, int N) {
     const int P = tensor ? tc::TC_PATHS : tileP(h);
     long long ntiles = (B_local + P - 1) / P;
     L.grid = (int)(ntiles < h->num_sms ? (ntiles < 1 ? 1 : ntiles) : h->num_sms);
+    L.nslab = tensor ? (L.grid < 16 ? L.grid : 16) : L.grid;
     size_t o = 0;
     L.imgA = L.imgV = L.imgG = L.vecA = L.vecV = L.vecG = 0;
     if (tensor) {
@@ -101,7 +104,7 @@ static Layout make_layout(const dpb_handle* h, long long B_local, int N) {
     }
     const long long gc = tensor ? h->sV.gtotal + h->sG.gtotal : h->nV.gtotal + h->nG.gtotal, ga = tensor ? h->sA.gtotal : h->nA.gtotal;
     const long long gmax = gc > ga ? gc : ga;
-    L.slabs = o; o += a256((size_t)L.grid * gmax * es);
+    L.slabs = o; o += a256((size_t)L.nslab * gmax * es);
     L.raw = o; o += a256((size_t)gmax * es);
     L.total = o;
     return L;
@@ -379,6 +382,13 @@ static int tc_pack(dpb_handle* h, const tc::TcNet& t, const void* theta, char* w
     return DPB_OK;
 }
 
+// the <24, EQN> instantiations keep the per-path vectors in registers: dim and control_dim + 1 must fit in 24 and the
+// equation must index its state statically (VDP's cyclic neighbours do not); DPB_TC_GENERIC=1 forces the generic kernels
+static bool tc_specialised(const dpb_handle* h) {
+    static const bool force_generic = getenv("DPB_TC_GENERIC") != nullptr;
+    return !force_generic && h->cfg.eqn != DPB_EQN_VDP && h->cfg.dim <= 23 && h->cfg.control_dim + 1 <= 24;
+}
+
 // ring geometry for a launch: slots of `slot_bytes` (largest chunk of the images used) in what is left of 227 KB
 static int tc_ring(dpb_handle* h, tc::TcArgs& a, bool grads) {
     a.actdz_bytes = grads ? tc::TC_PATHS * h->tc_maxw16 * 2 : 0;
@@ -409,6 +419,7 @@ static void tc_fill(dpb_handle* h, tc::TcArgs& a, const Layout& L, char* ws, con
     a.copies = (unsigned char*)(ws + L.copies);
     a.copies_per_cta = L.copies_per_cta;
     a.stats = (long long*)(ws + L.stats);
+    a.nslab = L.nslab;
     a.sr = h->sr;
     if (outs) {
         a.o_x = (float*)outs->x_smp; a.o_dt = (float*)outs->dt; a.o_coef = (float*)outs->coef;
@@ -447,13 +458,21 @@ static int critic_step_tc(dpb_handle* h, const void* thA, const void* thV, const
     }
     if (need_grad) {
         a.slabV = (float*)(ws + L.slabs);
-        a.slabG = a.slabV + (size_t)L.grid * h->sV.gtotal;
-        DPB_CUDA(h, cudaMemsetAsync(ws + L.slabs, 0, (size_t)L.grid * (h->sV.gtotal + h->sG.gtotal) * sizeof(float), st));
+        a.slabG = a.slabV + (size_t)L.nslab * h->sV.gtotal;
+        DPB_CUDA(h, cudaMemsetAsync(ws + L.slabs, 0, (size_t)L.nslab * (h->sV.gtotal + h->sG.gtotal) * sizeof(float), st));
     }
     const size_t smem = tc::tc_smem_bytes(h->tA.vec_floats, h->tV.vec_floats, h->tG.vec_floats, a.actdz_bytes, a.nslot, a.slot_bytes);
-    DPB_CUDA(h, cudaFuncSetAttribute(tc::critic_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    void (*kern)(const tc::TcArgs) = tc::critic_tc_kernel<0, -1>;
+    if (tc_specialised(h)) {
+        switch (h->cfg.eqn) {
+        case DPB_EQN_LQR: kern = tc::critic_tc_kernel<24, EQ_LQR>; break;
+        case DPB_EQN_EKN: kern = tc::critic_tc_kernel<24, EQ_EKN>; break;
+        case DPB_EQN_LQR_VAR: kern = tc::critic_tc_kernel<24, EQ_LQRVAR>; break;
+        }
+    }
+    DPB_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     ev_begin(h, st);
-    tc::critic_tc_kernel<<<L.grid, tc::TC_THREADS, smem, st>>>(a);
+    kern<<<L.grid, tc::TC_THREADS, smem, st>>>(a);
     ev_end(h, st);
     h->launches++;
     DPB_CUDA(h, cudaGetLastError());
@@ -464,9 +483,9 @@ static int critic_step_tc(dpb_handle* h, const void* thA, const void* thV, const
     }
     if (need_grad) {
         float* raw = (float*)(ws + L.raw);
-        if (grad_V) { if ((rc = tc_finalize(h, h->tV, h->sV, thV, a.slabV, L.grid, raw, grad_V, st))) return rc; }
+        if (grad_V) { if ((rc = tc_finalize(h, h->tV, h->sV, thV, a.slabV, L.nslab, raw, grad_V, st))) return rc; }
         if (grad_G) {
-            if (td1) { if ((rc = tc_finalize(h, h->tG, h->sG, thG, a.slabG, L.grid, raw + h->sV.gtotal, grad_G, st))) return rc; }
+            if (td1) { if ((rc = tc_finalize(h, h->tG, h->sG, thG, a.slabG, L.nslab, raw + h->sV.gtotal, grad_G, st))) return rc; }
             else DPB_CUDA(h, cudaMemsetAsync(grad_G, 0, (size_t)h->nG.ftotal * sizeof(float), st));
         }
     }
@@ -489,12 +508,20 @@ static int actor_step_tc(dpb_handle* h, const void* thA, const void* thV, const 
     if (!cheat_v) { if ((rc = tc_pack(h, h->tV, thV, ws, L.imgV, L.vecV, st))) return rc; a.vecV = (const float*)(ws + L.vecV); }
     if (need_grad) {
         a.slabA = (float*)(ws + L.slabs);
-        DPB_CUDA(h, cudaMemsetAsync(ws + L.slabs, 0, (size_t)L.grid * h->sA.gtotal * sizeof(float), st));
+        DPB_CUDA(h, cudaMemsetAsync(ws + L.slabs, 0, (size_t)L.nslab * h->sA.gtotal * sizeof(float), st));
     }
     const size_t smem = tc::tc_smem_bytes(h->tA.vec_floats, h->tV.vec_floats, h->tG.vec_floats, a.actdz_bytes, a.nslot, a.slot_bytes);
-    DPB_CUDA(h, cudaFuncSetAttribute(tc::actor_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    void (*kern)(const tc::TcArgs) = tc::actor_tc_kernel<0, -1>;
+    if (tc_specialised(h)) {
+        switch (h->cfg.eqn) {
+        case DPB_EQN_LQR: kern = tc::actor_tc_kernel<24, EQ_LQR>; break;
+        case DPB_EQN_EKN: kern = tc::actor_tc_kernel<24, EQ_EKN>; break;
+        case DPB_EQN_LQR_VAR: kern = tc::actor_tc_kernel<24, EQ_LQRVAR>; break;
+        }
+    }
+    DPB_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     ev_begin(h, st);
-    tc::actor_tc_kernel<<<L.grid, tc::TC_THREADS, smem, st>>>(a);
+    kern<<<L.grid, tc::TC_THREADS, smem, st>>>(a);
     ev_end(h, st);
     h->launches++;
     DPB_CUDA(h, cudaGetLastError());
@@ -503,7 +530,7 @@ static int actor_step_tc(dpb_handle* h, const void* thA, const void* thV, const 
         h->launches++;
     }
     if (grad_A) {
-        if (need_grad) { if ((rc = tc_finalize(h, h->tA, h->sA, thA, a.slabA, L.grid, (float*)(ws + L.raw), grad_A, st))) return rc; }
+        if (need_grad) { if ((rc = tc_finalize(h, h->tA, h->sA, thA, a.slabA, L.nslab, (float*)(ws + L.raw), grad_A, st))) return rc; }
         else if (flags & DPB_FLAG_NEED_GRAD) DPB_CUDA(h, cudaMemsetAsync(grad_A, 0, (size_t)h->nA.ftotal * sizeof(float), st));
     }
     DPB_CUDA(h, cudaGetLastError());

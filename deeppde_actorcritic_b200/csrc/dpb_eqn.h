@@ -18,11 +18,17 @@
 
 #if defined(__CUDACC__)
 #define DPB_HD __host__ __device__ __forceinline__
-#define DPB_UNROLL _Pragma("unroll 4")
+#define DPB_UNROLL _Pragma("unroll (DMAX > 0 ? DMAX : 4)")
 #else
 #define DPB_HD inline
 #define DPB_UNROLL
 #endif
+// Loop over the first n components.  With a compile-time bound DMAX > 0 (the tensor-path kernels are
+// instantiated per padded dimension) the loop is fully unrolled and guarded, so that the per-path vectors
+// live in registers; DMAX == 0 is the generic run-time loop.
+#define DPB_LOOP(k, n) DPB_UNROLL for (int k = 0; k < (DMAX > 0 ? DMAX : (n)); ++k) if (DMAX == 0 || k < (n))
+#define DPB_TPL template <typename real, int DMAX = 0, int EQN = -1>
+#define DPB_EQN(E) (EQN >= 0 ? EQN : (E).eqn)
 
 namespace dpb {
 
@@ -76,26 +82,23 @@ DPB_HD double dpb_max(double a, double b) { return fmax(a, b); }
 // All per-path functions address column arrays as v[k*ld + p].
 #define DPB_AT(v, k) ((v)[(k) * ld + p])
 
-template <typename real>
+DPB_TPL
 DPB_HD real norm2_path(const real* x, int d, int ld, int p) {
     real s = (real)0;
-    DPB_UNROLL
-    for (int k = 0; k < d; ++k) s = s + DPB_AT(x, k) * DPB_AT(x, k);
+    DPB_LOOP(k, d) s = s + DPB_AT(x, k) * DPB_AT(x, k);
     return s;
 }
 
 // u_true (equation.py:163-164, 212-217, 259-261, 298-299)
-template <typename real>
+DPB_TPL
 DPB_HD void eq_u_true(const Eq<real>& E, const real* x, real* u, int ld, int p) {
     const int d = E.d, m = E.m;
-    switch (E.eqn) {
+    switch (DPB_EQN(E)) {
     case EQ_LQR:
-        DPB_UNROLL
-        for (int k = 0; k < d; ++k) DPB_AT(u, k) = E.cu * DPB_AT(x, k);
+        DPB_LOOP(k, d) DPB_AT(u, k) = E.cu * DPB_AT(x, k);
         break;
     case EQ_VDP:
-        DPB_UNROLL
-        for (int j = 0; j < m; ++j) {
+        DPB_LOOP(j, m) {
             real x2 = DPB_AT(x, m + j);
             real px2 = DPB_AT(x, m + (j + 1 == m ? 0 : j + 1));
             real nx2 = DPB_AT(x, m + (j == 0 ? m - 1 : j - 1));
@@ -103,14 +106,12 @@ DPB_HD void eq_u_true(const Eq<real>& E, const real* x, real* u, int ld, int p) 
         }
         break;
     case EQ_EKN: {
-        real r = dpb_sqrt(norm2_path(x, d, ld, p));
-        DPB_UNROLL
-        for (int k = 0; k < d; ++k) DPB_AT(u, k) = DPB_AT(x, k) / r;
+        real r = dpb_sqrt(norm2_path<real, DMAX, EQN>(x, d, ld, p));
+        DPB_LOOP(k, d) DPB_AT(u, k) = DPB_AT(x, k) / r;
         break;
     }
     default:
-        DPB_UNROLL
-        for (int k = 0; k < d; ++k) {
+        DPB_LOOP(k, d) {
             real xk = DPB_AT(x, k);
             DPB_AT(u, k) = -E.lv_un * xk / (E.lv_ud + E.lv_ue * xk * xk);
         }
@@ -118,18 +119,17 @@ DPB_HD void eq_u_true(const Eq<real>& E, const real* x, real* u, int ld, int p) 
 }
 
 // V_true (equation.py:160,204-210,255-257,295)
-template <typename real>
+DPB_TPL
 DPB_HD real eq_V_true(const Eq<real>& E, const real* x, int ld, int p) {
     const int d = E.d, m = E.m;
-    real n2 = norm2_path(x, d, ld, p);
-    switch (E.eqn) {
+    real n2 = norm2_path<real, DMAX, EQN>(x, d, ld, p);
+    switch (DPB_EQN(E)) {
     case EQ_LQR:
     case EQ_LQRVAR:
         return n2 * E.k;
     case EQ_VDP: {
         real s = (real)0;
-        DPB_UNROLL
-        for (int j = 0; j < m; ++j) {
+        DPB_LOOP(j, m) {
             int jn = (j + 1 == m ? 0 : j + 1);
             s = s + (DPB_AT(x, j) * DPB_AT(x, jn) + DPB_AT(x, m + j) * DPB_AT(x, m + jn));
         }
@@ -143,48 +143,44 @@ DPB_HD real eq_V_true(const Eq<real>& E, const real* x, int ld, int p) {
 }
 
 // Z_tf on the boundary (equation.py:157,201,252,292)
-template <typename real>
+DPB_TPL
 DPB_HD real eq_Z(const Eq<real>& E, const real* x, int ld, int p) {
-    if (E.eqn == EQ_LQR || E.eqn == EQ_LQRVAR) return E.ZR;
-    return eq_V_true(E, x, ld, p);
+    if (DPB_EQN(E) == EQ_LQR || DPB_EQN(E) == EQ_LQRVAR) return E.ZR;
+    return eq_V_true<real, DMAX, EQN>(E, x, ld, p);
 }
 
 // V_grad_true (equation.py:166,219-227,263-265,301) -> g[k]
-template <typename real>
+DPB_TPL
 DPB_HD void eq_V_grad_true(const Eq<real>& E, const real* x, real* g, int ld, int p) {
     const int d = E.d, m = E.m;
-    switch (E.eqn) {
+    switch (DPB_EQN(E)) {
     case EQ_LQR:
     case EQ_LQRVAR:
-        DPB_UNROLL
-        for (int k = 0; k < d; ++k) DPB_AT(g, k) = (real)2 * E.k * DPB_AT(x, k);
+        DPB_LOOP(k, d) DPB_AT(g, k) = (real)2 * E.k * DPB_AT(x, k);
         break;
     case EQ_VDP:
-        DPB_UNROLL
-        for (int j = 0; j < m; ++j) {
+        DPB_LOOP(j, m) {
             int jn = (j + 1 == m ? 0 : j + 1), jp = (j == 0 ? m - 1 : j - 1);
             DPB_AT(g, j) = (real)2 * E.a * DPB_AT(x, j) - E.eps * (DPB_AT(x, jn) + DPB_AT(x, jp));
             DPB_AT(g, m + j) = (real)2 * E.a * DPB_AT(x, m + j) - E.eps * (DPB_AT(x, m + jn) + DPB_AT(x, m + jp));
         }
         break;
     default: {
-        real r = dpb_sqrt(norm2_path(x, d, ld, p));
+        real r = dpb_sqrt(norm2_path<real, DMAX, EQN>(x, d, ld, p));
         real c = (real)3 * E.a3 * r - (real)2 * E.a2;
-        DPB_UNROLL
-        for (int k = 0; k < d; ++k) DPB_AT(g, k) = c * DPB_AT(x, k);
+        DPB_LOOP(k, d) DPB_AT(g, k) = c * DPB_AT(x, k);
     }
     }
 }
 
 // running cost w_tf (equation.py:154,188-199,249,288-290)
-template <typename real>
+DPB_TPL
 DPB_HD real eq_w(const Eq<real>& E, const real* x, const real* u, int ld, int p) {
     const int d = E.d, m = E.m;
-    switch (E.eqn) {
+    switch (DPB_EQN(E)) {
     case EQ_LQR: {
         real s1 = (real)0, s2 = (real)0;
-        DPB_UNROLL
-        for (int k = 0; k < d; ++k) {
+        DPB_LOOP(k, d) {
             s1 = s1 + E.p * (DPB_AT(x, k) * DPB_AT(x, k));
             s2 = s2 + E.q * (DPB_AT(u, k) * DPB_AT(u, k));
         }
@@ -192,8 +188,7 @@ DPB_HD real eq_w(const Eq<real>& E, const real* x, const real* u, int ld, int p)
     }
     case EQ_VDP: {
         real s = (real)0, n2 = (real)0;
-        DPB_UNROLL
-        for (int j = 0; j < m; ++j) {
+        DPB_LOOP(j, m) {
             int jn = (j + 1 == m ? 0 : j + 1), jp = (j == 0 ? m - 1 : j - 1);
             real x1 = DPB_AT(x, j), x2 = DPB_AT(x, m + j);
             real px1 = DPB_AT(x, jn), px2 = DPB_AT(x, m + jn), nx1 = DPB_AT(x, jp), nx2 = DPB_AT(x, m + jp);
@@ -211,8 +206,7 @@ DPB_HD real eq_w(const Eq<real>& E, const real* x, const real* u, int ld, int p)
         return (real)1;
     default: {
         real s1 = (real)0, s2 = (real)0;
-        DPB_UNROLL
-        for (int k = 0; k < d; ++k) {
+        DPB_LOOP(k, d) {
             real xk = DPB_AT(x, k), uk = DPB_AT(u, k);
             s1 = s1 + E.lv_num * (xk * xk) / (E.q + E.lv_den * (xk * xk));
             s2 = s2 + (E.lv_gk * (xk * xk) + E.q * (uk * uk));
@@ -223,15 +217,15 @@ DPB_HD real eq_w(const Eq<real>& E, const real* x, const real* u, int ld, int p)
 }
 
 // ekn drift factor c(|x|) (equation.py:270-272); 0 for the other equations.
-template <typename real>
+DPB_TPL
 DPB_HD real eq_drift_c(const Eq<real>& E, real r) {
     return E.C0 / ((real)2 * E.a2 - (real)3 * E.a3 * r);
 }
 
-// drift component k (equation.py:172,232-235,270-273,307).  cc = eq_drift_c(|x|) for ekn.
-template <typename real>
+// drift component k (equation.py:172,232-235,270-273,307).  cc = eq_drift_c<real, DMAX, EQN>(|x|) for ekn.
+DPB_TPL
 DPB_HD real eq_drift(const Eq<real>& E, real cc, const real* x, const real* u, int k, int ld, int p) {
-    switch (E.eqn) {
+    switch (DPB_EQN(E)) {
     case EQ_LQR:
     case EQ_LQRVAR:
         return E.beta * DPB_AT(u, k);
@@ -248,15 +242,15 @@ DPB_HD real eq_drift(const Eq<real>& E, real cc, const real* x, const real* u, i
 }
 
 // diagonal of sigma, component k (equation.py:170,230,268,305)
-template <typename real>
+DPB_TPL
 DPB_HD real eq_sigma(const Eq<real>& E, const real* x, const real* u, int k, int ld, int p) {
-    if (E.eqn == EQ_LQRVAR) return E.sig * ((real)1 + E.eps * DPB_AT(x, k) * DPB_AT(u, k));
+    if (DPB_EQN(E) == EQ_LQRVAR) return E.sig * ((real)1 + E.eps * DPB_AT(x, k) * DPB_AT(u, k));
     return E.sig;
 }
 
 // adaptive-scheme flag of a point with norm nrm (equation.py:80-82,94-95):
 //   1 + floor((sign(R-n-hb) + sign(R-n))/2)  ==  (R-n > 0) ? ((R-n-hb > 0) ? 2 : 1) : 0
-template <typename real>
+DPB_TPL
 DPB_HD int eq_flag(const Eq<real>& E, real nrm) {
     real t2 = E.R - nrm;
     real t1 = E.R - nrm - E.hb;
@@ -266,15 +260,15 @@ DPB_HD int eq_flag(const Eq<real>& E, real nrm) {
 // ------------------------------------------------------------------------------------------------
 // Forward step.  `flag`: naive 1 = alive, 0 = frozen (equation.py:51,69); adaptive 2 = inner,
 // 1 = boundary layer, 0 = out (equation.py:80-82).
-template <typename real>
+DPB_TPL
 DPB_HD int fwd_initial_flag(const Eq<real>& E, const real* x, int ld, int p) {
     if (E.scheme == SCHEME_NAIVE) return 1;
-    return eq_flag(E, dpb_sqrt(norm2_path(x, E.d, ld, p)));
+    return eq_flag<real, DMAX, EQN>(E, dpb_sqrt(norm2_path<real, DMAX, EQN>(x, E.d, ld, p)));
 }
 
 // step size of this step (equation.py:49 | 84-86).  `clamped` tells the reverse sweep whether the
 // maximum() selected the constant (zero gradient).
-template <typename real>
+DPB_TPL
 DPB_HD void fwd_dt(const Eq<real>& E, const real* x, int flag, int ld, int p, real& dt, real& sqdt, real& xnorm, int& dt_grad) {
     dt_grad = 0;
     xnorm = (real)0;
@@ -283,7 +277,7 @@ DPB_HD void fwd_dt(const Eq<real>& E, const real* x, int flag, int ld, int p, re
         sqdt = E.sqrt_delta_t;
         return;
     }
-    xnorm = dpb_sqrt(norm2_path(x, E.d, ld, p));
+    xnorm = dpb_sqrt(norm2_path<real, DMAX, EQN>(x, E.d, ld, p));
     if (flag == 1) {
         real g = E.R - xnorm;
         dt = g * g / E.c3;
@@ -298,22 +292,21 @@ DPB_HD void fwd_dt(const Eq<real>& E, const real* x, int flag, int ld, int p, re
 // Proposal + exit logic + in-place state update (equation.py:58-69 | 91-105).
 //   x, u, dw: columns;  xdw_out (optional): sigma_k*dw_k per component (the diffusion vector).
 // Returns coef in {0,1}; updates x (only if coef) and flag.
-template <typename real>
+DPB_TPL
 DPB_HD int fwd_move(const Eq<real>& E, real* x, const real* u, const real* dw, real dt, real sqdt, real xnorm, int& flag,
                     real* sdw_out, int ld, int p) {
     const int d = E.d;
     real cc = (real)0;
-    if (E.eqn == EQ_EKN) {
-        real r = (E.scheme == SCHEME_ADAPTIVE) ? xnorm : dpb_sqrt(norm2_path(x, d, ld, p));
-        cc = eq_drift_c(E, r);
+    if (DPB_EQN(E) == EQ_EKN) {
+        real r = (E.scheme == SCHEME_ADAPTIVE) ? xnorm : dpb_sqrt(norm2_path<real, DMAX, EQN>(x, d, ld, p));
+        cc = eq_drift_c<real, DMAX, EQN>(E, r);
     }
     real n2 = (real)0;
-    real dx[32];
-    DPB_UNROLL
-    for (int k = 0; k < d; ++k) {
-        real sd = eq_sigma(E, x, u, k, ld, p) * DPB_AT(dw, k);
+    real dx[DMAX > 0 ? DMAX : 32];
+    DPB_LOOP(k, d) {
+        real sd = eq_sigma<real, DMAX, EQN>(E, x, u, k, ld, p) * DPB_AT(dw, k);
         if (sdw_out) DPB_AT(sdw_out, k) = sd;
-        real dk = eq_drift(E, cc, x, u, k, ld, p) * dt + sd * sqdt;
+        real dk = eq_drift<real, DMAX, EQN>(E, cc, x, u, k, ld, p) * dt + sd * sqdt;
         dx[k] = dk;
         real pk = DPB_AT(x, k) + dk;
         n2 = n2 + pk * pk;
@@ -324,13 +317,12 @@ DPB_HD int fwd_move(const Eq<real>& E, real* x, const real* u, const real* dw, r
         coef = flag * (1 - ex);
         newflag = coef;
     } else {
-        int nf = eq_flag(E, dpb_sqrt(n2));
+        int nf = eq_flag<real, DMAX, EQN>(E, dpb_sqrt(n2));
         newflag = (flag > 0) ? nf : 0;                      // flag(p) * sign(flag)
         coef = (flag > 0 && newflag > 0) ? 1 : 0;           // sign(flag) * sign(new_flag)
     }
     if (coef) {
-        DPB_UNROLL
-        for (int k = 0; k < d; ++k) DPB_AT(x, k) = DPB_AT(x, k) + dx[k];
+        DPB_LOOP(k, d) DPB_AT(x, k) = DPB_AT(x, k) + dx[k];
     }
     flag = newflag;
     return coef;
@@ -341,32 +333,30 @@ DPB_HD int fwd_move(const Eq<real>& E, real* x, const real* u, const real* dw, r
 // step t (x, u, dw), the step's (dt, sqdt, coef, dt_grad), D_t, and the adjoints of the state
 // AFTER the step: lam[k] (in/out -> becomes the direct part xbar), Dbar (in/out).
 // Outputs ubar[j] (cotangent of the control).  invB = 1/B_global.
-template <typename real>
+DPB_TPL
 DPB_HD void adj_step(const Eq<real>& E, const real* x, const real* u, const real* dw, real dt, real sqdt, int coef,
                      int dt_grad, real xnorm, real D_t, real invB, real* lam, real& Dbar, real* ubar, int ld, int p) {
     const int d = E.d, m = E.m;
     if (!coef) {                                            // identity step: contributes nothing
-        DPB_UNROLL
-        for (int j = 0; j < m; ++j) DPB_AT(ubar, j) = (real)0;
+        DPB_LOOP(j, m) DPB_AT(ubar, j) = (real)0;
         return;
     }
-    const real w = eq_w(E, x, u, ld, p);
+    const real w = eq_w<real, DMAX, EQN>(E, x, u, ld, p);
     const real ed = dpb_exp(-E.gamma * dt);
     const real D_next = D_t * ed;
     const real cw = dt * D_t * invB;                        // weight of dw/d(.) terms
     real cc = (real)0, r = (real)0;
-    if (E.eqn == EQ_EKN) {
-        r = (E.scheme == SCHEME_ADAPTIVE) ? xnorm : dpb_sqrt(norm2_path(x, d, ld, p));
-        cc = eq_drift_c(E, r);
+    if (DPB_EQN(E) == EQ_EKN) {
+        r = (E.scheme == SCHEME_ADAPTIVE) ? xnorm : dpb_sqrt(norm2_path<real, DMAX, EQN>(x, d, ld, p));
+        cc = eq_drift_c<real, DMAX, EQN>(E, r);
     }
     // hbar = D_t w /B - gamma Dbar D_{t+1} + <lam, mu + s*xi/(2 sqrt h)>
     real hbar = (real)0;
     if (dt_grad) {
         real acc = (real)0;
-        DPB_UNROLL
-        for (int k = 0; k < d; ++k) {
-            real mu = eq_drift(E, cc, x, u, k, ld, p);
-            real s = eq_sigma(E, x, u, k, ld, p);
+        DPB_LOOP(k, d) {
+            real mu = eq_drift<real, DMAX, EQN>(E, cc, x, u, k, ld, p);
+            real s = eq_sigma<real, DMAX, EQN>(E, x, u, k, ld, p);
             acc = acc + DPB_AT(lam, k) * (mu + s * DPB_AT(dw, k) / ((real)2 * sqdt));
         }
         hbar = D_t * w * invB - E.gamma * Dbar * D_next + acc;
@@ -375,20 +365,17 @@ DPB_HD void adj_step(const Eq<real>& E, const real* x, const real* u, const real
     Dbar = Dbar * ed + dt * w * invB;
 
     // ubar and the direct part of xbar
-    real xb[32];
-    DPB_UNROLL
-    for (int k = 0; k < d; ++k) xb[k] = DPB_AT(lam, k);
-    switch (E.eqn) {
+    real xb[DMAX > 0 ? DMAX : 32];
+    DPB_LOOP(k, d) xb[k] = DPB_AT(lam, k);
+    switch (DPB_EQN(E)) {
     case EQ_LQR:
-        DPB_UNROLL
-        for (int k = 0; k < d; ++k) {
+        DPB_LOOP(k, d) {
             DPB_AT(ubar, k) = cw * ((real)2 * E.q * DPB_AT(u, k)) + dt * E.beta * DPB_AT(lam, k);
             xb[k] = xb[k] + cw * ((real)2 * E.p * DPB_AT(x, k));
         }
         break;
     case EQ_LQRVAR:
-        DPB_UNROLL
-        for (int k = 0; k < d; ++k) {
+        DPB_LOOP(k, d) {
             real xk = DPB_AT(x, k), uk = DPB_AT(u, k), lk = DPB_AT(lam, k), xi = DPB_AT(dw, k);
             real den = E.q + E.lv_den * xk * xk;
             real dwdx = E.lv_num * (real)2 * xk * E.q / (den * den) + (real)2 * E.lv_gk * xk;
@@ -398,11 +385,9 @@ DPB_HD void adj_step(const Eq<real>& E, const real* x, const real* u, const real
         break;
     case EQ_EKN: {
         real lu = (real)0;
-        DPB_UNROLL
-        for (int k = 0; k < d; ++k) lu = lu + DPB_AT(lam, k) * DPB_AT(u, k);
+        DPB_LOOP(k, d) lu = lu + DPB_AT(lam, k) * DPB_AT(u, k);
         real dc = cc * (real)3 * E.a3 / ((real)2 * E.a2 - (real)3 * E.a3 * r);      // dc/dr
-        DPB_UNROLL
-        for (int k = 0; k < d; ++k) {
+        DPB_LOOP(k, d) {
             DPB_AT(ubar, k) = dt * cc * DPB_AT(lam, k);
             xb[k] = xb[k] + dt * lu * dc * DPB_AT(x, k) / r;
         }
@@ -410,16 +395,14 @@ DPB_HD void adj_step(const Eq<real>& E, const real* x, const real* u, const real
     }
     default: {                                              // VDP
         real dv1[16], dv2[16], f[16];
-        DPB_UNROLL
-        for (int j = 0; j < m; ++j) {
+        DPB_LOOP(j, m) {
             int jn = (j + 1 == m ? 0 : j + 1), jp = (j == 0 ? m - 1 : j - 1);
             real x1 = DPB_AT(x, j), x2 = DPB_AT(x, m + j);
             dv1[j] = (real)2 * E.a * x1 - E.eps * (DPB_AT(x, jn) + DPB_AT(x, jp));
             dv2[j] = (real)2 * E.a * x2 - E.eps * (DPB_AT(x, m + jn) + DPB_AT(x, m + jp));
             f[j] = ((real)1 - x1 * x1) * x2 - x1;
         }
-        DPB_UNROLL
-        for (int j = 0; j < m; ++j) {
+        DPB_LOOP(j, m) {
             int jn = (j + 1 == m ? 0 : j + 1), jp = (j == 0 ? m - 1 : j - 1);
             real x1 = DPB_AT(x, j), x2 = DPB_AT(x, m + j);
             real l1 = DPB_AT(lam, j), l2 = DPB_AT(lam, m + j);
@@ -438,20 +421,18 @@ DPB_HD void adj_step(const Eq<real>& E, const real* x, const real* u, const real
     if (dt_grad) {
         // dh/dx = -2 (R-|x|)/(3 d sigU^2) * x/|x|      (equation.py:85)
         real g = -(real)2 * (E.R - xnorm) / E.c3 / xnorm * hbar;
-        DPB_UNROLL
-        for (int k = 0; k < d; ++k) xb[k] = xb[k] + g * DPB_AT(x, k);
+        DPB_LOOP(k, d) xb[k] = xb[k] + g * DPB_AT(x, k);
     }
-    DPB_UNROLL
-    for (int k = 0; k < d; ++k) DPB_AT(lam, k) = xb[k];
+    DPB_LOOP(k, d) DPB_AT(lam, k) = xb[k];
 }
 
 // Gradient of clipped square rho (solver.py:76-77): 2 z if |z| < 50 else 100 sign(z).
-template <typename real>
+DPB_TPL
 DPB_HD real rho(real z, real clip) {
     real az = z < (real)0 ? -z : z;
     return az < clip ? z * z : (real)2 * clip * az - clip * clip;
 }
-template <typename real>
+DPB_TPL
 DPB_HD real rho_grad(real z, real clip) {
     real az = z < (real)0 ? -z : z;
     if (az < clip) return (real)2 * z;
@@ -459,23 +440,23 @@ DPB_HD real rho_grad(real z, real clip) {
 }
 
 // ekn actor head (solver.py:272-274): u = y[:m] / (1e-15 + relu(y[m]) + ||y[:m]||)
-template <typename real>
+DPB_TPL
 DPB_HD void ekn_head_fwd(const real* y, real* u, int m, int ld, int p) {
-    real n = dpb_sqrt(norm2_path(y, m, ld, p));
+    real n = dpb_sqrt(norm2_path<real, DMAX, EQN>(y, m, ld, p));
     real ym = DPB_AT(y, m);
     real D = (real)0.000000000000001 + (ym > (real)0 ? ym : (real)0) + n;
-    for (int k = 0; k < m; ++k) DPB_AT(u, k) = DPB_AT(y, k) / D;
+    DPB_LOOP(k, m) DPB_AT(u, k) = DPB_AT(y, k) / D;
 }
 // cotangent ubar[m] -> ybar[m+1] (in place allowed when ubar and ybar are distinct buffers)
-template <typename real>
+DPB_TPL
 DPB_HD void ekn_head_bwd(const real* y, const real* ubar, real* ybar, int m, int ld, int p) {
-    real n = dpb_sqrt(norm2_path(y, m, ld, p));
+    real n = dpb_sqrt(norm2_path<real, DMAX, EQN>(y, m, ld, p));
     real ym = DPB_AT(y, m);
     real D = (real)0.000000000000001 + (ym > (real)0 ? ym : (real)0) + n;
     real s = (real)0;
-    for (int k = 0; k < m; ++k) s = s + DPB_AT(ubar, k) * DPB_AT(y, k);
+    DPB_LOOP(k, m) s = s + DPB_AT(ubar, k) * DPB_AT(y, k);
     real c = s / (D * D);
-    for (int k = 0; k < m; ++k) DPB_AT(ybar, k) = DPB_AT(ubar, k) / D - c * (DPB_AT(y, k) / n);
+    DPB_LOOP(k, m) DPB_AT(ybar, k) = DPB_AT(ubar, k) / D - c * (DPB_AT(y, k) / n);
     DPB_AT(ybar, m) = (ym > (real)0) ? -c : (real)0;
 }
 

@@ -29,6 +29,7 @@ struct TcArgs {
     long long copies_per_cta;
     int sr;
     int nslot, slot_bytes, actdz_bytes;   // ring geometry; bytes of each of the ACT / DZ images (0: no gradients)
+    int nslab;                      // gradient slabs shared by the CTAs (CTA b reduces into slab b % nslab)
     float *o_x, *o_dt, *o_coef, *o_delta, *o_delta_b;
     int* o_exit;
     long long* stats;               // [grid][16] cycle counters (diagnostics), may be NULL
@@ -120,38 +121,43 @@ __device__ __forceinline__ float tc_block_sum(float v, float* red) {
     return s;
 }
 
+// loop over the first n (<= DPX) components with static indices
+#define KLOOP(k, n) _Pragma("unroll") for (int k = 0; k < DPX; ++k) if (k < (n))
+
 // increments of step t for one path (same generator and bits as load_dw of the exact path)
-__device__ __noinline__ void path_dw(const TcArgs& a, long long gpath_local, bool valid, int t, float* dw) {
+template <int DPX>
+__device__ __forceinline__ void path_dw(const TcArgs& a, long long gpath_local, bool valid, int t, float (&dw)[DPX]) {
     const int d = a.eq.d;
     if (a.dw_mode == DW_EXTERNAL) {
-        _Pragma("unroll 4")
-        for (int k = 0; k < d; ++k) dw[k] = valid ? a.dw[(gpath_local * d + k) * (long long)a.N + t] : 0.f;
+        KLOOP(k, d) dw[k] = valid ? a.dw[(gpath_local * d + k) * (long long)a.N + t] : 0.f;
         return;
     }
     uint32_t k0, k1;
     philox_key(a.seed, a.stream, k0, k1);
     const unsigned long long gp = (unsigned long long)(a.path_offset + gpath_local);
-    const int nch = (d + 3) >> 2;
-    for (int ch = 0; ch < nch; ++ch) {
-        uint32_t c[4] = {(uint32_t)gp, (uint32_t)(gp >> 32), (uint32_t)t, (uint32_t)ch};
-        philox4x32_10(c, k0, k1);
-        float o[4];
-        if (a.dw_mode == DW_PHILOX_BOUNDED) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) o[i] = philox_bounded(c[i]);
-        } else {
+    for (int ch = 0; ch < (DPX + 3) / 4; ++ch) {
+        if (4 * ch < d) {
+            uint32_t c[4] = {(uint32_t)gp, (uint32_t)(gp >> 32), (uint32_t)t, (uint32_t)ch};
+            philox4x32_10(c, k0, k1);
+            float o[4];
+            if (a.dw_mode == DW_PHILOX_BOUNDED) {
 #pragma unroll
-            for (int i = 0; i < 2; ++i) {
-                float r = sqrtf(-2.0f * logf(philox_u01(c[2 * i])));
-                float s, co;
-                sincospif(2.0f * philox_u01(c[2 * i + 1]), &s, &co);
-                o[2 * i] = r * co;
-                o[2 * i + 1] = r * s;
+                for (int i = 0; i < 4; ++i) o[i] = philox_bounded(c[i]);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    float r = sqrtf(-2.0f * logf(philox_u01(c[2 * i])));
+                    float s, co;
+                    sincospif(2.0f * philox_u01(c[2 * i + 1]), &s, &co);
+                    o[2 * i] = r * co;
+                    o[2 * i + 1] = r * s;
+                }
             }
-        }
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
-            if (4 * ch + i < d) dw[4 * ch + i] = o[i];
+            for (int i = 0; i < 4; ++i)
+                if (4 * ch + i < DPX && 4 * ch + i < d) dw[4 * ch + i < DPX ? 4 * ch + i : 0] = o[i];
+        }
     }
 }
 
@@ -200,7 +206,11 @@ __device__ __forceinline__ void reduce_rows_to(float* dst, const float* acc, int
 }
 
 // ================================================================================== critic (tensor)
+// DP > 0: instantiation for dim (and control_dim + 1) <= DP with equation EQN fixed at compile time -- the
+// per-path vectors are register arrays and every d-loop is unrolled; <0,-1>: generic run-time version.
+template <int DP, int EQN>
 __global__ void __launch_bounds__(TC_THREADS, 1) critic_tc_kernel(const TcArgs a) {
+    constexpr int DPX = DP > 0 ? DP : 32;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     TcSmem S;
     tc_carve(S, smem_raw, a);
@@ -235,10 +245,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) critic_tc_kernel(const TcArgs a
     const float fill = 0.5f * E.R / sqrtf((float)d);
     float* traj = a.scratch + (size_t)blockIdx.x * a.scratch_per_cta;               // [N][2*sr][128]
     unsigned char* copies = a.copies ? a.copies + (size_t)blockIdx.x * a.copies_per_cta : nullptr;
-    float* gsV = a.slabV ? a.slabV + (size_t)blockIdx.x * gV.gtotal : nullptr;
-    float* gsG = a.slabG ? a.slabG + (size_t)blockIdx.x * gG.gtotal : nullptr;
-    float sxV[32], s0V[32], sxG[32], s0G[32];
-    for (int k = 0; k < 32; ++k) { sxV[k] = 0.f; s0V[k] = 0.f; sxG[k] = 0.f; s0G[k] = 0.f; }
+    float* gsV = a.slabV ? a.slabV + (size_t)(blockIdx.x % a.nslab) * gV.gtotal : nullptr;
+    float* gsG = a.slabG ? a.slabG + (size_t)(blockIdx.x % a.nslab) * gG.gtotal : nullptr;
+    float sxV[DPX], s0V[DPX], sxG[DPX], s0G[DPX];
+    KLOOP(k, DPX) { sxV[k] = 0.f; s0V[k] = 0.f; sxG[k] = 0.f; s0G[k] = 0.f; }
 
     float loss0 = 0.f, loss1 = 0.f;
     const long long ntiles = (a.B_local + TC_PATHS - 1) / TC_PATHS;
@@ -247,16 +257,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) critic_tc_kernel(const TcArgs a
         const long long gp = base + row;                          // local path index of this thread
         const bool valid = is_path && gp < a.B_local;
         const bool wr = valid && primary;               // this thread does the global stores of its path
-        float x[32], u[32], dwv[32], sdw[32], g[32], raw[32];
+        float x[DPX], u[DPX], dwv[DPX], sdw[DPX], g[DPX], raw[DPX];
         int flag = 0, nacc = 0;
         float disc = 1.f, y = 0.f;
         if (is_path) {
-            _Pragma("unroll 4")
-            for (int k = 0; k < d; ++k) x[k] = valid ? a.x0[gp * d + k] : fill;
-            flag = fwd_initial_flag(E, x, 1, 0);
+            KLOOP(k, d) x[k] = valid ? a.x0[gp * d + k] : fill;
+            flag = fwd_initial_flag<float, DP, EQN>(E, x, 1, 0);
             if (a.o_x && wr)
-                _Pragma("unroll 4")
-                for (int k = 0; k < d; ++k) a.o_x[(gp * d + k) * (long long)(N + 1)] = x[k];
+                KLOOP(k, d) a.o_x[(gp * d + k) * (long long)(N + 1)] = x[k];
         }
         if (is_ctrl) {                                            // schedule of the rollout
             ctrl_flush(C);
@@ -278,35 +286,32 @@ __global__ void __launch_bounds__(TC_THREADS, 1) critic_tc_kernel(const TcArgs a
                 if (!cheat) path_net_begin(P, nA, S.vecA, x);
                 path_dw(a, gp, valid, t, dwv);
                 float dt, sqdt, xn; int dtg;
-                fwd_dt(E, x, flag, 1, 0, dt, sqdt, xn, dtg);
+                fwd_dt<float, DP, EQN>(E, x, flag, 1, 0, dt, sqdt, xn, dtg);
                 if (cheat) {
-                    eq_u_true(E, x, u, 1, 0);
+                    eq_u_true<float, DP, EQN>(E, x, u, 1, 0);
                 } else {
                     path_net_finish(P, nA, S.vecA, raw);
-                    if (nA.ekn_head) ekn_head_fwd(raw, u, nA.mctrl, 1, 0);
-                    else for (int j = 0; j < E.m; ++j) u[j] = raw[j];
+                    if (nA.ekn_head) ekn_head_fwd<float, DP, EQN>(raw, u, nA.mctrl, 1, 0);
+                    else KLOOP(j, E.m) u[j] = raw[j];
                 }
                 if (td1) path_net_begin(P, nG, S.vecG, x);                        // NN_value_grad at x_t (before the move)
                 float* tr = traj + (size_t)t * 2 * sr * TC_PATHS;
                 if (need_grad && td1 && primary)
-                    _Pragma("unroll 4")
-                    for (int k = 0; k < d; ++k) tr[k * TC_PATHS + row] = x[k];
+                    KLOOP(k, d) tr[k * TC_PATHS + row] = x[k];
                 float w = 0.f;
-                if (!prop_only) w = eq_w(E, x, u, 1, 0);
-                const int coef = fwd_move(E, x, u, dwv, dt, sqdt, xn, flag, sdw, 1, 0);
+                if (!prop_only) w = eq_w<float, DP, EQN>(E, x, u, 1, 0);
+                const int coef = fwd_move<float, DP, EQN>(E, x, u, dwv, dt, sqdt, xn, flag, sdw, 1, 0);
                 const float cf = (float)coef;
                 if (td1) path_net_finish(P, nG, S.vecG, g);
                 y = y + w * disc * cf * dt;                                       // solver.py:170-174
                 if (td1) {
                     float dif = 0.f;
-                    _Pragma("unroll 4")
-                    for (int k = 0; k < d; ++k) dif = dif + sdw[k] * g[k];        // solver.py:177-182
+                    KLOOP(k, d) dif = dif + sdw[k] * g[k];        // solver.py:177-182
                     dif = dif * disc;
                     y = y - dif * cf * sqdt;                                      // solver.py:184
                     if (need_grad && primary) {
                         const float q = disc * cf * sqdt;
-                        _Pragma("unroll 4")
-                        for (int k = 0; k < d; ++k) tr[(sr + k) * TC_PATHS + row] = sdw[k] * q;
+                        KLOOP(k, d) tr[(sr + k) * TC_PATHS + row] = sdw[k] * q;
                     }
                 }
                 disc = disc * expf(-E.gamma * dt * cf);                          // solver.py:187
@@ -315,8 +320,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) critic_tc_kernel(const TcArgs a
                     if (a.o_dt) a.o_dt[gp * N + t] = dt;
                     if (a.o_coef) a.o_coef[gp * N + t] = cf;
                     if (a.o_x)
-                        _Pragma("unroll 4")
-                        for (int k = 0; k < d; ++k) a.o_x[(gp * d + k) * (long long)(N + 1) + t + 1] = x[k];
+                        KLOOP(k, d) a.o_x[(gp * d + k) * (long long)(N + 1) + t + 1] = x[k];
                 }
             }
         }
@@ -325,8 +329,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) critic_tc_kernel(const TcArgs a
                 if (a.o_dt) a.o_dt[gp * N + t] = E.delta_t;
                 if (a.o_coef) a.o_coef[gp * N + t] = 0.f;
                 if (a.o_x)
-                    _Pragma("unroll 4")
-                    for (int k = 0; k < d; ++k) a.o_x[(gp * d + k) * (long long)(N + 1) + t + 1] = x[k];
+                    KLOOP(k, d) a.o_x[(gp * d + k) * (long long)(N + 1) + t + 1] = x[k];
             }
             if (a.o_exit) a.o_exit[gp] = nacc;
         }
@@ -347,11 +350,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) critic_tc_kernel(const TcArgs a
                 for (int i = 0; i < 3; ++i) { ctrl_net_forward(C, nV, nV.L); ctrl_net_backward(C, nV, true, copies); }
             }
         } else if (is_path) {
-            float vN[1], v0[1], vb[1], x0v[32], xbv[32], dy0[32], cot[1];
-            _Pragma("unroll 4")
-            for (int k = 0; k < d; ++k) x0v[k] = valid ? a.x0[gp * d + k] : fill;
-            _Pragma("unroll 4")
-            for (int k = 0; k < d; ++k) xbv[k] = valid ? a.xb[gp * d + k] : fill;
+            float vN[1], v0[1], vb[1], x0v[DPX], xbv[DPX], dy0[DPX], cot[1];
+            KLOOP(k, d) x0v[k] = valid ? a.x0[gp * d + k] : fill;
+            KLOOP(k, d) xbv[k] = valid ? a.xb[gp * d + k] : fill;
             if (!need_grad) {
                 path_net_forward(P, nV, S.vecV, x0v, v0);
                 path_net_forward(P, nV, S.vecV, x, vN);
@@ -364,22 +365,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) critic_tc_kernel(const TcArgs a
                 rhog = valid ? rho_grad(delta, 50.f) * scale : 0.f;
                 cot[0] = -rhog * disc;
                 path_net_backward(P, nV, gV, mk, cot, true, gsV, S.dz, row, dy0);
-                _Pragma("unroll 4")
-                for (int k = 0; k < d; ++k) { sxV[k] += x[k] * dy0[k]; s0V[k] += dy0[k]; }
+                KLOOP(k, d) { sxV[k] += x[k] * dy0[k]; s0V[k] += dy0[k]; }
                 path_net_forward_keep(P, nV, S.vecV, x0v, v0, mk, copies, S.act, row, false);
                 cot[0] = rhog;
                 path_net_backward(P, nV, gV, mk, cot, true, gsV, S.dz, row, dy0);
-                _Pragma("unroll 4")
-                for (int k = 0; k < d; ++k) { sxV[k] += x0v[k] * dy0[k]; s0V[k] += dy0[k]; }
+                KLOOP(k, d) { sxV[k] += x0v[k] * dy0[k]; s0V[k] += dy0[k]; }
                 path_net_forward_keep(P, nV, S.vecV, xbv, vb, mk, copies, S.act, row, false);
-                const float dbb = vb[0] - eq_Z(E, xbv, 1, 0);
+                const float dbb = vb[0] - eq_Z<float, DP, EQN>(E, xbv, 1, 0);
                 cot[0] = valid ? rho_grad(dbb, 50.f) * scale : 0.f;
                 path_net_backward(P, nV, gV, mk, cot, true, gsV, S.dz, row, dy0);
-                _Pragma("unroll 4")
-                for (int k = 0; k < d; ++k) { sxV[k] += xbv[k] * dy0[k]; s0V[k] += dy0[k]; }
+                KLOOP(k, d) { sxV[k] += xbv[k] * dy0[k]; s0V[k] += dy0[k]; }
             }
             const float delta = v0[0] - y - vN[0] * disc;                         // solver.py:189
-            const float db = vb[0] - eq_Z(E, xbv, 1, 0);                          // solver.py:190
+            const float db = vb[0] - eq_Z<float, DP, EQN>(E, xbv, 1, 0);                          // solver.py:190
             if (wr) {
                 rho_v = rho(delta, 50.f);
                 rho_b = rho(db, 50.f);
@@ -402,15 +400,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) critic_tc_kernel(const TcArgs a
                 }
             } else if (is_path) {
                 Masks mk;
-                float xt[32], cot[32], dy0[32];
+                float xt[DPX], cot[DPX], dy0[DPX];
                 for (int t = 0; t < tlive; ++t) {
                     const float* tr = traj + (size_t)t * 2 * sr * TC_PATHS;
-                    _Pragma("unroll 4")
-                    for (int k = 0; k < d; ++k) { xt[k] = tr[k * TC_PATHS + row]; cot[k] = tr[(sr + k) * TC_PATHS + row] * rhog; }
-                    path_net_forward_keep(P, nG, S.vecG, xt, (float*)nullptr, mk, copies, S.act, row, true);
+                    KLOOP(k, d) { xt[k] = tr[k * TC_PATHS + row]; cot[k] = tr[(sr + k) * TC_PATHS + row] * rhog; }
+                    float unused[1];
+                    path_net_forward_keep(P, nG, S.vecG, xt, unused, mk, copies, S.act, row, true);
                     path_net_backward(P, nG, gG, mk, cot, true, gsG, S.dz, row, dy0);
-                    _Pragma("unroll 4")
-                    for (int k = 0; k < d; ++k) { sxG[k] += xt[k] * dy0[k]; s0G[k] += dy0[k]; }
+                    KLOOP(k, d) { sxG[k] += xt[k] * dy0[k]; s0G[k] += dy0[k]; }
                 }
             }
         }
@@ -435,7 +432,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) critic_tc_kernel(const TcArgs a
 }
 
 // =================================================================================== actor (tensor)
+template <int DP, int EQN>
 __global__ void __launch_bounds__(TC_THREADS, 1) actor_tc_kernel(const TcArgs a) {
+    constexpr int DPX = DP > 0 ? DP : 32;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     TcSmem S;
     tc_carve(S, smem_raw, a);
@@ -469,9 +468,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) actor_tc_kernel(const TcArgs a)
     const int trs = 2 * sr + A_NSCAL;
     float* traj = a.scratch + (size_t)blockIdx.x * a.scratch_per_cta;               // [N][2*sr + A_NSCAL][128]
     unsigned char* copies = a.copies ? a.copies + (size_t)blockIdx.x * a.copies_per_cta : nullptr;
-    float* gsA = a.slabA ? a.slabA + (size_t)blockIdx.x * gA.gtotal : nullptr;
-    float sxA[32], s0A[32];
-    for (int k = 0; k < 32; ++k) { sxA[k] = 0.f; s0A[k] = 0.f; }
+    float* gsA = a.slabA ? a.slabA + (size_t)(blockIdx.x % a.nslab) * gA.gtotal : nullptr;
+    float sxA[DPX], s0A[DPX];
+    KLOOP(k, DPX) { sxA[k] = 0.f; s0A[k] = 0.f; }
 
     float loss0 = 0.f;
     const long long ntiles = (a.B_local + TC_PATHS - 1) / TC_PATHS;
@@ -480,16 +479,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) actor_tc_kernel(const TcArgs a)
         const long long gp = base + row;
         const bool valid = is_path && gp < a.B_local;
         const bool wr = valid && primary;               // this thread does the global stores of its path
-        float x[32], u[32], dwv[32], raw[32];
+        float x[DPX], u[DPX], dwv[DPX], raw[DPX];
         int flag = 0, nacc = 0;
         float disc = 1.f, y = 0.f;
         if (is_path) {
-            _Pragma("unroll 4")
-            for (int k = 0; k < d; ++k) x[k] = valid ? a.x0[gp * d + k] : fill;
-            flag = fwd_initial_flag(E, x, 1, 0);
+            KLOOP(k, d) x[k] = valid ? a.x0[gp * d + k] : fill;
+            flag = fwd_initial_flag<float, DP, EQN>(E, x, 1, 0);
             if (a.o_x && wr)
-                _Pragma("unroll 4")
-                for (int k = 0; k < d; ++k) a.o_x[(gp * d + k) * (long long)(N + 1)] = x[k];
+                KLOOP(k, d) a.o_x[(gp * d + k) * (long long)(N + 1)] = x[k];
         }
         if (is_ctrl) {
             ctrl_flush(C);
@@ -508,20 +505,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) actor_tc_kernel(const TcArgs a)
                 if (!cheat) path_net_begin(P, nA, S.vecA, x);
                 path_dw(a, gp, valid, t, dwv);
                 float dt, sqdt, xn; int dtg;
-                fwd_dt(E, x, flag, 1, 0, dt, sqdt, xn, dtg);
+                fwd_dt<float, DP, EQN>(E, x, flag, 1, 0, dt, sqdt, xn, dtg);
                 if (cheat) {
-                    eq_u_true(E, x, u, 1, 0);
+                    eq_u_true<float, DP, EQN>(E, x, u, 1, 0);
                 } else {
                     path_net_finish(P, nA, S.vecA, raw);
-                    if (nA.ekn_head) ekn_head_fwd(raw, u, nA.mctrl, 1, 0);
-                    else for (int j = 0; j < m; ++j) u[j] = raw[j];
+                    if (nA.ekn_head) ekn_head_fwd<float, DP, EQN>(raw, u, nA.mctrl, 1, 0);
+                    else KLOOP(j, m) u[j] = raw[j];
                 }
                 float* tr = traj + (size_t)t * trs * TC_PATHS;
                 if (need_grad && primary)
-                    _Pragma("unroll 4")
-                    for (int k = 0; k < d; ++k) { tr[k * TC_PATHS + row] = x[k]; tr[(sr + k) * TC_PATHS + row] = dwv[k]; }
-                const float w = eq_w(E, x, u, 1, 0);
-                const int coef = fwd_move(E, x, u, dwv, dt, sqdt, xn, flag, (float*)nullptr, 1, 0);
+                    KLOOP(k, d) { tr[k * TC_PATHS + row] = x[k]; tr[(sr + k) * TC_PATHS + row] = dwv[k]; }
+                const float w = eq_w<float, DP, EQN>(E, x, u, 1, 0);
+                const int coef = fwd_move<float, DP, EQN>(E, x, u, dwv, dt, sqdt, xn, flag, (float*)nullptr, 1, 0);
                 const float cf = (float)coef;
                 if (need_grad && primary) {
                     float* sc = tr + (size_t)2 * sr * TC_PATHS;
@@ -535,8 +531,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) actor_tc_kernel(const TcArgs a)
                     if (a.o_dt) a.o_dt[gp * N + t] = dt;
                     if (a.o_coef) a.o_coef[gp * N + t] = cf;
                     if (a.o_x)
-                        _Pragma("unroll 4")
-                        for (int k = 0; k < d; ++k) a.o_x[(gp * d + k) * (long long)(N + 1) + t + 1] = x[k];
+                        KLOOP(k, d) a.o_x[(gp * d + k) * (long long)(N + 1) + t + 1] = x[k];
                 }
             }
         }
@@ -545,14 +540,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) actor_tc_kernel(const TcArgs a)
                 if (a.o_dt) a.o_dt[gp * N + t] = E.delta_t;
                 if (a.o_coef) a.o_coef[gp * N + t] = 0.f;
                 if (a.o_x)
-                    _Pragma("unroll 4")
-                    for (int k = 0; k < d; ++k) a.o_x[(gp * d + k) * (long long)(N + 1) + t + 1] = x[k];
+                    KLOOP(k, d) a.o_x[(gp * d + k) * (long long)(N + 1) + t + 1] = x[k];
             }
             if (a.o_exit) a.o_exit[gp] = nacc;
         }
         // ------------------------------------------------------------------ terminal value (+ its input gradient)
         float yv = 0.f;
-        float lam[32];
+        float lam[DPX];
         float Dbar = 0.f;
         if (is_ctrl) {
             ctrl_flush(C);
@@ -567,23 +561,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) actor_tc_kernel(const TcArgs a)
             float vN[1];
             const float seed = valid ? disc * a.invB : 0.f;
             if (cheat_v) {
-                vN[0] = eq_V_true(E, x, 1, 0);                                    // solver.py:223
+                vN[0] = eq_V_true<float, DP, EQN>(E, x, 1, 0);                                    // solver.py:223
                 if (need_grad) {
-                    eq_V_grad_true(E, x, lam, 1, 0);
-                    _Pragma("unroll 4")
-                    for (int k = 0; k < d; ++k) lam[k] = lam[k] * seed;
+                    eq_V_grad_true<float, DP, EQN>(E, x, lam, 1, 0);
+                    KLOOP(k, d) lam[k] = lam[k] * seed;
                 }
             } else if (!need_grad) {
                 path_net_forward(P, nV, S.vecV, x, vN);                         // solver.py:221
             } else {
                 Masks mk;
-                float cot[1], dy0[32];
+                float cot[1], dy0[DPX];
                 path_net_forward_keep(P, nV, S.vecV, x, vN, mk, nullptr, nullptr, row, false);
                 cot[0] = seed;
                 path_net_backward(P, nV, gV, mk, cot, false, nullptr, nullptr, row, dy0);
                 const float* g0c = S.vecV + nV.vec_g0;
-                _Pragma("unroll 4")
-                for (int k = 0; k < d; ++k) lam[k] = dy0[k] * g0c[k];
+                KLOOP(k, d) lam[k] = dy0[k] * g0c[k];
             }
             Dbar = valid ? vN[0] * a.invB : 0.f;
             y = y + vN[0] * disc;
@@ -611,25 +603,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1) actor_tc_kernel(const TcArgs a)
                 ctrl_net_backward(C, nA, true, copies);
             } else if (is_path) {
                 Masks mk;
-                float xt[32], ubar[32], cot[32], dy0[32];
-                _Pragma("unroll 4")
-                for (int k = 0; k < d; ++k) { xt[k] = tr[k * TC_PATHS + row]; dwv[k] = tr[(sr + k) * TC_PATHS + row]; }
+                float xt[DPX], ubar[DPX], cot[DPX], dy0[DPX];
+                KLOOP(k, d) { xt[k] = tr[k * TC_PATHS + row]; dwv[k] = tr[(sr + k) * TC_PATHS + row]; }
                 path_net_forward_keep(P, nA, S.vecA, xt, raw, mk, copies, S.act, row, false);
-                if (nA.ekn_head) ekn_head_fwd(raw, u, nA.mctrl, 1, 0);
-                else for (int j = 0; j < m; ++j) u[j] = raw[j];
+                if (nA.ekn_head) ekn_head_fwd<float, DP, EQN>(raw, u, nA.mctrl, 1, 0);
+                else KLOOP(j, m) u[j] = raw[j];
                 const int coef = (valid && sc[A_COEF * TC_PATHS + row] > 0.f) ? 1 : 0;
-                adj_step(E, xt, u, dwv, sc[A_DT * TC_PATHS + row], sc[A_SQDT * TC_PATHS + row], coef, (int)sc[A_DTG * TC_PATHS + row],
+                adj_step<float, DP, EQN>(E, xt, u, dwv, sc[A_DT * TC_PATHS + row], sc[A_SQDT * TC_PATHS + row], coef, (int)sc[A_DTG * TC_PATHS + row],
                          sc[A_XN * TC_PATHS + row], sc[A_DISC * TC_PATHS + row], a.invB, lam, Dbar, ubar, 1, 0);
                 if (nA.ekn_head) {
-                    if (coef) ekn_head_bwd(raw, ubar, cot, m, 1, 0);
-                    else for (int j = 0; j <= m; ++j) cot[j] = 0.f;
+                    if (coef) ekn_head_bwd<float, DP, EQN>(raw, ubar, cot, m, 1, 0);
+                    else KLOOP(j, m + 1) cot[j] = 0.f;
                 } else {
-                    for (int j = 0; j < m; ++j) cot[j] = ubar[j];
+                    KLOOP(j, m) cot[j] = ubar[j];
                 }
                 path_net_backward(P, nA, gA, mk, cot, true, gsA, S.dz, row, dy0);
                 const float* g0c = S.vecA + nA.vec_g0;
-                _Pragma("unroll 4")
-                for (int k = 0; k < d; ++k) {
+                KLOOP(k, d) {
                     sxA[k] += xt[k] * dy0[k]; s0A[k] += dy0[k];
                     lam[k] = lam[k] + dy0[k] * g0c[k];
                 }

@@ -346,20 +346,43 @@ __device__ __forceinline__ void affine16(const uint32_t* r, const float* gc, con
     }
 }
 
-// y0 = x * g0c + b0 (solver.py:265) -> planes; x: this thread's point (in values)
-__device__ __forceinline__ void path_write_y0(PathCtx& p, const TcNet& t, const float* vec, const float* x) {
+// 16 features 16c.. of this thread's row (packed bf16 hi words) -> image (R = 128 rows) at `img` (shared or global)
+__device__ __forceinline__ void copy16h(unsigned char* img, int row, int c, uint32_t* w, int one_at /* feature index set to 1, or -1 */) {
+    const int o = one_at - 16 * c;
+    if (o >= 0 && o < 16) {                                          // bf16(1.0) = 0x3F80
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            if (o == 2 * j) w[j] = (w[j] & 0xffff0000u) | 0x3F80u;
+            if (o == 2 * j + 1) w[j] = (w[j] & 0x0000ffffu) | 0x3F800000u;
+        }
+    }
+    unsigned char* p = img + (size_t)(2 * c) * 2048 + (row >> 3) * 128 + (row & 7) * 16;
+    *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+    *reinterpret_cast<uint4*>(p + 2048) = make_uint4(w[4], w[5], w[6], w[7]);
+}
+
+// y0 = x * g0c + b0 (solver.py:265) -> planes (+ bf16 copy with the constant-1 feature when `copies`), then
+// publish.  Everything indexed statically (K16_0 <= 32) so that x can live in registers.
+template <int NX>
+__device__ __forceinline__ void path_put_y0(PathCtx& p, const TcNet& t, const float* vec, const float (&x)[NX], unsigned char* copies, int row) {
     const int K0 = t.ly[0].K16;
     const float* g0c = vec + t.vec_g0;
     const float* b0 = g0c + K0;
-    for (int c = p.grp; c < K0 / 16; c += 2) {
-        float v[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-            const int k = 16 * c + j;
-            v[j] = (k < t.in) ? x[k] * g0c[k] + b0[k] : 0.f;
+    for (int c = 0; c < 2; ++c) {
+        if (c < K0 / 16 && (c & 1) == p.grp) {
+            float v[16];
+            uint32_t h[8];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const int k = 16 * c + j;
+                v[j] = (k < NX && k < t.in) ? x[k < NX ? k : 0] * g0c[k] + b0[k] : 0.f;
+            }
+            put16h(p.tl, c, v, h);
+            if (copies) copy16h(copies, row, c, h, t.ly[0].kl);
         }
-        put16(p.tl, c, v);
     }
+    if (copies) fence_proxy_async_all();
     path_publish(p);
 }
 
@@ -380,37 +403,46 @@ __device__ __forceinline__ void path_epi_hidden(PathCtx& p, const float* gcbb, i
     p.t_hid += clock64() - th0;
 }
 
-// last layer: out[n] = acc * gc + bb (solver.py:270-271), n < nl
-__device__ __forceinline__ void path_epi_last(PathCtx& p, const float* gcbb, int N16, int nl, float* out) {
+// last layer: out[n] = acc * gc + bb (solver.py:270-271), n < nl <= 32; static indexing
+template <int NO>
+__device__ __forceinline__ void path_last(PathCtx& p, const float* gcbb, int N16, int nl, float (&out)[NO]) {
     path_wait_acc(p);
     const float* gc = gcbb;
     const float* bb = gcbb + N16;
-    for (int c = 0; c < N16 / 16; ++c) {
-        uint32_t r[16];
-        tmem_ld16(p.tl + COL_ACC + 16 * c, r);
-        tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-            const int n = 16 * c + j;
-            if (n < nl) out[n] = __uint_as_float(r[j]) * gc[n] + bb[n];
+    for (int c = 0; c < 2; ++c) {
+        if (c < N16 / 16) {
+            uint32_t r[16];
+            tmem_ld16(p.tl + COL_ACC + 16 * c, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const int n = 16 * c + j;
+                if (n < NO && n < nl) out[n < NO ? n : 0] = __uint_as_float(r[j]) * gc[n] + bb[n];
+            }
         }
     }
 }
 
-// whole network, forward only: x -> raw output (before the ekn head).  Split in two so that the caller can
-// put per-path arithmetic that does not need the output between begin and finish (it then runs while the
-// tensor pipe works on the first layer).
-__device__ __forceinline__ void path_net_begin(PathCtx& p, const TcNet& t, const float* vec, const float* x) {
-    path_write_y0(p, t, vec, x);
-}
-__device__ __noinline__ void path_net_finish(PathCtx& p, const TcNet& t, const float* vec, float* out) {
+// all hidden-layer epilogues of a forward-only evaluation (no per-path arrays involved)
+__device__ __noinline__ void path_hidden(PathCtx& p, const TcNet& t, const float* vec) {
     for (int l = 0; l < t.L; ++l) path_epi_hidden(p, vec + t.ly[l].vec, t.ly[l].N16);
-    path_epi_last(p, vec + t.ly[t.L].vec, t.ly[t.L].N16, t.ly[t.L].nl, out);
 }
-__device__ __noinline__ void path_net_forward(PathCtx& p, const TcNet& t, const float* vec, const float* x, float* out) {
-    path_write_y0(p, t, vec, x);
-    for (int l = 0; l < t.L; ++l) path_epi_hidden(p, vec + t.ly[l].vec, t.ly[l].N16);
-    path_epi_last(p, vec + t.ly[t.L].vec, t.ly[t.L].N16, t.ly[t.L].nl, out);
+
+// forward-only evaluation:  begin (y0 -> planes)  ...caller's own arithmetic...  finish (-> raw output)
+template <int NX>
+__device__ __forceinline__ void path_net_begin(PathCtx& p, const TcNet& t, const float* vec, const float (&x)[NX]) {
+    path_put_y0(p, t, vec, x, nullptr, 0);
+}
+template <int NO>
+__device__ __forceinline__ void path_net_finish(PathCtx& p, const TcNet& t, const float* vec, float (&out)[NO]) {
+    path_hidden(p, t, vec);
+    path_last(p, vec + t.ly[t.L].vec, t.ly[t.L].N16, t.ly[t.L].nl, out);
+}
+template <int NX, int NO>
+__device__ __forceinline__ void path_net_forward(PathCtx& p, const TcNet& t, const float* vec, const float (&x)[NX], float (&out)[NO]) {
+    path_net_begin(p, t, vec, x);
+    path_net_finish(p, t, vec, out);
 }
 
 }  // namespace tc
@@ -516,47 +548,15 @@ __device__ __noinline__ void ctrl_net_backward(Ctrl& c, const TcNet& t, bool nee
 // ---- path threads ------------------------------------------------------------------------------------
 struct Masks { uint32_t m[MAXLIN][8]; };     // m[l] bit k: a_l[k] > 0  (l = 1..L), K16 <= 256
 
-// 16 features 16c.. of this thread's row (packed bf16 hi words) -> image (R = 128 rows) at `img` (shared or global)
-__device__ __forceinline__ void copy16h(unsigned char* img, int row, int c, uint32_t* w, int one_at /* feature index set to 1, or -1 */) {
-    const int o = one_at - 16 * c;
-    if (o >= 0 && o < 16) {                                          // bf16(1.0) = 0x3F80
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            if (o == 2 * j) w[j] = (w[j] & 0xffff0000u) | 0x3F80u;
-            if (o == 2 * j + 1) w[j] = (w[j] & 0x0000ffffu) | 0x3F800000u;
-        }
-    }
-    unsigned char* p = img + (size_t)(2 * c) * 2048 + (row >> 3) * 128 + (row & 7) * 16;
-    *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
-    *reinterpret_cast<uint4*>(p + 2048) = make_uint4(w[4], w[5], w[6], w[7]);
-}
-
-// forward keeping what the backward needs: relu masks (registers), bf16 copies of a_0..a_{L-1} (global
-// scratch `copies`, NULL: none) and of a_L (shared ACT image, NULL: none).  skip_last: stop after the
-// last hidden layer (the raw output is not needed) -- then the caller must write dz_L and publish.
-__device__ __noinline__ void path_net_forward_keep(PathCtx& p, const TcNet& t, const float* vec, const float* x, float* out, Masks& mk,
-                                                      unsigned char* copies, unsigned char* act, int row, bool skip_last) {
+// hidden layers of a forward evaluation that keeps what the backward needs: relu masks (bits), bf16 copies of
+// a_1..a_{L-1} (global scratch `copies`, NULL: none) and of a_L (shared ACT image, NULL: none).
+// skip_last: the raw output is not needed -- the last hidden epilogue does not publish (the caller writes
+// dz_L and publishes).
+__device__ __noinline__ void path_hidden_keep(PathCtx& p, const TcNet& t, const float* vec, Masks& mk, unsigned char* copies,
+                                              unsigned char* act, int row, bool skip_last) {
     for (int l = 0; l <= t.L; ++l)
 #pragma unroll
         for (int w = 0; w < 8; ++w) mk.m[l][w] = 0u;
-    {
-        const int K0 = t.ly[0].K16;
-        const float* g0c = vec + t.vec_g0;
-        const float* b0 = g0c + K0;
-        for (int c = p.grp; c < K0 / 16; c += 2) {
-            float v[16];
-            uint32_t h[8];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                const int k = 16 * c + j;
-                v[j] = (k < t.in) ? x[k] * g0c[k] + b0[k] : 0.f;
-            }
-            put16h(p.tl, c, v, h);
-            if (copies) copy16h(copies, row, c, h, t.ly[0].kl);
-        }
-        if (copies) fence_proxy_async_all();
-        path_publish(p);
-    }
     for (int l = 0; l < t.L; ++l) {
         const int N16 = t.ly[l].N16;
         const float* gc = vec + t.ly[l].vec;
@@ -582,7 +582,14 @@ __device__ __noinline__ void path_net_forward_keep(PathCtx& p, const TcNet& t, c
         if (dst) fence_proxy_async_all();
         if (!(last_hidden && skip_last)) path_publish(p);
     }
-    if (!skip_last) path_epi_last(p, vec + t.ly[t.L].vec, t.ly[t.L].N16, t.ly[t.L].nl, out);
+}
+// x -> (masks, copies) [-> raw output]
+template <int NX, int NO>
+__device__ __forceinline__ void path_net_forward_keep(PathCtx& p, const TcNet& t, const float* vec, const float (&x)[NX], float (&out)[NO],
+                                                      Masks& mk, unsigned char* copies, unsigned char* act, int row, bool skip_last) {
+    path_put_y0(p, t, vec, x, copies, row);
+    path_hidden_keep(p, t, vec, mk, copies, act, row, skip_last);
+    if (!skip_last) path_last(p, vec + t.ly[t.L].vec, t.ly[t.L].N16, t.ly[t.L].nl, out);
 }
 
 // this thread's row of a dW block -> RED into the slab:  rows f = 128*blk + row (f <= kl), cols n < nl
@@ -615,60 +622,83 @@ __device__ __forceinline__ void path_drain(PathCtx& p, int blk, int row, int kl,
     mbar_arrive(p.a_ready);                    // accumulator drained
 }
 
-// cotangent row (N16 values, zero beyond nl) -> planes (+ DZ image)
-__device__ __forceinline__ void path_write_dz(PathCtx& p, const float* dz, int N16, unsigned char* dzimg, int row) {
-    for (int c = p.grp; c < N16 / 16; c += 2) {
-        uint32_t h[8];
-        put16h(p.tl, c, dz + 16 * c, h);
-        if (dzimg) copy16h(dzimg, row, c, h, -1);
+// cotangent of the raw output (nl <= 32 values, static indexing) -> planes (+ DZ image), publish
+template <int NO>
+__device__ __forceinline__ void path_put_dz(PathCtx& p, const TcNet& t, const float (&dout)[NO], unsigned char* dzimg, int row) {
+    const int N16 = t.ly[t.L].N16, nl = t.ly[t.L].nl;
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+        if (c < N16 / 16 && (c & 1) == p.grp) {
+            float v[16];
+            uint32_t h[8];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const int n = 16 * c + j;
+                v[j] = (n < NO && n < nl) ? dout[n < NO ? n : 0] : 0.f;
+            }
+            put16h(p.tl, c, v, h);
+            if (dzimg) copy16h(dzimg, row, c, h, -1);
+        }
     }
     if (dzimg) fence_proxy_async();
     path_publish(p);
 }
 
-// backward of one network evaluation on the path side.  dout: cotangent of the raw output (nl_L values).
-// slab: this CTA's gradient slab of the network (need_w) ; dy0 receives the cotangent of y0 (in values).
-__device__ __noinline__ void path_net_backward(PathCtx& p, const TcNet& t, const TcSlab& g, const Masks& mk, const float* dout, bool need_w,
-                                                  float* slab, unsigned char* dzimg, int row, float* dy0) {
-    {
-        float v[32];
-        const int N16 = t.ly[t.L].N16;
-        for (int n = 0; n < N16; ++n) v[n] = (n < t.ly[t.L].nl) ? dout[n] : 0.f;
-        path_write_dz(p, v, N16, need_w ? dzimg : nullptr, row);
-    }
+// middle of the backward: for l = L..0 the dW drains (need_w), and for l >= 1 the dX epilogue
+// dz_{l-1} = dA_l (.) slope(a_l) -> planes (+ DZ).  Ends before the result of the last product (dy0) is read.
+__device__ __noinline__ void path_backward_mid(PathCtx& p, const TcNet& t, const TcSlab& g, const Masks& mk, bool need_w, float* slab,
+                                               unsigned char* dzimg, int row) {
     for (int l = t.L; l >= 0; --l) {
         if (need_w) {
             const int nblk = (t.ly[l].kl + 1 + 127) >> 7;
             for (int b = 0; b < nblk; ++b) path_drain(p, b, row, t.ly[l].kl, t.ly[l].nl, t.ly[l].N16, slab + g.gW[l]);
         }
+        if (l == 0) break;
         path_wait_acc(p);                                                // dA_l in the accumulator (K16_l columns)
         const int K16 = t.ly[l].K16;
-        if (l > 0) {
-            for_acc_chunks(p.tl, p.grp, K16 / 16, [&](int c, const uint32_t* r) {
-                const uint32_t bits = mk.m[l][c >> 1] >> ((c & 1) * 16);
-                float v[16];
-                uint32_t h[8];
+        for_acc_chunks(p.tl, p.grp, K16 / 16, [&](int c, const uint32_t* r) {
+            const uint32_t bits = mk.m[l][c >> 1] >> ((c & 1) * 16);
+            float v[16];
+            uint32_t h[8];
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const float a = __uint_as_float(r[j]);
-                    v[j] = ((bits >> j) & 1u) ? 2.f * a : a;                 // d(z + relu z)
-                }
-                put16h(p.tl, c, v, h);
-                if (need_w) copy16h(dzimg, row, c, h, -1);
-            });
-            if (need_w) fence_proxy_async();
-            path_publish(p);
-        } else {
-            for (int c = 0; c < K16 / 16; ++c) {
-                uint32_t r[16];
-                tmem_ld16(p.tl + COL_ACC + 16 * c, r);
-                tmem_ld_wait();
+            for (int j = 0; j < 16; ++j) {
+                const float a = __uint_as_float(r[j]);
+                v[j] = ((bits >> j) & 1u) ? 2.f * a : a;                     // d(z + relu z)
+            }
+            put16h(p.tl, c, v, h);
+            if (need_w) copy16h(dzimg, row, c, h, -1);
+        });
+        if (need_w) fence_proxy_async();
+        path_publish(p);
+    }
+}
+// cotangent of y0 (in <= 31 values, static indexing)
+template <int NX>
+__device__ __forceinline__ void path_get_dy0(PathCtx& p, const TcNet& t, float (&dy0)[NX]) {
+    path_wait_acc(p);
+    const int K16 = t.ly[0].K16;
 #pragma unroll
-                for (int j = 0; j < 16; ++j)
-                    if (16 * c + j < t.in) dy0[16 * c + j] = __uint_as_float(r[j]);
+    for (int c = 0; c < 2; ++c) {
+        if (c < K16 / 16) {
+            uint32_t r[16];
+            tmem_ld16(p.tl + COL_ACC + 16 * c, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const int k = 16 * c + j;
+                if (k < NX && k < t.in) dy0[k < NX ? k : 0] = __uint_as_float(r[j]);
             }
         }
     }
+}
+// backward of one network evaluation on the path side.  dout: cotangent of the raw output; slab: this CTA's
+// gradient slab of the network (need_w); dy0 receives the cotangent of y0.
+template <int NO, int NX>
+__device__ __forceinline__ void path_net_backward(PathCtx& p, const TcNet& t, const TcSlab& g, const Masks& mk, const float (&dout)[NO], bool need_w,
+                                                  float* slab, unsigned char* dzimg, int row, float (&dy0)[NX]) {
+    path_put_dz(p, t, dout, need_w ? dzimg : nullptr, row);
+    path_backward_mid(p, t, g, mk, need_w, slab, dzimg, row);
+    path_get_dy0(p, t, dy0);
 }
 
 }  // namespace tc
