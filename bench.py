@@ -173,7 +173,7 @@ def main():
                 "config": config_desc, "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
                 "cpu_model": cpu_model_name(), "iters_per_sec": 1.0 / r["sec_per_iter"],
                 "e2e": {"value": r["value"], "unit": "path-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
         return
 
     import numpy as np
@@ -182,6 +182,8 @@ def main():
     from deeppde_actorcritic_b200 import equation, munchify
     from deeppde_actorcritic_b200.solver import ActorCriticSolver
     torch.cuda.set_device(local_rank)
+    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"                      # keep stdout to the one JSON line (no NCCL version banner)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     impl = "exact" if args.impl == "exact" else "tensor"          # "ours" = the tensor path (tcgen05, bf16x3 products, FP32 accumulation)
@@ -314,8 +316,9 @@ def main():
                 "scaling": "strong", "vs_baseline": None, "dtype": ("f32 (bf16x3 tensor-core products, FP32 accumulate)" if impl == "tensor" else "f32" if args.dtype == "float32" else "f64"), "data": "synthetic",
                 "config": config_desc, "impl": impl, "iters_per_sec": args.steps / (ms * 1e-3), "clocks": clocks, "e2e": e2e,
                 "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "last_losses": losses}
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 
