@@ -70,6 +70,7 @@ SYMBOLS = {
                                  _P, _P, C.POINTER(dpb_path_outputs), _P, _I64, _P]),
     "dpb_mlp_forward": (C.c_int, [_P, C.c_int, _P, _P, _I64, _P, _P, _I64, _P]),
     "dpb_closed_form": (C.c_int, [_P, C.c_int, _P, _P, _I64, _P, _P]),
+    "dpb_err_metrics": (C.c_int, [_P, _P, _P, _I64, _P, _P]),
     "dpb_adam_step": (C.c_int, [_P, _P, _P, _P, _P, _I64, _D, _D, _D, _D, _P]),
     "dpb_philox_dw": (C.c_int, [_P, _I32, _U64, _U64, _I64, _I64, _I32, _P, _P]),
     "dpb_sample_x": (C.c_int, [_P, _U64, _U64, _I64, _I64, _P, _P, _P]),

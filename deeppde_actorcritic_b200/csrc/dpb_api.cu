@@ -744,3 +744,15 @@ extern "C" int dpb_tc_stats(dpb_handle* h, const void* workspace, int64_t B_loca
     DPB_CUDA(h, cudaMemcpy(out_host, (const char*)workspace + L.stats, 16 * 8, cudaMemcpyDeviceToHost));
     return DPB_OK;
 }
+
+extern "C" int dpb_err_metrics(dpb_handle* h, const void* truth, const void* approx, int64_t n, void* out3, void* stream) {
+    if (!h) return fail(nullptr, DPB_ERR_ARG, "dpb_err_metrics: null handle");
+    if (!truth || !approx || !out3 || n < 1) return fail(h, DPB_ERR_ARG, "dpb_err_metrics: bad argument");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) { cudaGetLastError(); return fail(h, DPB_ERR_CUDA, "dpb_err_metrics: no CUDA device (there is no CPU fallback)"); }
+    if (h->cfg.dtype == DPB_F64) err_metrics_kernel<double><<<1, 256, 0, (cudaStream_t)stream>>>((const double*)truth, (const double*)approx, n, (double*)out3);
+    else err_metrics_kernel<float><<<1, 256, 0, (cudaStream_t)stream>>>((const float*)truth, (const float*)approx, n, (float*)out3);
+    h->launches++;
+    DPB_CUDA(h, cudaGetLastError());
+    return DPB_OK;
+}

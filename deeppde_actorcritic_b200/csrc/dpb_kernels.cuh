@@ -574,6 +574,33 @@ __global__ void closed_form_kernel(EqnD eq, int which, const real* __restrict__ 
     }
 }
 
+// error metrics of solver.py:109-130 on n values: out[0] = sum (t-a)^2, out[1] = sum t^2, out[2] = max |t-a|
+// (one CTA, fixed order => deterministic; validation sets are a few thousand points)
+template <typename real>
+__global__ void err_metrics_kernel(const real* __restrict__ t, const real* __restrict__ a, long long n, real* __restrict__ out) {
+    __shared__ real sh[3][256];
+    real s0 = (real)0, s1 = (real)0, mx = (real)0;
+    for (long long i = threadIdx.x; i < n; i += 256) {
+        const real e = t[i] - a[i];
+        s0 = s0 + e * e;
+        s1 = s1 + t[i] * t[i];
+        const real ae = e < (real)0 ? -e : e;
+        mx = ae > mx ? ae : mx;
+    }
+    sh[0][threadIdx.x] = s0; sh[1][threadIdx.x] = s1; sh[2][threadIdx.x] = mx;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) {
+            sh[0][threadIdx.x] = sh[0][threadIdx.x] + sh[0][threadIdx.x + o];
+            sh[1][threadIdx.x] = sh[1][threadIdx.x] + sh[1][threadIdx.x + o];
+            const real b = sh[2][threadIdx.x + o];
+            if (b > sh[2][threadIdx.x]) sh[2][threadIdx.x] = b;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { out[0] = sh[0][0]; out[1] = sh[1][0]; out[2] = sh[2][0]; }
+}
+
 // tf.keras Adam (solver.py:16-21): m,v EMA then theta -= lr_t * m / (sqrt(v) + eps)
 template <typename real>
 __global__ void adam_kernel(real* __restrict__ th, const real* __restrict__ g, real* __restrict__ m, real* __restrict__ v, long long n,

@@ -240,6 +240,13 @@ class Engine:
         self._chk(rc)
         return out
 
+    def err_metrics(self, truth, approx):
+        """{sum (t-a)^2, sum t^2, max |t-a|} (solver.py:109-130) as a 3-vector on the device"""
+        out = torch.empty(3, dtype=self.dtype, device=self.device)
+        t, a = truth.contiguous(), approx.contiguous()
+        self._chk(self.lib.dpb_err_metrics(self.handle, self._p(t), self._p(a), t.numel(), self._p(out), self._stream()))
+        return out
+
     def adam_step(self, theta, grad, m, v, lr_t, beta1=0.9, beta2=0.999, eps=1e-8):
         rc = self.lib.dpb_adam_step(self.handle, self._p(theta), self._p(grad), self._p(m), self._p(v), theta.numel(),
                                     float(lr_t), beta1, beta2, eps, self._stream())

@@ -25,6 +25,8 @@ flags.DEFINE_string('compute_dtype', 'float32', """float32 (default), float64, o
 flags.DEFINE_string('impl', 'exact', """exact (CUDA-core FMA) or tensor (tcgen05 MLP layers)""")
 flags.DEFINE_integer('seed', None, """seed of weights and device sampling (the reference seeds nothing)""")
 flags.DEFINE_integer('num_iterations', None, """override net_config.num_iterations""")
+flags.DEFINE_string('checkpoint', None, """checkpoint file: written every --checkpoint_every iterations, resumed from if it exists""")
+flags.DEFINE_integer('checkpoint_every', 1000, """iterations between checkpoints""")
 FLAGS = flags.FLAGS
 
 
@@ -64,6 +66,11 @@ def main(argv):
     absl_logging.set_verbosity('info')
     logging.info('Begin to solve %s ' % config.eqn_config.eqn_name)
     solver = ActorCriticSolver(config, bsde, compute_dtype=FLAGS.compute_dtype, seed=FLAGS.seed, impl=FLAGS.impl)
+    if FLAGS.checkpoint:
+        solver.checkpoint_path, solver.checkpoint_every = FLAGS.checkpoint, FLAGS.checkpoint_every
+        if os.path.exists(FLAGS.checkpoint):
+            solver.load_checkpoint(FLAGS.checkpoint)
+            logging.info('resumed from %s at iteration %d' % (FLAGS.checkpoint, solver._iter))
     training_history, x, y, true_y, z, true_z, grad_y = solver.train()
     if rank != 0:
         return

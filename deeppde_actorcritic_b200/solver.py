@@ -331,6 +331,32 @@ class ActorCriticSolver(object):
                 self.train_step_actor(self.sample(B, self.N_a))
         self._iter += 1
 
+    # ------------------------------------------------------------------ checkpoint / resume (absent in the reference)
+    def state_dict(self):
+        opt = lambda o: {"m": [t.cpu() for t in o.m], "v": [t.cpu() for t in o.v], "iterations": o.iterations}
+        return {"theta_actor": self.model_actor.NN_control.theta.cpu(), "theta_critic": self.model_critic.NN_value.theta.cpu(),
+                "theta_critic_grad": self.model_critic.NN_value_grad.theta.cpu(), "opt_critic": opt(self.optimizer_critic),
+                "opt_actor": opt(self.optimizer_actor), "iter": self._iter, "seed": self.seed, "dtype": self.engine.dtype_name}
+
+    def load_state_dict(self, sd):
+        self.model_actor.NN_control.theta.copy_(sd["theta_actor"])
+        self.model_critic.NN_value.theta.copy_(sd["theta_critic"])
+        self.model_critic.NN_value_grad.theta.copy_(sd["theta_critic_grad"])
+        for o, k in ((self.optimizer_critic, "opt_critic"), (self.optimizer_actor, "opt_actor")):
+            for dst, src in zip(o.m, sd[k]["m"]):
+                dst.copy_(src)
+            for dst, src in zip(o.v, sd[k]["v"]):
+                dst.copy_(src)
+            o.iterations = int(sd[k]["iterations"])
+        self._iter, self.seed = int(sd["iter"]), int(sd["seed"])      # device sampling is keyed by (seed, iteration): the run continues bit for bit
+
+    def save_checkpoint(self, path):
+        if self.rank == 0:
+            torch.save(self.state_dict(), path)
+
+    def load_checkpoint(self, path):
+        self.load_state_dict(torch.load(path, map_location="cpu"))
+
     # ------------------------------------------------------------------ train loop (solver.py:36-71)
     def train(self):
         start_time = time.time()
@@ -344,7 +370,11 @@ class ActorCriticSolver(object):
         true_loss_actor = float(self.loss_actor(valid_data_actor, training=False, cheat_value=True, cheat_control=True))
         num_iterations = int(_get(n, "num_iterations"))
         elapsed_time = 0.0
-        for step in range(num_iterations + 1):
+        ckpt_path, ckpt_every = getattr(self, "checkpoint_path", None), int(getattr(self, "checkpoint_every", 0) or 0)
+        start = self._iter
+        for step in range(start, num_iterations + 1):
+            if ckpt_path and ckpt_every and step > start and step % ckpt_every == 0:
+                self.save_checkpoint(ckpt_path)
             if step % int(_get(n, "logging_frequency")) == 0:
                 loss_critic = float(self.loss_critic(valid_data_critic, training=False, cheat_control=False))
                 loss_actor = float(self.loss_actor(valid_data_actor, training=False, cheat_value=False, cheat_control=False))
@@ -373,9 +403,9 @@ class ActorCriticSolver(object):
         return np.array(training_history), cpu(x0), cpu(y), cpu(true_y), cpu(z), cpu(true_z), cpu(grad_y)
 
     # ------------------------------------------------------------------ error metrics (solver.py:109-136)
-    @staticmethod
-    def _rel_l2(true, approx):
-        return torch.sqrt(torch.sum((true - approx) ** 2) / torch.sum(true ** 2))
+    def _rel_l2(self, true, approx):
+        m = self.engine.err_metrics(true, approx)
+        return torch.sqrt(m[0] / m[1])
 
     def err_value(self, inputs):
         x0 = self.engine.tensor(inputs[0])
@@ -391,7 +421,7 @@ class ActorCriticSolver(object):
 
     def err_value_infty(self, inputs):
         x0 = self.engine.tensor(inputs[0])
-        return torch.max(torch.abs(self.bsde.V_true(x0) - self.model_critic.NN_value(x0, training=False, need_grad=False)))
+        return self.engine.err_metrics(self.bsde.V_true(x0), self.model_critic.NN_value(x0, training=False, need_grad=False))[2]
 
     def err_cost(self, inputs):
         x0 = self.engine.tensor(inputs[0])

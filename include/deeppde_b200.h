@@ -138,6 +138,10 @@ int dpb_mlp_forward(dpb_handle* h, int which_net, const void* theta, const void*
  *   DPB_CF_Z (Z_tf, out[n]), DPB_CF_W (w_tf(x,u), out[n]; u[n][control_dim] required, else NULL). */
 int dpb_closed_form(dpb_handle* h, int which, const void* x, const void* u, int64_t n, void* out, void* stream);
 
+/* The reductions of err_value / err_control / err_value_grad / err_value_infty (solver.py:109-130) on n
+ * values: out3 = { sum (truth-approx)^2, sum truth^2, max |truth-approx| } (device, deterministic). */
+int dpb_err_metrics(dpb_handle* h, const void* truth, const void* approx, int64_t n, void* out3, void* stream);
+
 /* tf.keras Adam step as used at solver.py:16-21,99-107 on a flat vector:
  *   m += (g-m)(1-b1); v += (g*g-v)(1-b2); theta -= lr_t * m / (sqrt(v)+eps),  lr_t given by the host. */
 int dpb_adam_step(dpb_handle* h, void* theta, const void* grad, void* m, void* v, int64_t n,

@@ -332,3 +332,35 @@ def test_error_paths():
         Engine(dict(cfg["eqn_config"], eqn_name="nope"), cfg["net_config"], cfg["train_config"])
     with pytest.raises(_cabi.DpbError):
         Engine(dict(cfg["eqn_config"], control_dim=3), cfg["net_config"], cfg["train_config"])
+
+
+def test_checkpoint_resume_is_bit_exact(tmp_path):
+    """train 6 iterations == train 3, checkpoint, reload into a fresh solver, train 3 (device sampling is keyed
+    by (seed, iteration); exact path => bitwise equal weights)."""
+    from deeppde_actorcritic_b200 import equation, munchify
+    from deeppde_actorcritic_b200.solver import ActorCriticSolver
+    z, cfg = load("lqr_d5_adaptive_normal_td1")
+    cfg = json.loads(json.dumps(cfg))
+    cfg["net_config"]["batch_size"] = 96
+
+    def make():
+        config = munchify(cfg)
+        bsde = getattr(equation, config.eqn_config.eqn_name)(config.eqn_config)
+        return ActorCriticSolver(config, bsde, compute_dtype="float32", seed=3, impl="exact")
+
+    a = make()
+    for _ in range(6):
+        a.train_iteration()
+    b = make()
+    for _ in range(3):
+        b.train_iteration()
+    path = str(tmp_path / "ck.pt")
+    b.save_checkpoint(path)
+    c = make()
+    c.load_checkpoint(path)
+    for _ in range(3):
+        c.train_iteration()
+    for ta, tc in ((a.model_actor.NN_control.theta, c.model_actor.NN_control.theta),
+                   (a.model_critic.NN_value.theta, c.model_critic.NN_value.theta),
+                   (a.model_critic.NN_value_grad.theta, c.model_critic.NN_value_grad.theta)):
+        assert torch.equal(ta, tc)
