@@ -94,7 +94,7 @@ __device__ __forceinline__ uint32_t tc_setup(TcSmem& s, const TcArgs& a) {
     if (tid == 0) {
         for (int i = 0; i < MAX_NSLOT; ++i) { mbar_init(&s.full[i], 1); mbar_init(&s.empty[i], 1); }
         mbar_init(s.acc_full, 1);
-        mbar_init(s.a_ready, TC_PATH_THREADS);
+        mbar_init(s.a_ready, TC_PATH_THREADS / 32);
         mbar_init(s.act_full, 1);
         s.sch->nops = 0;
         s.pc->req = 0; s.pc->gen = 0; s.pc->quit = 0;

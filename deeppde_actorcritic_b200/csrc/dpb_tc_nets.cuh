@@ -272,10 +272,12 @@ struct PathCtx {
     long long t_epi, t_hid;        // t_hid: cycles inside hidden-layer epilogues only
 };
 
-__device__ __forceinline__ void path_publish(PathCtx& p) {   // A planes written and accumulator drained
+// A planes written and accumulator drained: one arrival per path warp (a_ready counts the 8 path warps)
+__device__ __forceinline__ void path_publish(PathCtx& p) {
     tmem_st_wait();
     tc_fence_before();
-    mbar_arrive(p.a_ready);
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) mbar_arrive(p.a_ready);
     p.t_epi += clock64() - p.t_mark;
 }
 __device__ __forceinline__ void path_wait_acc(PathCtx& p) {
@@ -619,7 +621,8 @@ __device__ __forceinline__ void path_drain(PathCtx& p, int blk, int row, int kl,
         }
     }
     tc_fence_before();
-    mbar_arrive(p.a_ready);                    // accumulator drained
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) mbar_arrive(p.a_ready);   // accumulator drained
 }
 
 // cotangent of the raw output (nl <= 32 values, static indexing) -> planes (+ DZ image), publish

@@ -190,3 +190,52 @@ def test_tensor_gradients_vs_exact_d20_3x200():
     print("tensor vs exact gradients (max-norm relative):", {k: f"{v:.2e}" for k, v in errs.items()})
     assert errs["gV"] < GTOL_TENSOR and errs["gG"] < GTOL_TENSOR and errs["gA"] < GTOL_TENSOR
     assert errs["loss_c"] < 1e-4 and errs["loss_a"] < 1e-4
+
+
+ODD = {
+    # specialised <24, LQR> kernels, widths that are not multiples of 16, three tiles with a ragged tail
+    "lqr_d13_w72_40": ({"eqn_name": "LQR", "discount": 1.0, "p": 1.0, "q": 1.0, "beta": 1.0, "R": 1.0, "dim": 13, "control_dim": 13}, [72, 40], [40, 72, 24], "adaptive", "TD1"),
+    # generic <0,-1> kernels (VDP indexes its state cyclically), hidden width 50 as configs/vdp_d4.json
+    "vdp_d10_w50": ({"eqn_name": "VDP", "discount": 1.0, "a": 1.0, "epsilon": 0.1, "q": 1.0, "R": 1.0, "dim": 10, "control_dim": 5}, [50, 50], [50, 50], "naive", "TD1"),
+    # ekn head (control_dim + 1 outputs) and a 255-wide layer: the widest the tensor path supports
+    "ekn_d9_w255": ({"eqn_name": "EKN", "discount": 0, "a2": 1.2, "a3": 0.2, "R": 1.0, "dim": 9, "control_dim": 9}, [255, 64], [64, 255], "adaptive", "TD1"),
+}
+
+
+@pytest.mark.parametrize("key", list(ODD))
+def test_tensor_vs_exact_odd_shapes(key):
+    e, ha, hc, scheme, td = ODD[key]
+    N, T, B = 12, 0.3, 300
+    e = dict(e, total_time_critic=T, total_time_actor=T, num_time_interval_critic=N, num_time_interval_actor=N)
+    net = {"num_hiddens_actor": ha, "num_hiddens_critic": hc}
+    tr = {"scheme": scheme, "TD_type": td}
+    ex = Engine(e, net, tr, dtype="float32", impl="exact")
+    tn = Engine(e, net, tr, dtype="float32", impl="tensor")
+    from oracle import ref_solver as RS
+    rng = np.random.RandomState(3)
+    cfg = {"eqn_config": e, "net_config": net, "train_config": tr}
+    th = {}
+    for k in ("actor", "critic", "critic_grad"):
+        i, h, o, _ = RS.net_dims(cfg, k)
+        p = RS.init_params(i, h, o, rng)
+        p[-3 * o:-2 * o] = rng.normal(0, 0.1, o)
+        th[k] = ex.tensor(p)
+    x0, xb = ex.sample_x(11, 1, 0, B)
+    x0 = x0 * 0.8
+    kw = dict(dw_mode=2 if key.startswith("vdp") else 1, seed=11, stream_id=5)
+    a = ex.critic_step(th["actor"], th["critic"], th["critic_grad"], x0, None, xb, N, T, need_grad=True, want=("delta", "delta_bdry", "coef"), **kw)
+    b = tn.critic_step(th["actor"], th["critic"], th["critic_grad"], x0, None, xb, N, T, need_grad=True, want=("delta", "delta_bdry", "coef"), **kw)
+    same = (a["coef"] == b["coef"]).all(1).cpu().numpy()
+    assert same.mean() > 0.98
+    np.testing.assert_allclose(_npy(b["delta"])[same], _npy(a["delta"])[same], **VTOL)
+    np.testing.assert_allclose(_npy(b["delta_bdry"]), _npy(a["delta_bdry"]), **VTOL)
+    ya = ex.actor_step(th["actor"], th["critic"], x0, None, N, T, need_grad=True, want=("delta", "coef"), **kw)
+    yb = tn.actor_step(th["actor"], th["critic"], x0, None, N, T, need_grad=True, want=("delta", "coef"), **kw)
+    same_a = (ya["coef"] == yb["coef"]).all(1).cpu().numpy()
+    np.testing.assert_allclose(_npy(yb["delta"])[same_a], _npy(ya["delta"])[same_a], **VTOL)
+    if same.all() and same_a.all():
+        errs = {"gV": _gerr(_npy(b["grad_V"]), _npy(a["grad_V"])), "gG": _gerr(_npy(b["grad_G"]), _npy(a["grad_G"])),
+                "gA": _gerr(_npy(yb["grad_actor"]), _npy(ya["grad_actor"]))}
+        print(key, {k: f"{v:.2e}" for k, v in errs.items()})
+        for k, v in errs.items():
+            assert v < GTOL_TENSOR, (k, v)
