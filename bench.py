@@ -250,9 +250,16 @@ def main():
         pass
     peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
     achieved = kfl_avg / (kms_avg * 1e-3) / 1e12
+    traffic = None                                     # DRAM bytes of one launch of this kernel, from the committed ncu capture
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.workload)
+        if tr and impl == "tensor" and world == 1:
+            traffic = tr["dram_bytes_read"] + tr["dram_bytes_write"]
+    except Exception:
+        pass
     sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
     fp32_peak = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12
-    roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+    roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
                 "kernel": ("critic_tc_kernel" if impl == "tensor" else "critic_kernel<%s>" % ("float" if args.dtype == "float32" else "double")), "kernel_ms": kms_avg,
                 "algorithmic_flop_per_launch": kfl_avg, "live_fraction": live_frac, "peak_source": pk_src,
                 "note": ("impl=tensor: every product is formed as 3 bf16 MMAs (hi*hi + hi*lo + lo*hi, FP32 accumulation) to hold FP32 tolerance, so the "
