@@ -297,7 +297,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) critic_tc_kernel(const TcArgs a
                 if (td1) path_net_begin(P, nG, S.vecG, x);                        // NN_value_grad at x_t (before the move)
                 float* tr = traj + (size_t)t * 2 * sr * TC_PATHS;
                 if (need_grad && td1 && primary)
-                    KLOOP(k, d) tr[k * TC_PATHS + row] = x[k];
+                    KLOOP(k, d) __stcs(&tr[k * TC_PATHS + row], x[k]);
                 float w = 0.f;
                 if (!prop_only) w = eq_w<float, DP, EQN>(E, x, u, 1, 0);
                 const int coef = fwd_move<float, DP, EQN>(E, x, u, dwv, dt, sqdt, xn, flag, sdw, 1, 0);
@@ -311,7 +311,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) critic_tc_kernel(const TcArgs a
                     y = y - dif * cf * sqdt;                                      // solver.py:184
                     if (need_grad && primary) {
                         const float q = disc * cf * sqdt;
-                        KLOOP(k, d) tr[(sr + k) * TC_PATHS + row] = sdw[k] * q;
+                        KLOOP(k, d) __stcs(&tr[(sr + k) * TC_PATHS + row], sdw[k] * q);
                     }
                 }
                 disc = disc * expf(-E.gamma * dt * cf);                          // solver.py:187
@@ -403,7 +403,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) critic_tc_kernel(const TcArgs a
                 float xt[DPX], cot[DPX], dy0[DPX];
                 for (int t = 0; t < tlive; ++t) {
                     const float* tr = traj + (size_t)t * 2 * sr * TC_PATHS;
-                    KLOOP(k, d) { xt[k] = tr[k * TC_PATHS + row]; cot[k] = tr[(sr + k) * TC_PATHS + row] * rhog; }
+                    KLOOP(k, d) { xt[k] = __ldcs(&tr[k * TC_PATHS + row]); cot[k] = __ldcs(&tr[(sr + k) * TC_PATHS + row]) * rhog; }
                     float unused[1];
                     path_net_forward_keep(P, nG, S.vecG, xt, unused, mk, copies, S.act, row, true);
                     path_net_backward(P, nG, gG, mk, cot, true, gsG, S.dz, row, dy0);
@@ -515,7 +515,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) actor_tc_kernel(const TcArgs a)
                 }
                 float* tr = traj + (size_t)t * trs * TC_PATHS;
                 if (need_grad && primary)
-                    KLOOP(k, d) { tr[k * TC_PATHS + row] = x[k]; tr[(sr + k) * TC_PATHS + row] = dwv[k]; }
+                    KLOOP(k, d) { __stcs(&tr[k * TC_PATHS + row], x[k]); __stcs(&tr[(sr + k) * TC_PATHS + row], dwv[k]); }
                 const float w = eq_w<float, DP, EQN>(E, x, u, 1, 0);
                 const int coef = fwd_move<float, DP, EQN>(E, x, u, dwv, dt, sqdt, xn, flag, (float*)nullptr, 1, 0);
                 const float cf = (float)coef;
@@ -604,7 +604,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) actor_tc_kernel(const TcArgs a)
             } else if (is_path) {
                 Masks mk;
                 float xt[DPX], ubar[DPX], cot[DPX], dy0[DPX];
-                KLOOP(k, d) { xt[k] = tr[k * TC_PATHS + row]; dwv[k] = tr[(sr + k) * TC_PATHS + row]; }
+                KLOOP(k, d) { xt[k] = __ldcs(&tr[k * TC_PATHS + row]); dwv[k] = __ldcs(&tr[(sr + k) * TC_PATHS + row]); }
                 path_net_forward_keep(P, nA, S.vecA, xt, raw, mk, copies, S.act, row, false);
                 if (nA.ekn_head) ekn_head_fwd<float, DP, EQN>(raw, u, nA.mctrl, 1, 0);
                 else KLOOP(j, m) u[j] = raw[j];
