@@ -239,3 +239,63 @@ def test_tensor_vs_exact_odd_shapes(key):
         print(key, {k: f"{v:.2e}" for k, v in errs.items()})
         for k, v in errs.items():
             assert v < GTOL_TENSOR, (k, v)
+
+
+def test_tensor_sharding_invariance_philox():
+    """Two shards (path_offset, B_global) with in-kernel Philox increments == the whole batch:
+    the generator is keyed by the GLOBAL path index; sums agree up to FP32 reduction order."""
+    e = {"eqn_name": "LQR_var", "discount": 1.0, "q": 1.0, "beta": 1.0, "epsilon": 0.05, "R": 1.0, "dim": 8, "control_dim": 8,
+         "total_time_critic": 0.3, "total_time_actor": 0.3, "num_time_interval_critic": 10, "num_time_interval_actor": 10}
+    net = {"num_hiddens_actor": [40, 40], "num_hiddens_critic": [40, 40]}
+    tr = {"scheme": "adaptive", "TD_type": "TD1"}
+    tn = Engine(e, net, tr, dtype="float32", impl="tensor")
+    from oracle import ref_solver as RS
+    rng = np.random.RandomState(5)
+    cfg = {"eqn_config": e, "net_config": net, "train_config": tr}
+    th = {}
+    for k in ("actor", "critic", "critic_grad"):
+        i, h, o, _ = RS.net_dims(cfg, k)
+        th[k] = tn.tensor(RS.init_params(i, h, o, rng))
+    B, N, T, cut = 500, 10, 0.3, 200
+    x0, xb = tn.sample_x(9, 4, 0, B)
+    kw = dict(dw_mode=1, seed=9, stream_id=8, need_grad=True)
+    whole = tn.critic_step(th["actor"], th["critic"], th["critic_grad"], x0, None, xb, N, T, want=("delta",), **kw)
+    parts = [tn.critic_step(th["actor"], th["critic"], th["critic_grad"], x0[lo:hi].contiguous(), None, xb[lo:hi].contiguous(), N, T,
+                            B_global=B, path_offset=lo, want=("delta",), **kw) for lo, hi in ((0, cut), (cut, B))]
+    assert torch.equal(torch.cat([p["delta"] for p in parts]), whole["delta"])             # identical paths, identical arithmetic
+    np.testing.assert_allclose(_npy(parts[0]["loss"] + parts[1]["loss"]), _npy(whole["loss"]), rtol=1e-5)
+    for g in ("grad_V", "grad_G"):
+        assert _gerr(_npy(parts[0][g] + parts[1][g]), _npy(whole[g])) < 1e-4
+    wa = tn.actor_step(th["actor"], th["critic"], x0, None, N, T, **kw)
+    pa = [tn.actor_step(th["actor"], th["critic"], x0[lo:hi].contiguous(), None, N, T, B_global=B, path_offset=lo, **kw) for lo, hi in ((0, cut), (cut, B))]
+    assert _gerr(_npy(pa[0]["grad_actor"] + pa[1]["grad_actor"]), _npy(wa["grad_actor"])) < 1e-4
+
+
+@pytest.mark.parametrize("impl", ["exact", "tensor"])
+@pytest.mark.parametrize("train,scheme,sample,td", [("critic", "naive", "bounded", "TD2"), ("actor", "adaptive", "normal", "TD1"),
+                                                    ("actor-critic", "naive", "normal", "TD1")])
+def test_solver_modes_run(impl, train, scheme, sample, td):
+    """every train / scheme / sample_type / TD_type field of the reference's JSON drives the solver on both
+    implementations: a few device-sampled and host-sampled iterations change the right networks and stay finite."""
+    from deeppde_actorcritic_b200 import equation, munchify
+    from deeppde_actorcritic_b200.solver import ActorCriticSolver
+    z, cfg = _load("vdp_d10_adaptive_bounded_td2")
+    cfg = json.loads(json.dumps(cfg))
+    cfg["train_config"] = {"sample_type": sample, "scheme": scheme, "TD_type": td, "train": train}
+    cfg["net_config"]["batch_size"] = 160
+    config = munchify(cfg)
+    bsde = getattr(equation, config.eqn_config.eqn_name)(config.eqn_config)
+    s = ActorCriticSolver(config, bsde, compute_dtype="float32", seed=2, impl=impl)
+    before = [t.clone() for t in (s.model_actor.NN_control.theta, s.model_critic.NN_value.theta, s.model_critic.NN_value_grad.theta)]
+    for _ in range(2):
+        s.train_iteration()                      # device sampling
+    s.sampler = "host"
+    s.train_iteration()                          # the reference's NumPy samplers
+    after = [s.model_actor.NN_control.theta, s.model_critic.NN_value.theta, s.model_critic.NN_value_grad.theta]
+    changed = [not torch.equal(a, b) for a, b in zip(before, after)]
+    assert all(torch.isfinite(t).all() for t in after)
+    assert changed[0] == (train in ("actor", "actor-critic"))
+    assert changed[1] == (train in ("critic", "actor-critic"))
+    assert changed[2] == (train in ("critic", "actor-critic") and td == "TD1")
+    valid = tuple(s.engine.tensor(a) for a in s.sample(64, s.N_c))
+    assert np.isfinite(float(s.loss_critic(valid, False, False))) and np.isfinite(float(s.loss_actor(valid, False, False, False)))
