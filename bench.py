@@ -182,8 +182,7 @@ def main():
     from deeppde_actorcritic_b200 import equation, munchify
     from deeppde_actorcritic_b200.solver import ActorCriticSolver
     torch.cuda.set_device(local_rank)
-    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-        os.environ["NCCL_DEBUG"] = "WARN"                      # keep stdout to the one JSON line (no NCCL version banner)
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # NCCL's banner / debug lines go to stderr: stdout is the one JSON line
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     impl = "exact" if args.impl == "exact" else "tensor"          # "ours" = the tensor path (tcgen05, bf16x3 products, FP32 accumulation)
