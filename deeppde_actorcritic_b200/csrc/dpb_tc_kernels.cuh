@@ -1,6 +1,10 @@
 // dpb_tc_kernels.cuh -- the fused rollout + TD kernels with the MLP layers on tcgen05 (impl = tensor).
-// Same algorithm and per-path arithmetic (dpb_eqn.h) as dpb_kernels.cuh; thread t of warps 0-3 owns
-// path t of the 128-path tile entirely in registers, warp 4 lane 0 drives the tensor pipe.
+// Same algorithm and per-path arithmetic (dpb_eqn.h) as dpb_kernels.cuh.  CTA = one tile of 128 paths = the 128
+// TMEM lanes; warps 0-7: path threads (t and t+128 own path t, state in registers, epilogue chunks split between
+// them); warp 8 lane 0: control thread (issues every tcgen05.mma); warp 9 lane 0: weight-stream producer.
+// Phases per tile -- critic: rollout (actor + NN_value_grad forward) -> NN_value at x_N, x_0, x_bdry (+ backward)
+// -> second sweep re-evaluating NN_value_grad at the stored x_t and back-propagating; actor: rollout -> terminal
+// value (+ input gradient) -> reverse sweep (re-evaluate the actor, adjoint step, back-propagate).
 #pragma once
 #include "dpb_kernels.cuh"
 #include "dpb_tc_nets.cuh"
@@ -183,7 +187,7 @@ __device__ __forceinline__ void roles_init(Roles& r, const TcSmem& S, const TcAr
     r.P.grp = (warp >> 2) & 1;
     r.P.acc_full = S.acc_full; r.P.a_ready = S.a_ready; r.P.op_count = 0;
     r.P.t_accw = 0; r.P.t_epi = 0; r.P.t_hid = 0; r.P.t_mark = clock64();
-    C.t_aready = 0; C.t_full = 0; C.t_issue = 0; C.t_accw = 0; C.n_ops = 0;
+    C.t_aready = 0; C.t_issue = 0; C.t_accw = 0; C.n_ops = 0;
     C.mm_slot = 0; C.mm_use = 0;
 }
 // stats row: [0] kernel cycles, ctrl: [1] waiting for the path threads, [2] waiting for weights, [3] ops;
@@ -191,7 +195,7 @@ __device__ __forceinline__ void roles_init(Roles& r, const TcSmem& S, const TcAr
 __device__ __forceinline__ void roles_stats(const Roles& r, const TcArgs& a, long long t_start) {
     if (!a.stats) return;
     long long* st = a.stats + (size_t)blockIdx.x * 16;
-    if (r.is_ctrl) { st[0] = clock64() - t_start; st[1] = r.C.t_aready; st[2] = r.C.t_full; st[3] = r.C.n_ops; st[7] = r.C.t_issue; st[8] = r.C.t_accw; }
+    if (r.is_ctrl) { st[0] = clock64() - t_start; st[1] = r.C.t_aready; st[2] = 0; st[3] = r.C.n_ops; st[7] = r.C.t_issue; st[8] = r.C.t_accw; }
     if (threadIdx.x == 0) { st[4] = r.P.t_accw; st[5] = r.P.t_epi; st[6] = r.P.t_hid; }
 }
 

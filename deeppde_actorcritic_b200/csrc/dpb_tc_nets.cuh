@@ -156,7 +156,7 @@ struct Ctrl {
     uint32_t n_req, n_consumed, op_count, act_count, tmem;
     uint32_t mm_slot, mm_use;        // ring cursor (slot index, wrap count) of the MMA issuer
     unsigned char *act, *dz;         // shared-memory operand images of the dW products (128 paths x K16 features, bf16)
-    long long t_aready, t_full, t_issue, t_accw, n_ops;   // cycle counters (diagnostics)
+    long long t_aready, t_issue, t_accw, n_ops;   // cycle counters (diagnostics)
 };
 
 // let the producer run up to nslot chunks ahead of the MMAs (one shared-memory store, never waits)

@@ -185,8 +185,9 @@ double dpb_last_kernel_ms(dpb_handle* h);
 int dpb_tc_selftest(const float* A, const float* B, float* D, int K, void* stream);
 
 /* Diagnostic (tensor path): cycle counters of CTA 0 of the last critic/actor launch that used `workspace`
- * (synchronous copy): [0] kernel cycles, [1] control thread waiting for the path threads, [2] waiting for
- * weight chunks, [3] tensor-pipe ops, [4] path thread 0 waiting for the tensor pipe, [5] its epilogue cycles. */
+ * (synchronous copy): [0] kernel cycles, [1] control thread waiting for the path threads, [3] tensor-pipe ops,
+ * [4] path thread 0 waiting for the tensor pipe, [5] its epilogue cycles, [6] of which hidden-layer epilogues,
+ * [7] control thread inside MMA issue loops. */
 int dpb_tc_stats(dpb_handle* h, const void* workspace, int64_t B_local, int32_t N, int64_t* out_host);
 
 #ifdef __cplusplus
