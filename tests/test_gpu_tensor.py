@@ -197,6 +197,8 @@ ODD = {
     "lqr_d13_w72_40": ({"eqn_name": "LQR", "discount": 1.0, "p": 1.0, "q": 1.0, "beta": 1.0, "R": 1.0, "dim": 13, "control_dim": 13}, [72, 40], [40, 72, 24], "adaptive", "TD1"),
     # generic <0,-1> kernels (VDP indexes its state cyclically), hidden width 50 as configs/vdp_d4.json
     "vdp_d10_w50": ({"eqn_name": "VDP", "discount": 1.0, "a": 1.0, "epsilon": 0.1, "q": 1.0, "R": 1.0, "dim": 10, "control_dim": 5}, [50, 50], [50, 50], "naive", "TD1"),
+    # one hidden layer (actor) / four hidden layers (critic)
+    "lqr_var_d6_L1_L4": ({"eqn_name": "LQR_var", "discount": 1.0, "q": 1.0, "beta": 1.0, "epsilon": 0.05, "R": 1.0, "dim": 6, "control_dim": 6}, [48], [32, 48, 32, 16], "adaptive", "TD1"),
     # ekn head (control_dim + 1 outputs) and a 255-wide layer: the widest the tensor path supports
     "ekn_d9_w255": ({"eqn_name": "EKN", "discount": 0, "a2": 1.2, "a3": 0.2, "R": 1.0, "dim": 9, "control_dim": 9}, [255, 64], [64, 255], "adaptive", "TD1"),
 }
