@@ -383,10 +383,11 @@ static int tc_pack(dpb_handle* h, const tc::TcNet& t, const void* theta, char* w
 }
 
 // the <24, EQN> instantiations keep the per-path vectors in registers: dim and control_dim + 1 must fit in 24 and the
-// equation must index its state statically (VDP's cyclic neighbours do not); DPB_TC_GENERIC=1 forces the generic kernels
+// equation must index its state statically (VDP's cyclic neighbours do only for a compile-time control_dim: the shipped
+// 2, 5, 10 are instantiated); DPB_TC_GENERIC=1 forces the generic kernels
 static bool tc_specialised(const dpb_handle* h) {
     static const bool force_generic = getenv("DPB_TC_GENERIC") != nullptr;
-    return !force_generic && h->cfg.eqn != DPB_EQN_VDP && h->cfg.dim <= 23 && h->cfg.control_dim + 1 <= 24;
+    return !force_generic && h->cfg.dim <= 23 && h->cfg.control_dim + 1 <= 24;       // VDP: instantiated for control_dim 2, 5, 10
 }
 
 // ring geometry for a launch: slots of `slot_bytes` (largest chunk of the images used) in what is left of 227 KB
@@ -462,12 +463,17 @@ static int critic_step_tc(dpb_handle* h, const void* thA, const void* thV, const
         DPB_CUDA(h, cudaMemsetAsync(ws + L.slabs, 0, (size_t)L.nslab * (h->sV.gtotal + h->sG.gtotal) * sizeof(float), st));
     }
     const size_t smem = tc::tc_smem_bytes(h->tA.vec_floats, h->tV.vec_floats, h->tG.vec_floats, a.actdz_bytes, a.nslot, a.slot_bytes);
-    void (*kern)(const tc::TcArgs) = tc::critic_tc_kernel<0, -1>;
+    void (*kern)(const tc::TcArgs) = tc::critic_tc_kernel<0, -1, 0>;
     if (tc_specialised(h)) {
         switch (h->cfg.eqn) {
-        case DPB_EQN_LQR: kern = tc::critic_tc_kernel<24, EQ_LQR>; break;
-        case DPB_EQN_EKN: kern = tc::critic_tc_kernel<24, EQ_EKN>; break;
-        case DPB_EQN_LQR_VAR: kern = tc::critic_tc_kernel<24, EQ_LQRVAR>; break;
+        case DPB_EQN_LQR: kern = tc::critic_tc_kernel<24, EQ_LQR, 0>; break;
+        case DPB_EQN_EKN: kern = tc::critic_tc_kernel<24, EQ_EKN, 0>; break;
+        case DPB_EQN_LQR_VAR: kern = tc::critic_tc_kernel<24, EQ_LQRVAR, 0>; break;
+        case DPB_EQN_VDP:
+            if (h->cfg.control_dim == 2) kern = tc::critic_tc_kernel<24, EQ_VDP, 2>;
+            else if (h->cfg.control_dim == 5) kern = tc::critic_tc_kernel<24, EQ_VDP, 5>;
+            else if (h->cfg.control_dim == 10) kern = tc::critic_tc_kernel<24, EQ_VDP, 10>;
+            break;
         }
     }
     DPB_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -511,12 +517,17 @@ static int actor_step_tc(dpb_handle* h, const void* thA, const void* thV, const 
         DPB_CUDA(h, cudaMemsetAsync(ws + L.slabs, 0, (size_t)L.nslab * h->sA.gtotal * sizeof(float), st));
     }
     const size_t smem = tc::tc_smem_bytes(h->tA.vec_floats, h->tV.vec_floats, h->tG.vec_floats, a.actdz_bytes, a.nslot, a.slot_bytes);
-    void (*kern)(const tc::TcArgs) = tc::actor_tc_kernel<0, -1>;
+    void (*kern)(const tc::TcArgs) = tc::actor_tc_kernel<0, -1, 0>;
     if (tc_specialised(h)) {
         switch (h->cfg.eqn) {
-        case DPB_EQN_LQR: kern = tc::actor_tc_kernel<24, EQ_LQR>; break;
-        case DPB_EQN_EKN: kern = tc::actor_tc_kernel<24, EQ_EKN>; break;
-        case DPB_EQN_LQR_VAR: kern = tc::actor_tc_kernel<24, EQ_LQRVAR>; break;
+        case DPB_EQN_LQR: kern = tc::actor_tc_kernel<24, EQ_LQR, 0>; break;
+        case DPB_EQN_EKN: kern = tc::actor_tc_kernel<24, EQ_EKN, 0>; break;
+        case DPB_EQN_LQR_VAR: kern = tc::actor_tc_kernel<24, EQ_LQRVAR, 0>; break;
+        case DPB_EQN_VDP:
+            if (h->cfg.control_dim == 2) kern = tc::actor_tc_kernel<24, EQ_VDP, 2>;
+            else if (h->cfg.control_dim == 5) kern = tc::actor_tc_kernel<24, EQ_VDP, 5>;
+            else if (h->cfg.control_dim == 10) kern = tc::actor_tc_kernel<24, EQ_VDP, 10>;
+            break;
         }
     }
     DPB_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

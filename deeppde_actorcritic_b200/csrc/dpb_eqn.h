@@ -27,7 +27,8 @@
 // instantiated per padded dimension) the loop is fully unrolled and guarded, so that the per-path vectors
 // live in registers; DMAX == 0 is the generic run-time loop.
 #define DPB_LOOP(k, n) DPB_UNROLL for (int k = 0; k < (DMAX > 0 ? DMAX : (n)); ++k) if (DMAX == 0 || k < (n))
-#define DPB_TPL template <typename real, int DMAX = 0, int EQN = -1>
+#define DPB_TPL template <typename real, int DMAX = 0, int EQN = -1, int MV = 0>
+// MV > 0: control_dim of the VDP instantiations (makes the cyclic neighbour indices of equation.py:192-195 static)
 #define DPB_EQN(E) (EQN >= 0 ? EQN : (E).eqn)
 
 namespace dpb {
@@ -92,7 +93,7 @@ DPB_HD real norm2_path(const real* x, int d, int ld, int p) {
 // u_true (equation.py:163-164, 212-217, 259-261, 298-299)
 DPB_TPL
 DPB_HD void eq_u_true(const Eq<real>& E, const real* x, real* u, int ld, int p) {
-    const int d = E.d, m = E.m;
+    const int d = E.d, m = (MV > 0 ? MV : E.m);
     switch (DPB_EQN(E)) {
     case EQ_LQR:
         DPB_LOOP(k, d) DPB_AT(u, k) = E.cu * DPB_AT(x, k);
@@ -106,7 +107,7 @@ DPB_HD void eq_u_true(const Eq<real>& E, const real* x, real* u, int ld, int p) 
         }
         break;
     case EQ_EKN: {
-        real r = dpb_sqrt(norm2_path<real, DMAX, EQN>(x, d, ld, p));
+        real r = dpb_sqrt(norm2_path<real, DMAX, EQN, MV>(x, d, ld, p));
         DPB_LOOP(k, d) DPB_AT(u, k) = DPB_AT(x, k) / r;
         break;
     }
@@ -121,8 +122,8 @@ DPB_HD void eq_u_true(const Eq<real>& E, const real* x, real* u, int ld, int p) 
 // V_true (equation.py:160,204-210,255-257,295)
 DPB_TPL
 DPB_HD real eq_V_true(const Eq<real>& E, const real* x, int ld, int p) {
-    const int d = E.d, m = E.m;
-    real n2 = norm2_path<real, DMAX, EQN>(x, d, ld, p);
+    const int d = E.d, m = (MV > 0 ? MV : E.m);
+    real n2 = norm2_path<real, DMAX, EQN, MV>(x, d, ld, p);
     switch (DPB_EQN(E)) {
     case EQ_LQR:
     case EQ_LQRVAR:
@@ -146,13 +147,13 @@ DPB_HD real eq_V_true(const Eq<real>& E, const real* x, int ld, int p) {
 DPB_TPL
 DPB_HD real eq_Z(const Eq<real>& E, const real* x, int ld, int p) {
     if (DPB_EQN(E) == EQ_LQR || DPB_EQN(E) == EQ_LQRVAR) return E.ZR;
-    return eq_V_true<real, DMAX, EQN>(E, x, ld, p);
+    return eq_V_true<real, DMAX, EQN, MV>(E, x, ld, p);
 }
 
 // V_grad_true (equation.py:166,219-227,263-265,301) -> g[k]
 DPB_TPL
 DPB_HD void eq_V_grad_true(const Eq<real>& E, const real* x, real* g, int ld, int p) {
-    const int d = E.d, m = E.m;
+    const int d = E.d, m = (MV > 0 ? MV : E.m);
     switch (DPB_EQN(E)) {
     case EQ_LQR:
     case EQ_LQRVAR:
@@ -166,7 +167,7 @@ DPB_HD void eq_V_grad_true(const Eq<real>& E, const real* x, real* g, int ld, in
         }
         break;
     default: {
-        real r = dpb_sqrt(norm2_path<real, DMAX, EQN>(x, d, ld, p));
+        real r = dpb_sqrt(norm2_path<real, DMAX, EQN, MV>(x, d, ld, p));
         real c = (real)3 * E.a3 * r - (real)2 * E.a2;
         DPB_LOOP(k, d) DPB_AT(g, k) = c * DPB_AT(x, k);
     }
@@ -176,7 +177,7 @@ DPB_HD void eq_V_grad_true(const Eq<real>& E, const real* x, real* g, int ld, in
 // running cost w_tf (equation.py:154,188-199,249,288-290)
 DPB_TPL
 DPB_HD real eq_w(const Eq<real>& E, const real* x, const real* u, int ld, int p) {
-    const int d = E.d, m = E.m;
+    const int d = E.d, m = (MV > 0 ? MV : E.m);
     switch (DPB_EQN(E)) {
     case EQ_LQR: {
         real s1 = (real)0, s2 = (real)0;
@@ -222,7 +223,7 @@ DPB_HD real eq_drift_c(const Eq<real>& E, real r) {
     return E.C0 / ((real)2 * E.a2 - (real)3 * E.a3 * r);
 }
 
-// drift component k (equation.py:172,232-235,270-273,307).  cc = eq_drift_c<real, DMAX, EQN>(|x|) for ekn.
+// drift component k (equation.py:172,232-235,270-273,307).  cc = eq_drift_c<real, DMAX, EQN, MV>(|x|) for ekn.
 DPB_TPL
 DPB_HD real eq_drift(const Eq<real>& E, real cc, const real* x, const real* u, int k, int ld, int p) {
     switch (DPB_EQN(E)) {
@@ -230,7 +231,7 @@ DPB_HD real eq_drift(const Eq<real>& E, real cc, const real* x, const real* u, i
     case EQ_LQRVAR:
         return E.beta * DPB_AT(u, k);
     case EQ_VDP: {
-        const int m = E.m;
+        const int m = (MV > 0 ? MV : E.m);
         if (k < m) return DPB_AT(x, m + k);
         int j = k - m;
         real x1 = DPB_AT(x, j), x2 = DPB_AT(x, m + j);
@@ -263,7 +264,7 @@ DPB_HD int eq_flag(const Eq<real>& E, real nrm) {
 DPB_TPL
 DPB_HD int fwd_initial_flag(const Eq<real>& E, const real* x, int ld, int p) {
     if (E.scheme == SCHEME_NAIVE) return 1;
-    return eq_flag<real, DMAX, EQN>(E, dpb_sqrt(norm2_path<real, DMAX, EQN>(x, E.d, ld, p)));
+    return eq_flag<real, DMAX, EQN, MV>(E, dpb_sqrt(norm2_path<real, DMAX, EQN, MV>(x, E.d, ld, p)));
 }
 
 // step size of this step (equation.py:49 | 84-86).  `clamped` tells the reverse sweep whether the
@@ -277,7 +278,7 @@ DPB_HD void fwd_dt(const Eq<real>& E, const real* x, int flag, int ld, int p, re
         sqdt = E.sqrt_delta_t;
         return;
     }
-    xnorm = dpb_sqrt(norm2_path<real, DMAX, EQN>(x, E.d, ld, p));
+    xnorm = dpb_sqrt(norm2_path<real, DMAX, EQN, MV>(x, E.d, ld, p));
     if (flag == 1) {
         real g = E.R - xnorm;
         dt = g * g / E.c3;
@@ -298,15 +299,15 @@ DPB_HD int fwd_move(const Eq<real>& E, real* x, const real* u, const real* dw, r
     const int d = E.d;
     real cc = (real)0;
     if (DPB_EQN(E) == EQ_EKN) {
-        real r = (E.scheme == SCHEME_ADAPTIVE) ? xnorm : dpb_sqrt(norm2_path<real, DMAX, EQN>(x, d, ld, p));
-        cc = eq_drift_c<real, DMAX, EQN>(E, r);
+        real r = (E.scheme == SCHEME_ADAPTIVE) ? xnorm : dpb_sqrt(norm2_path<real, DMAX, EQN, MV>(x, d, ld, p));
+        cc = eq_drift_c<real, DMAX, EQN, MV>(E, r);
     }
     real n2 = (real)0;
     real dx[DMAX > 0 ? DMAX : 32];
     DPB_LOOP(k, d) {
-        real sd = eq_sigma<real, DMAX, EQN>(E, x, u, k, ld, p) * DPB_AT(dw, k);
+        real sd = eq_sigma<real, DMAX, EQN, MV>(E, x, u, k, ld, p) * DPB_AT(dw, k);
         if (sdw_out) DPB_AT(sdw_out, k) = sd;
-        real dk = eq_drift<real, DMAX, EQN>(E, cc, x, u, k, ld, p) * dt + sd * sqdt;
+        real dk = eq_drift<real, DMAX, EQN, MV>(E, cc, x, u, k, ld, p) * dt + sd * sqdt;
         dx[k] = dk;
         real pk = DPB_AT(x, k) + dk;
         n2 = n2 + pk * pk;
@@ -317,7 +318,7 @@ DPB_HD int fwd_move(const Eq<real>& E, real* x, const real* u, const real* dw, r
         coef = flag * (1 - ex);
         newflag = coef;
     } else {
-        int nf = eq_flag<real, DMAX, EQN>(E, dpb_sqrt(n2));
+        int nf = eq_flag<real, DMAX, EQN, MV>(E, dpb_sqrt(n2));
         newflag = (flag > 0) ? nf : 0;                      // flag(p) * sign(flag)
         coef = (flag > 0 && newflag > 0) ? 1 : 0;           // sign(flag) * sign(new_flag)
     }
@@ -336,27 +337,27 @@ DPB_HD int fwd_move(const Eq<real>& E, real* x, const real* u, const real* dw, r
 DPB_TPL
 DPB_HD void adj_step(const Eq<real>& E, const real* x, const real* u, const real* dw, real dt, real sqdt, int coef,
                      int dt_grad, real xnorm, real D_t, real invB, real* lam, real& Dbar, real* ubar, int ld, int p) {
-    const int d = E.d, m = E.m;
+    const int d = E.d, m = (MV > 0 ? MV : E.m);
     if (!coef) {                                            // identity step: contributes nothing
         DPB_LOOP(j, m) DPB_AT(ubar, j) = (real)0;
         return;
     }
-    const real w = eq_w<real, DMAX, EQN>(E, x, u, ld, p);
+    const real w = eq_w<real, DMAX, EQN, MV>(E, x, u, ld, p);
     const real ed = dpb_exp(-E.gamma * dt);
     const real D_next = D_t * ed;
     const real cw = dt * D_t * invB;                        // weight of dw/d(.) terms
     real cc = (real)0, r = (real)0;
     if (DPB_EQN(E) == EQ_EKN) {
-        r = (E.scheme == SCHEME_ADAPTIVE) ? xnorm : dpb_sqrt(norm2_path<real, DMAX, EQN>(x, d, ld, p));
-        cc = eq_drift_c<real, DMAX, EQN>(E, r);
+        r = (E.scheme == SCHEME_ADAPTIVE) ? xnorm : dpb_sqrt(norm2_path<real, DMAX, EQN, MV>(x, d, ld, p));
+        cc = eq_drift_c<real, DMAX, EQN, MV>(E, r);
     }
     // hbar = D_t w /B - gamma Dbar D_{t+1} + <lam, mu + s*xi/(2 sqrt h)>
     real hbar = (real)0;
     if (dt_grad) {
         real acc = (real)0;
         DPB_LOOP(k, d) {
-            real mu = eq_drift<real, DMAX, EQN>(E, cc, x, u, k, ld, p);
-            real s = eq_sigma<real, DMAX, EQN>(E, x, u, k, ld, p);
+            real mu = eq_drift<real, DMAX, EQN, MV>(E, cc, x, u, k, ld, p);
+            real s = eq_sigma<real, DMAX, EQN, MV>(E, x, u, k, ld, p);
             acc = acc + DPB_AT(lam, k) * (mu + s * DPB_AT(dw, k) / ((real)2 * sqdt));
         }
         hbar = D_t * w * invB - E.gamma * Dbar * D_next + acc;
@@ -442,7 +443,7 @@ DPB_HD real rho_grad(real z, real clip) {
 // ekn actor head (solver.py:272-274): u = y[:m] / (1e-15 + relu(y[m]) + ||y[:m]||)
 DPB_TPL
 DPB_HD void ekn_head_fwd(const real* y, real* u, int m, int ld, int p) {
-    real n = dpb_sqrt(norm2_path<real, DMAX, EQN>(y, m, ld, p));
+    real n = dpb_sqrt(norm2_path<real, DMAX, EQN, MV>(y, m, ld, p));
     real ym = DPB_AT(y, m);
     real D = (real)0.000000000000001 + (ym > (real)0 ? ym : (real)0) + n;
     DPB_LOOP(k, m) DPB_AT(u, k) = DPB_AT(y, k) / D;
@@ -450,7 +451,7 @@ DPB_HD void ekn_head_fwd(const real* y, real* u, int m, int ld, int p) {
 // cotangent ubar[m] -> ybar[m+1] (in place allowed when ubar and ybar are distinct buffers)
 DPB_TPL
 DPB_HD void ekn_head_bwd(const real* y, const real* ubar, real* ybar, int m, int ld, int p) {
-    real n = dpb_sqrt(norm2_path<real, DMAX, EQN>(y, m, ld, p));
+    real n = dpb_sqrt(norm2_path<real, DMAX, EQN, MV>(y, m, ld, p));
     real ym = DPB_AT(y, m);
     real D = (real)0.000000000000001 + (ym > (real)0 ? ym : (real)0) + n;
     real s = (real)0;

@@ -211,8 +211,9 @@ __device__ __forceinline__ void reduce_rows_to(float* dst, const float* acc, int
 
 // ================================================================================== critic (tensor)
 // DP > 0: instantiation for dim (and control_dim + 1) <= DP with equation EQN fixed at compile time -- the
-// per-path vectors are register arrays and every d-loop is unrolled; <0,-1>: generic run-time version.
-template <int DP, int EQN>
+// per-path vectors are register arrays and every d-loop is unrolled (MV > 0: VDP with control_dim = MV, which makes its
+// cyclic neighbour indices static); <0,-1,0>: generic run-time version.
+template <int DP, int EQN, int MV>
 __global__ void __launch_bounds__(TC_THREADS, 1) critic_tc_kernel(const TcArgs a) {
     constexpr int DPX = DP > 0 ? DP : 32;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -266,7 +267,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) critic_tc_kernel(const TcArgs a
         float disc = 1.f, y = 0.f;
         if (is_path) {
             KLOOP(k, d) x[k] = valid ? a.x0[gp * d + k] : fill;
-            flag = fwd_initial_flag<float, DP, EQN>(E, x, 1, 0);
+            flag = fwd_initial_flag<float, DP, EQN, MV>(E, x, 1, 0);
             if (a.o_x && wr)
                 KLOOP(k, d) a.o_x[(gp * d + k) * (long long)(N + 1)] = x[k];
         }
@@ -290,12 +291,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) critic_tc_kernel(const TcArgs a
                 if (!cheat) path_net_begin(P, nA, S.vecA, x);
                 path_dw(a, gp, valid, t, dwv);
                 float dt, sqdt, xn; int dtg;
-                fwd_dt<float, DP, EQN>(E, x, flag, 1, 0, dt, sqdt, xn, dtg);
+                fwd_dt<float, DP, EQN, MV>(E, x, flag, 1, 0, dt, sqdt, xn, dtg);
                 if (cheat) {
-                    eq_u_true<float, DP, EQN>(E, x, u, 1, 0);
+                    eq_u_true<float, DP, EQN, MV>(E, x, u, 1, 0);
                 } else {
                     path_net_finish(P, nA, S.vecA, raw);
-                    if (nA.ekn_head) ekn_head_fwd<float, DP, EQN>(raw, u, nA.mctrl, 1, 0);
+                    if (nA.ekn_head) ekn_head_fwd<float, DP, EQN, MV>(raw, u, nA.mctrl, 1, 0);
                     else KLOOP(j, E.m) u[j] = raw[j];
                 }
                 if (td1) path_net_begin(P, nG, S.vecG, x);                        // NN_value_grad at x_t (before the move)
@@ -303,8 +304,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) critic_tc_kernel(const TcArgs a
                 if (need_grad && td1 && primary)
                     KLOOP(k, d) __stcs(&tr[k * TC_PATHS + row], x[k]);
                 float w = 0.f;
-                if (!prop_only) w = eq_w<float, DP, EQN>(E, x, u, 1, 0);
-                const int coef = fwd_move<float, DP, EQN>(E, x, u, dwv, dt, sqdt, xn, flag, sdw, 1, 0);
+                if (!prop_only) w = eq_w<float, DP, EQN, MV>(E, x, u, 1, 0);
+                const int coef = fwd_move<float, DP, EQN, MV>(E, x, u, dwv, dt, sqdt, xn, flag, sdw, 1, 0);
                 const float cf = (float)coef;
                 if (td1) path_net_finish(P, nG, S.vecG, g);
                 y = y + w * disc * cf * dt;                                       // solver.py:170-174
@@ -375,13 +376,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) critic_tc_kernel(const TcArgs a
                 path_net_backward(P, nV, gV, mk, cot, true, gsV, S.dz, row, dy0);
                 KLOOP(k, d) { sxV[k] += x0v[k] * dy0[k]; s0V[k] += dy0[k]; }
                 path_net_forward_keep(P, nV, S.vecV, xbv, vb, mk, copies, S.act, row, false);
-                const float dbb = vb[0] - eq_Z<float, DP, EQN>(E, xbv, 1, 0);
+                const float dbb = vb[0] - eq_Z<float, DP, EQN, MV>(E, xbv, 1, 0);
                 cot[0] = valid ? rho_grad(dbb, 50.f) * scale : 0.f;
                 path_net_backward(P, nV, gV, mk, cot, true, gsV, S.dz, row, dy0);
                 KLOOP(k, d) { sxV[k] += xbv[k] * dy0[k]; s0V[k] += dy0[k]; }
             }
             const float delta = v0[0] - y - vN[0] * disc;                         // solver.py:189
-            const float db = vb[0] - eq_Z<float, DP, EQN>(E, xbv, 1, 0);                          // solver.py:190
+            const float db = vb[0] - eq_Z<float, DP, EQN, MV>(E, xbv, 1, 0);                          // solver.py:190
             if (wr) {
                 rho_v = rho(delta, 50.f);
                 rho_b = rho(db, 50.f);
@@ -436,7 +437,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) critic_tc_kernel(const TcArgs a
 }
 
 // =================================================================================== actor (tensor)
-template <int DP, int EQN>
+template <int DP, int EQN, int MV>
 __global__ void __launch_bounds__(TC_THREADS, 1) actor_tc_kernel(const TcArgs a) {
     constexpr int DPX = DP > 0 ? DP : 32;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -488,7 +489,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) actor_tc_kernel(const TcArgs a)
         float disc = 1.f, y = 0.f;
         if (is_path) {
             KLOOP(k, d) x[k] = valid ? a.x0[gp * d + k] : fill;
-            flag = fwd_initial_flag<float, DP, EQN>(E, x, 1, 0);
+            flag = fwd_initial_flag<float, DP, EQN, MV>(E, x, 1, 0);
             if (a.o_x && wr)
                 KLOOP(k, d) a.o_x[(gp * d + k) * (long long)(N + 1)] = x[k];
         }
@@ -509,19 +510,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) actor_tc_kernel(const TcArgs a)
                 if (!cheat) path_net_begin(P, nA, S.vecA, x);
                 path_dw(a, gp, valid, t, dwv);
                 float dt, sqdt, xn; int dtg;
-                fwd_dt<float, DP, EQN>(E, x, flag, 1, 0, dt, sqdt, xn, dtg);
+                fwd_dt<float, DP, EQN, MV>(E, x, flag, 1, 0, dt, sqdt, xn, dtg);
                 if (cheat) {
-                    eq_u_true<float, DP, EQN>(E, x, u, 1, 0);
+                    eq_u_true<float, DP, EQN, MV>(E, x, u, 1, 0);
                 } else {
                     path_net_finish(P, nA, S.vecA, raw);
-                    if (nA.ekn_head) ekn_head_fwd<float, DP, EQN>(raw, u, nA.mctrl, 1, 0);
+                    if (nA.ekn_head) ekn_head_fwd<float, DP, EQN, MV>(raw, u, nA.mctrl, 1, 0);
                     else KLOOP(j, m) u[j] = raw[j];
                 }
                 float* tr = traj + (size_t)t * trs * TC_PATHS;
                 if (need_grad && primary)
                     KLOOP(k, d) { __stcs(&tr[k * TC_PATHS + row], x[k]); __stcs(&tr[(sr + k) * TC_PATHS + row], dwv[k]); }
-                const float w = eq_w<float, DP, EQN>(E, x, u, 1, 0);
-                const int coef = fwd_move<float, DP, EQN>(E, x, u, dwv, dt, sqdt, xn, flag, (float*)nullptr, 1, 0);
+                const float w = eq_w<float, DP, EQN, MV>(E, x, u, 1, 0);
+                const int coef = fwd_move<float, DP, EQN, MV>(E, x, u, dwv, dt, sqdt, xn, flag, (float*)nullptr, 1, 0);
                 const float cf = (float)coef;
                 if (need_grad && primary) {
                     float* sc = tr + (size_t)2 * sr * TC_PATHS;
@@ -565,9 +566,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) actor_tc_kernel(const TcArgs a)
             float vN[1];
             const float seed = valid ? disc * a.invB : 0.f;
             if (cheat_v) {
-                vN[0] = eq_V_true<float, DP, EQN>(E, x, 1, 0);                                    // solver.py:223
+                vN[0] = eq_V_true<float, DP, EQN, MV>(E, x, 1, 0);                                    // solver.py:223
                 if (need_grad) {
-                    eq_V_grad_true<float, DP, EQN>(E, x, lam, 1, 0);
+                    eq_V_grad_true<float, DP, EQN, MV>(E, x, lam, 1, 0);
                     KLOOP(k, d) lam[k] = lam[k] * seed;
                 }
             } else if (!need_grad) {
@@ -610,13 +611,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) actor_tc_kernel(const TcArgs a)
                 float xt[DPX], ubar[DPX], cot[DPX], dy0[DPX];
                 KLOOP(k, d) { xt[k] = __ldcs(&tr[k * TC_PATHS + row]); dwv[k] = __ldcs(&tr[(sr + k) * TC_PATHS + row]); }
                 path_net_forward_keep(P, nA, S.vecA, xt, raw, mk, copies, S.act, row, false);
-                if (nA.ekn_head) ekn_head_fwd<float, DP, EQN>(raw, u, nA.mctrl, 1, 0);
+                if (nA.ekn_head) ekn_head_fwd<float, DP, EQN, MV>(raw, u, nA.mctrl, 1, 0);
                 else KLOOP(j, m) u[j] = raw[j];
                 const int coef = (valid && sc[A_COEF * TC_PATHS + row] > 0.f) ? 1 : 0;
-                adj_step<float, DP, EQN>(E, xt, u, dwv, sc[A_DT * TC_PATHS + row], sc[A_SQDT * TC_PATHS + row], coef, (int)sc[A_DTG * TC_PATHS + row],
+                adj_step<float, DP, EQN, MV>(E, xt, u, dwv, sc[A_DT * TC_PATHS + row], sc[A_SQDT * TC_PATHS + row], coef, (int)sc[A_DTG * TC_PATHS + row],
                          sc[A_XN * TC_PATHS + row], sc[A_DISC * TC_PATHS + row], a.invB, lam, Dbar, ubar, 1, 0);
                 if (nA.ekn_head) {
-                    if (coef) ekn_head_bwd<float, DP, EQN>(raw, ubar, cot, m, 1, 0);
+                    if (coef) ekn_head_bwd<float, DP, EQN, MV>(raw, ubar, cot, m, 1, 0);
                     else KLOOP(j, m + 1) cot[j] = 0.f;
                 } else {
                     KLOOP(j, m) cot[j] = ubar[j];
