@@ -22,7 +22,7 @@ from .solver import ActorCriticSolver
 flags.DEFINE_string('config_path', 'configs/lqr_d5.json', """The path to load json file.""")
 flags.DEFINE_string('exp_name', None, """The name of numerical experiments, prefix for logging""")
 flags.DEFINE_string('compute_dtype', 'float32', """float32 (default), float64, or config (= net_config.dtype)""")
-flags.DEFINE_string('impl', 'exact', """exact (CUDA-core FMA) or tensor (tcgen05 MLP layers)""")
+flags.DEFINE_string('impl', None, """tensor (tcgen05 MLP layers; default for float32) or exact (CUDA-core FMA; default for float64)""")
 flags.DEFINE_integer('seed', None, """seed of weights and device sampling (the reference seeds nothing)""")
 flags.DEFINE_integer('num_iterations', None, """override net_config.num_iterations""")
 flags.DEFINE_string('checkpoint', None, """checkpoint file: written every --checkpoint_every iterations, resumed from if it exists""")

@@ -185,10 +185,12 @@ class KerasAdam(object):
 class ActorCriticSolver(object):
     """solver.py:7-136."""
 
-    def __init__(self, config, bsde, compute_dtype="float32", device=None, seed=None, impl="exact"):
+    def __init__(self, config, bsde, compute_dtype="float32", device=None, seed=None, impl=None):
         self.eqn_config, self.net_config, self.train_config = config.eqn_config, config.net_config, config.train_config
         self.bsde = bsde
         dtype = _get(self.net_config, "dtype", "float64") if compute_dtype == "config" else compute_dtype
+        if impl is None:                       # tensor cores compute in float32 (bf16x3); float64 is the exact path's
+            impl = "tensor" if dtype == "float32" else "exact"
         dist = _dist()
         self.rank = dist.get_rank() if dist else 0
         self.world = dist.get_world_size() if dist else 1
