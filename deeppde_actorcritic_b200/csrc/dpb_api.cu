@@ -767,3 +767,16 @@ extern "C" int dpb_err_metrics(dpb_handle* h, const void* truth, const void* app
     DPB_CUDA(h, cudaGetLastError());
     return DPB_OK;
 }
+
+extern "C" int dpb_tc_handshake_cycles(int64_t* out_host, int rounds) {
+    if (!out_host || rounds < 1) return fail(nullptr, DPB_ERR_ARG, "dpb_tc_handshake_cycles: bad argument");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) { cudaGetLastError(); return fail(nullptr, DPB_ERR_CUDA, "dpb_tc_handshake_cycles: no CUDA device"); }
+    long long* d = nullptr;
+    DPB_CUDA(nullptr, cudaMalloc(&d, 16));
+    tc::tc_handshake_kernel<<<1, 288>>>(d, rounds);
+    cudaError_t e = cudaMemcpy(out_host, d, 16, cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    if (e != cudaSuccess) return fail(nullptr, DPB_ERR_CUDA, std::string("dpb_tc_handshake_cycles: ") + cudaGetErrorString(e));
+    return DPB_OK;
+}

@@ -112,5 +112,53 @@ __global__ void __launch_bounds__(128, 1) tc_selftest_kernel(const float* __rest
     if (warp == 0) tmem_dealloc(tbase, 512);
 }
 
+
+// Latency of one control-thread <-> path-thread hand-off of the tensor path with (almost) no work in it:
+// control thread: wait a_ready -> one tcgen05.mma (M=128, N=16, K=16) -> tcgen05.commit(acc_full);
+// 8 path warps: wait acc_full -> tcgen05.ld of 16 columns -> tcgen05.st of 8 -> publish (one arrival per warp).
+// out[0] = cycles per round trip (thread 0), out[1] = rounds.
+__global__ void __launch_bounds__(288, 1) tc_handshake_kernel(long long* out, int rounds) {
+    __shared__ __align__(128) unsigned char img[2 * 128 * 16 * 2];
+    __shared__ __align__(8) uint64_t bars[2];
+    __shared__ uint32_t tslot;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    for (int i = tid; i < (int)sizeof(img) / 4; i += 288) reinterpret_cast<uint32_t*>(img)[i] = 0u;
+    if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 8); fence_barrier_init(); }
+    if (warp == 8) tmem_alloc(&tslot, 512);
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tbase = tslot;
+    const uint32_t tl = tbase + ((uint32_t)((warp & 3) * 32) << 16);
+    const uint32_t idesc = idesc_bf16(128, 16, 0, 0);
+    const long long t0 = clock64();
+    if (warp == 8) {
+        if (lane == 0) {
+            for (int r = 0; r < rounds; ++r) {
+                mbar_wait(&bars[1], r & 1);
+                tc_fence_after();
+                mma_ss(tbase, smem_desc(smem_u32(img), 2048, 128), smem_desc(smem_u32(img) + 4096, 256, 128), idesc, 0);
+                tc_commit(&bars[0]);
+            }
+        }
+    } else {
+        for (int r = 0; r < rounds; ++r) {
+            uint32_t v[16];
+            if (r > 0) { mbar_wait(&bars[0], (r - 1) & 1); tc_fence_after(); tmem_ld16(tl, v); tmem_ld_wait(); } else { for (int j = 0; j < 16; ++j) v[j] = 0u; }
+            tmem_st8(tl + 256, v);
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bars[1]);
+        }
+        mbar_wait(&bars[0], (rounds - 1) & 1);
+    }
+    if (tid == 0) { out[0] = (clock64() - t0) / rounds; out[1] = rounds; }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 8) tmem_dealloc(tbase, 512);
+}
+
 }  // namespace tc
 }  // namespace dpb

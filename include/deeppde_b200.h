@@ -184,6 +184,10 @@ double dpb_last_kernel_ms(dpb_handle* h);
  * D1 = A B^T (A read from tensor memory), D2[f][g] = sum_p A[p][f] B[p][g] (both operands MN-major). */
 int dpb_tc_selftest(const float* A, const float* B, float* D, int K, void* stream);
 
+/* Diagnostic (tensor path): cycles of one empty control-thread <-> path-thread round trip (mbarrier hand-offs, one
+ * minimal tcgen05.mma + commit, one TMEM load/store): out_host[0] = cycles per round trip, out_host[1] = rounds. */
+int dpb_tc_handshake_cycles(int64_t* out_host, int rounds);
+
 /* Diagnostic (tensor path): cycle counters of CTA 0 of the last critic/actor launch that used `workspace`
  * (synchronous copy): [0] kernel cycles, [1] control thread waiting for the path threads, [3] tensor-pipe ops,
  * [4] path thread 0 waiting for the tensor pipe, [5] its epilogue cycles, [6] of which hidden-layer epilogues,

@@ -35,6 +35,16 @@ def test_tcgen05_product_forms(K):
     assert err[2] < tol, f"SS MN-major product wrong: {err}"
 
 
+def test_tcgen05_handshake_latency():
+    """empty control <-> path round trip of the tensor path's protocol completes and is timed (diagnostic)"""
+    lib = _cabi.load()
+    out = np.zeros(2, dtype=np.int64)
+    rc = lib.dpb_tc_handshake_cycles(out.ctypes.data_as(C.c_void_p), 2000)
+    assert rc == 0, lib.dpb_last_error(None)
+    print("tcgen05 hand-off round trip:", int(out[0]), "cycles")
+    assert out[1] == 2000 and 0 < out[0] < 100000
+
+
 # ------------------------------------------------------------------------------------------------
 # tensor path (impl="tensor": bf16x3 products on tcgen05, FP32 accumulation) vs golden / exact path
 import glob
