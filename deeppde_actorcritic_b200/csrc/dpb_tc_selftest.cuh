@@ -5,6 +5,7 @@
 // Inputs are float (expected bf16-representable), outputs float [3][128][208].
 #pragma once
 #include "dpb_tc.cuh"
+#include "dpb_tc_nets.cuh"
 
 namespace dpb {
 namespace tc {
@@ -158,6 +159,51 @@ __global__ void __launch_bounds__(288, 1) tc_handshake_kernel(long long* out, in
     tc_fence_before();
     __syncthreads();
     if (warp == 8) tmem_dealloc(tbase, 512);
+}
+
+
+// Cost of one hidden-layer epilogue (13 chunks of 16 columns: TMEM load, affine + y+relu(y), bf16 hi/lo split,
+// two TMEM stores) when `ngroups` groups of 4 warps share the chunks of the 128 lanes.  No MMAs, no barriers:
+// the pure path-thread work.  out[0] = cycles per epilogue.
+__global__ void tc_epilogue_bench_kernel(long long* out, int rounds, int ngroups) {
+    __shared__ __align__(16) float gcbb[2 * 208];
+    __shared__ uint32_t tslot;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    for (int i = tid; i < 416; i += blockDim.x) gcbb[i] = 0.5f + 0.001f * i;
+    if (warp == 0) tmem_alloc(&tslot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tbase = tslot;
+    const uint32_t tl = tbase + ((uint32_t)((warp & 3) * 32) << 16);
+    const int grp = warp >> 2;
+    {   // defined accumulator contents
+        uint32_t z[8];
+        for (int j = 0; j < 8; ++j) z[j] = __float_as_uint(0.25f * (j - 3));
+        for (int c = 0; c < 32; ++c) tmem_st8(tl + 8 * c, z);
+        tmem_st_wait();
+    }
+    __syncthreads();
+    const long long t0 = clock64();
+    for (int r = 0; r < rounds; ++r) {
+        const float* gc = gcbb;
+        const float* bb = gcbb + 208;
+        uint32_t ra[16];
+        for (int c = grp; c < 13; c += ngroups) {
+            tmem_ld16(tl + COL_ACC + 16 * c, ra);
+            tmem_ld_wait();
+            float v[16];
+            affine16(ra, gc + 16 * c, bb + 16 * c, v);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = v[j] + fmaxf(v[j], 0.f);
+            put16(tl, c, v);
+        }
+        tmem_st_wait();
+        __syncthreads();
+    }
+    if (tid == 0) { out[0] = (clock64() - t0) / rounds; out[1] = rounds; }
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tbase, 512);
 }
 
 }  // namespace tc

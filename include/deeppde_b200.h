@@ -188,6 +188,10 @@ int dpb_tc_selftest(const float* A, const float* B, float* D, int K, void* strea
  * minimal tcgen05.mma + commit, one TMEM load/store): out_host[0] = cycles per round trip, out_host[1] = rounds. */
 int dpb_tc_handshake_cycles(int64_t* out_host, int rounds);
 
+/* Diagnostic (tensor path): cycles of one 200-wide hidden-layer epilogue (13 chunks: TMEM load, affine + activation,
+ * bf16 hi/lo split, TMEM stores) with `ngroups` (1..4) groups of 4 warps sharing the chunks; out_host[0] = cycles. */
+int dpb_tc_epilogue_cycles(int64_t* out_host, int rounds, int ngroups);
+
 /* Diagnostic (tensor path): cycle counters of CTA 0 of the last critic/actor launch that used `workspace`
  * (synchronous copy): [0] kernel cycles, [1] control thread waiting for the path threads, [3] tensor-pipe ops,
  * [4] path thread 0 waiting for the tensor pipe, [5] its epilogue cycles, [6] of which hidden-layer epilogues,

@@ -43,6 +43,10 @@ def test_tcgen05_handshake_latency():
     assert rc == 0, lib.dpb_last_error(None)
     print("tcgen05 hand-off round trip:", int(out[0]), "cycles")
     assert out[1] == 2000 and 0 < out[0] < 100000
+    for g in (1, 2, 3, 4):
+        assert lib.dpb_tc_epilogue_cycles(out.ctypes.data_as(C.c_void_p), 500, g) == 0, lib.dpb_last_error(None)
+        print(f"hidden-layer epilogue (200 wide) with {4 * g} warps: {int(out[0])} cycles")
+        assert 0 < out[0] < 1000000
 
 
 # ------------------------------------------------------------------------------------------------
