@@ -321,18 +321,13 @@ __device__ __forceinline__ void put16h(uint32_t tl, int c, const float* v, uint3
 // flight while chunk c is processed:  f(c, const uint32_t r[16])
 template <class F>
 __device__ __forceinline__ void for_acc_chunks(uint32_t tl, int first, int nchunks, F f) {
-    uint32_t ra[16], rb[16];
-    if (first >= nchunks) return;
-    tmem_ld16(tl + COL_ACC + 16 * first, ra);
-    for (int c = first; c < nchunks; c += 4) {
+    // (the TMEM->register path is the bound of every epilogue -- 64 B/clk/SM, see DESIGN.md -- so a plain loop does as
+    //  well as a software-pipelined one and needs 16 registers fewer)
+    uint32_t ra[16];
+    for (int c = first; c < nchunks; c += 2) {
+        tmem_ld16(tl + COL_ACC + 16 * c, ra);
         tmem_ld_wait();
-        if (c + 2 < nchunks) tmem_ld16(tl + COL_ACC + 16 * (c + 2), rb);
         f(c, ra);
-        if (c + 2 < nchunks) {
-            tmem_ld_wait();
-            if (c + 4 < nchunks) tmem_ld16(tl + COL_ACC + 16 * (c + 4), ra);
-            f(c + 2, rb);
-        }
     }
 }
 
