@@ -41,8 +41,7 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
 }
 // Waits for the phase with the given parity to complete.  A wait that lasts ~4 s of GPU clocks is a
 // protocol bug: trap (the launch fails with an error) instead of hanging the device.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    const uint32_t addr = smem_u32(bar);
+__device__ __forceinline__ void mbar_wait_u32(uint32_t addr, uint32_t parity) {
     uint32_t done;
     asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                  : "=r"(done) : "r"(addr), "r"(parity) : "memory");
@@ -55,6 +54,8 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         if (clock64() - t0 > 8000000000LL) asm volatile("trap;");
     }
 }
+
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) { mbar_wait_u32(smem_u32(bar), parity); }
 
 // one non-blocking probe of the phase with the given parity
 __device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity) {
@@ -92,9 +93,23 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t base, uint32_t ncols) {
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
+// One lane of the (converged) warp: the control warp runs its protocol on all 32 lanes with identical, provably
+// warp-uniform values and issues tcgen05.mma / commit / arrive from the elected lane only -- the operands then sit in
+// uniform registers; issued from `if (lane == 0)` code every MMA costs a broadcast loop of ~100 cycles.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t p;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(p)::"memory");
+    return p != 0;
+}
+__device__ __forceinline__ uint32_t warp_uniform(uint32_t v) { return __shfl_sync(0xffffffffu, v, 0); }
+
 // all previously issued tcgen05.mma of this thread complete -> arrive(1) on the mbarrier
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void tc_commit_u32(uint32_t bar_saddr) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_saddr) : "memory");
 }
 
 // 16 consecutive fp32 columns of this thread's TMEM lane (warp w reads lanes 32*(w%4)..+31)

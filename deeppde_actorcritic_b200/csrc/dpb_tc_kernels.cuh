@@ -174,14 +174,14 @@ struct Roles {
     int row;
 };
 __device__ __forceinline__ void roles_init(Roles& r, const TcSmem& S, const TcArgs& a, uint32_t tmem) {
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, warp = (int)warp_uniform(tid >> 5);
     r.is_path = warp < TC_CTRL_WARP;
-    r.is_ctrl = (warp == TC_CTRL_WARP && lane == 0);
+    r.is_ctrl = (warp == TC_CTRL_WARP);          // the whole warp runs the control protocol (elect_one() issues)
     r.primary = warp < 4;
     r.row = tid & 127;
     Ctrl& C = r.C;
     C.ring = S.ring; C.full = S.full; C.empty = S.empty; C.acc_full = S.acc_full; C.a_ready = S.a_ready; C.sch = S.sch;
-    C.pc = S.pc; C.n_req = 0; C.n_consumed = 0; C.op_count = 0; C.tmem = tmem;
+    C.pc = S.pc; C.n_req = 0; C.n_consumed = 0; C.op_count = 0; C.tmem = warp_uniform(tmem); C.gen = 0;
     C.act_full = S.act_full; C.act_count = 0; C.nslot = a.nslot; C.slot_bytes = a.slot_bytes; C.act = S.act; C.dz = S.dz;
     r.P.tl = tmem + ((uint32_t)((warp & 3) * 32) << 16);
     r.P.grp = (warp >> 2) & 1;
@@ -195,7 +195,7 @@ __device__ __forceinline__ void roles_init(Roles& r, const TcSmem& S, const TcAr
 __device__ __forceinline__ void roles_stats(const Roles& r, const TcArgs& a, long long t_start) {
     if (!a.stats) return;
     long long* st = a.stats + (size_t)blockIdx.x * 16;
-    if (r.is_ctrl) { st[0] = clock64() - t_start; st[1] = r.C.t_aready; st[2] = 0; st[3] = r.C.n_ops; st[7] = r.C.t_issue; st[8] = r.C.t_accw; }
+    if (r.is_ctrl && (threadIdx.x & 31) == 0) { st[0] = clock64() - t_start; st[1] = r.C.t_aready; st[2] = 0; st[3] = r.C.n_ops; st[7] = r.C.t_issue; st[8] = r.C.t_accw; }
     if (threadIdx.x == 0) { st[4] = r.P.t_accw; st[5] = r.P.t_epi; st[6] = r.P.t_hid; }
 }
 

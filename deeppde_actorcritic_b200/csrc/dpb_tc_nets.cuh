@@ -153,7 +153,7 @@ struct Ctrl {
     Sched* sch;
     ProdCtl* pc;
     uint32_t nslot, slot_bytes;
-    uint32_t n_req, n_consumed, op_count, act_count, tmem;
+    uint32_t n_req, n_consumed, op_count, act_count, tmem, gen;
     uint32_t mm_slot, mm_use;        // ring cursor (slot index, wrap count) of the MMA issuer
     unsigned char *act, *dz;         // shared-memory operand images of the dW products (128 paths x K16 features, bf16)
     long long t_aready, t_issue, t_accw, n_ops;   // cycle counters (diagnostics)
@@ -169,16 +169,18 @@ __device__ __forceinline__ void ctrl_request(Ctrl& c) {
 __device__ __forceinline__ void ctrl_flush(Ctrl& c) {
     while (c.n_consumed != c.n_req) {
         mbar_wait(&c.full[c.mm_slot], c.mm_use & 1);
-        mbar_arrive(&c.empty[c.mm_slot]);
+        if (elect_one()) mbar_arrive(&c.empty[c.mm_slot]);        // (elect.sync: every lane has seen the phase complete)
         ++c.n_consumed;
         if (++c.mm_slot == c.nslot) { c.mm_slot = 0; ++c.mm_use; }
     }
-    c.sch->nops = 0;
+    if ((threadIdx.x & 31) == 0) c.sch->nops = 0;
+    __syncwarp();
 }
 // call after the schedule of a phase has been written (the producer is idle: everything requested was flushed)
 __device__ __forceinline__ void ctrl_sched_ready(Ctrl& c) {
+    __syncwarp();                                                 // lane 0 wrote the schedule
     __threadfence_block();
-    c.pc->gen = c.pc->gen + 1;
+    c.pc->gen = ++c.gen;
     __threadfence_block();
 }
 
@@ -218,15 +220,22 @@ __device__ __forceinline__ void producer_loop(unsigned char* ring, uint64_t* ful
 }
 
 __device__ __forceinline__ void sched_add(Sched* s, const unsigned char* p, int nch, int cb) {
-    s->ptr[s->nops] = p; s->nch[s->nops] = nch; s->cb[s->nops] = cb; ++s->nops;
+    if ((threadIdx.x & 31) == 0) { s->ptr[s->nops] = p; s->nch[s->nops] = nch; s->cb[s->nops] = cb; ++s->nops; }
 }
 __device__ __forceinline__ void sched_add_fwd(Sched* s, const TcNet& t, const unsigned char* img, int upto /*layers 0..upto*/) {
     for (int l = 0; l <= upto; ++l) sched_add(s, img + t.ly[l].img_f, t.ly[l].K16 / 16, t.ly[l].N16 * 64);
 }
 
 // D[acc] = A(planes in TMEM) x B(streamed image with R rows): nchunks contraction chunks, 3 split products
-__device__ __forceinline__ void ctrl_gemm_ts(Ctrl& cref, int nchunks, int R) {
+__device__ __forceinline__ void ctrl_gemm_ts(Ctrl& cref, int nchunks_, int R_) {
     Ctrl c = cref;                                                       // registers for the issue loop
+    // everything an MMA / commit operand is computed from goes through a lane-0 broadcast: the compiler then knows the
+    // values are warp-uniform (the state lives in per-thread local memory across the noinline callers)
+    const int nchunks = (int)warp_uniform((uint32_t)nchunks_), R = (int)warp_uniform((uint32_t)R_);
+    const uint32_t tmem = warp_uniform(c.tmem), nslot = warp_uniform(c.nslot), slot_bytes = warp_uniform(c.slot_bytes);
+    const uint32_t ring0 = warp_uniform(smem_u32(c.ring)), full0 = warp_uniform(smem_u32(c.full)), empty0 = warp_uniform(smem_u32(c.empty));
+    const uint32_t accf = warp_uniform(smem_u32(c.acc_full));
+    uint32_t mm_slot = warp_uniform(c.mm_slot), mm_use = warp_uniform(c.mm_use);
     const uint32_t idesc = idesc_bf16(128, R, 0, 0);
     ctrl_request(c);
     const long long t0 = clock64();
@@ -237,24 +246,25 @@ __device__ __forceinline__ void ctrl_gemm_ts(Ctrl& cref, int nchunks, int R) {
     tc_fence_after();
     const uint32_t lbo = (R >> 3) * 128;
     const uint64_t dlo = ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) | ((uint64_t)(128 >> 4) << 32) | (1ull << 46);
-    const uint32_t ring0 = smem_u32(c.ring);
     for (int s = 0; s < nchunks; ++s) {
-        const uint32_t slot = c.mm_slot;
-        mbar_wait(&c.full[slot], c.mm_use & 1);
-        const uint32_t sb = ring0 + slot * c.slot_bytes;
+        mbar_wait_u32(full0 + mm_slot * 8, mm_use & 1);
+        const uint32_t sb = ring0 + mm_slot * slot_bytes;
         const uint64_t bhi = dlo | (uint64_t)((sb >> 4) & 0x3FFF), blo = dlo | (uint64_t)(((sb + R * 32) >> 4) & 0x3FFF);
-        const uint32_t ahi = c.tmem + COL_AHI + s * 8, alo = c.tmem + COL_ALO + s * 8;
-        mma_ts(c.tmem + COL_ACC, ahi, bhi, idesc, s > 0);
-        mma_ts(c.tmem + COL_ACC, ahi, blo, idesc, 1);
-        mma_ts(c.tmem + COL_ACC, alo, bhi, idesc, 1);
-        tc_commit(&c.empty[slot]);
+        const uint32_t ahi = tmem + COL_AHI + s * 8, alo = tmem + COL_ALO + s * 8;
+        if (elect_one()) {
+            mma_ts(tmem + COL_ACC, ahi, bhi, idesc, s > 0);
+            mma_ts(tmem + COL_ACC, ahi, blo, idesc, 1);
+            mma_ts(tmem + COL_ACC, alo, bhi, idesc, 1);
+            tc_commit_u32(empty0 + mm_slot * 8);
+        }
         ++c.n_consumed;
-        if (++c.mm_slot == c.nslot) { c.mm_slot = 0; ++c.mm_use; }
+        if (++mm_slot == nslot) { mm_slot = 0; ++mm_use; }
         ctrl_request(c);
     }
-    tc_commit(c.acc_full);
+    if (elect_one()) tc_commit_u32(accf);
     c.t_issue += clock64() - ti0;
     ++c.op_count;
+    c.mm_slot = mm_slot; c.mm_use = mm_use;
     cref = c;
 }
 
@@ -502,8 +512,10 @@ __device__ __forceinline__ void sched_add_bwd(Sched* s, const TcNet& t, const un
 
 // global copy scratch -> ACT (bulk copy; waits until it has landed)
 __device__ __forceinline__ void ctrl_act_load(Ctrl& c, const unsigned char* src, uint32_t bytes) {
-    mbar_arrive_expect_tx(c.act_full, bytes);
-    bulk_g2s(c.act, src, bytes, c.act_full);
+    if (elect_one()) {
+        mbar_arrive_expect_tx(c.act_full, bytes);
+        bulk_g2s(c.act, src, bytes, c.act_full);
+    }
 }
 __device__ __forceinline__ void ctrl_act_wait(Ctrl& c) {
     mbar_wait(c.act_full, c.act_count & 1);
@@ -511,17 +523,21 @@ __device__ __forceinline__ void ctrl_act_wait(Ctrl& c) {
 }
 
 // D[acc] (rows = features 128*blk .. of ACT, cols = N16 features of DZ) = ACT^T DZ over the 128 paths
-__device__ __forceinline__ void ctrl_gemm_dw(Ctrl& c, int blk, int N16) {
+__device__ __forceinline__ void ctrl_gemm_dw(Ctrl& c, int blk_, int N16_) {
+    const int blk = (int)warp_uniform((uint32_t)blk_), N16 = (int)warp_uniform((uint32_t)N16_);
     const uint32_t idesc = idesc_bf16(128, N16, 1, 1);
     mbar_wait(c.a_ready, c.op_count & 1);
     tc_fence_after();
-    const uint32_t a0 = smem_u32(c.act) + blk * 16 * 2048, b0 = smem_u32(c.dz);
+    const uint32_t a0 = warp_uniform(smem_u32(c.act)) + blk * 16 * 2048, b0 = warp_uniform(smem_u32(c.dz));
+    const uint32_t tmem = warp_uniform(c.tmem), accf = warp_uniform(smem_u32(c.acc_full));
+    if (elect_one()) {
 #pragma unroll
-    for (int s = 0; s < TC_PATHS / 16; ++s) {
-        const uint64_t ad = smem_desc(a0 + s * 256, 128, 2048), bd = smem_desc(b0 + s * 256, 128, 2048);
-        mma_ss(c.tmem + COL_ACC, ad, bd, idesc, s > 0);
+        for (int s = 0; s < TC_PATHS / 16; ++s) {
+            const uint64_t ad = smem_desc(a0 + s * 256, 128, 2048), bd = smem_desc(b0 + s * 256, 128, 2048);
+            mma_ss(tmem + COL_ACC, ad, bd, idesc, s > 0);
+        }
+        tc_commit_u32(accf);
     }
-    tc_commit(c.acc_full);
     ++c.op_count;
 }
 
