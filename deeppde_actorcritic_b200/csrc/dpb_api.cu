@@ -463,16 +463,16 @@ static int critic_step_tc(dpb_handle* h, const void* thA, const void* thV, const
         DPB_CUDA(h, cudaMemsetAsync(ws + L.slabs, 0, (size_t)L.nslab * (h->sV.gtotal + h->sG.gtotal) * sizeof(float), st));
     }
     const size_t smem = tc::tc_smem_bytes(h->tA.vec_floats, h->tV.vec_floats, h->tG.vec_floats, a.actdz_bytes, a.nslot, a.slot_bytes);
-    void (*kern)(const tc::TcArgs) = tc::critic_tc_kernel<0, -1, 0>;
+    tc::TcKernelFn kern = tc::tc_get_critic_generic();
     if (tc_specialised(h)) {
         switch (h->cfg.eqn) {
-        case DPB_EQN_LQR: kern = tc::critic_tc_kernel<24, EQ_LQR, 0>; break;
-        case DPB_EQN_EKN: kern = tc::critic_tc_kernel<24, EQ_EKN, 0>; break;
-        case DPB_EQN_LQR_VAR: kern = tc::critic_tc_kernel<24, EQ_LQRVAR, 0>; break;
+        case DPB_EQN_LQR: kern = tc::tc_get_critic_lqr(); break;
+        case DPB_EQN_EKN: kern = tc::tc_get_critic_ekn(); break;
+        case DPB_EQN_LQR_VAR: kern = tc::tc_get_critic_lqrvar(); break;
         case DPB_EQN_VDP:
-            if (h->cfg.control_dim == 2) kern = tc::critic_tc_kernel<24, EQ_VDP, 2>;
-            else if (h->cfg.control_dim == 5) kern = tc::critic_tc_kernel<24, EQ_VDP, 5>;
-            else if (h->cfg.control_dim == 10) kern = tc::critic_tc_kernel<24, EQ_VDP, 10>;
+            if (h->cfg.control_dim == 2) kern = tc::tc_get_critic_vdp2();
+            else if (h->cfg.control_dim == 5) kern = tc::tc_get_critic_vdp5();
+            else if (h->cfg.control_dim == 10) kern = tc::tc_get_critic_vdp10();
             break;
         }
     }
@@ -517,16 +517,16 @@ static int actor_step_tc(dpb_handle* h, const void* thA, const void* thV, const 
         DPB_CUDA(h, cudaMemsetAsync(ws + L.slabs, 0, (size_t)L.nslab * h->sA.gtotal * sizeof(float), st));
     }
     const size_t smem = tc::tc_smem_bytes(h->tA.vec_floats, h->tV.vec_floats, h->tG.vec_floats, a.actdz_bytes, a.nslot, a.slot_bytes);
-    void (*kern)(const tc::TcArgs) = tc::actor_tc_kernel<0, -1, 0>;
+    tc::TcKernelFn kern = tc::tc_get_actor_generic();
     if (tc_specialised(h)) {
         switch (h->cfg.eqn) {
-        case DPB_EQN_LQR: kern = tc::actor_tc_kernel<24, EQ_LQR, 0>; break;
-        case DPB_EQN_EKN: kern = tc::actor_tc_kernel<24, EQ_EKN, 0>; break;
-        case DPB_EQN_LQR_VAR: kern = tc::actor_tc_kernel<24, EQ_LQRVAR, 0>; break;
+        case DPB_EQN_LQR: kern = tc::tc_get_actor_lqr(); break;
+        case DPB_EQN_EKN: kern = tc::tc_get_actor_ekn(); break;
+        case DPB_EQN_LQR_VAR: kern = tc::tc_get_actor_lqrvar(); break;
         case DPB_EQN_VDP:
-            if (h->cfg.control_dim == 2) kern = tc::actor_tc_kernel<24, EQ_VDP, 2>;
-            else if (h->cfg.control_dim == 5) kern = tc::actor_tc_kernel<24, EQ_VDP, 5>;
-            else if (h->cfg.control_dim == 10) kern = tc::actor_tc_kernel<24, EQ_VDP, 10>;
+            if (h->cfg.control_dim == 2) kern = tc::tc_get_actor_vdp2();
+            else if (h->cfg.control_dim == 5) kern = tc::tc_get_actor_vdp5();
+            else if (h->cfg.control_dim == 10) kern = tc::tc_get_actor_vdp10();
             break;
         }
     }

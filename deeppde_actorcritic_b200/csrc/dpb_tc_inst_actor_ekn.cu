@@ -1,0 +1,7 @@
+// actor_tc_kernel<24, EQ_EKN, 0> (see dpb_tc_inst.cuh)
+#define DPB_INST_NAME actor_ekn
+#define DPB_INST_KERNEL actor_tc_kernel
+#define DPB_INST_DP 24
+#define DPB_INST_EQN EQ_EKN
+#define DPB_INST_MV 0
+#include "dpb_tc_inst.cuh"

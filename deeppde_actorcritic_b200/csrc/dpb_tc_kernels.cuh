@@ -39,6 +39,12 @@ struct TcArgs {
     long long* stats;               // [grid][16] cycle counters (diagnostics), may be NULL
 };
 
+// the kernels are instantiated in their own translation units (dpb_tc_inst_*.cu)
+typedef void (*TcKernelFn)(const TcArgs);
+#define DPB_TC_FOR_INSTANCES(X) X(lqr) X(ekn) X(lqrvar) X(vdp2) X(vdp5) X(vdp10) X(generic)
+#define DPB_TC_DECL_GETTERS(n) TcKernelFn tc_get_critic_##n(); TcKernelFn tc_get_actor_##n();
+DPB_TC_FOR_INSTANCES(DPB_TC_DECL_GETTERS)
+
 struct TcSmem {
     unsigned char *act, *dz;
     unsigned char* ring;
@@ -185,9 +191,10 @@ __device__ __forceinline__ void roles_init(Roles& r, const TcSmem& S, const TcAr
     C.act_full = S.act_full; C.act_count = 0; C.nslot = a.nslot; C.slot_bytes = a.slot_bytes; C.act = S.act; C.dz = S.dz;
     r.P.tl = tmem + ((uint32_t)((warp & 3) * 32) << 16);
     r.P.grp = (warp >> 2) & 1;
-    r.P.acc_full = S.acc_full; r.P.a_ready = S.a_ready; r.P.op_count = 0;
-    r.P.t_accw = 0; r.P.t_epi = 0; r.P.t_hid = 0; r.P.t_mark = clock64();
-    C.t_aready = 0; C.t_issue = 0; C.t_accw = 0; C.n_ops = 0;
+    r.P.acc_full = smem_u32(S.acc_full); r.P.a_ready = smem_u32(S.a_ready); r.P.op_count = 0;
+    TC_STAT(r.P.t_accw = 0; r.P.t_epi = 0; r.P.t_hid = 0; r.P.t_mark = clock64();)
+    TC_STAT(C.t_aready = 0; C.t_issue = 0; C.t_accw = 0;)
+    C.n_ops = 0;
     C.mm_slot = 0; C.mm_use = 0;
 }
 // stats row: [0] kernel cycles, ctrl: [1] waiting for the path threads, [2] waiting for weights, [3] ops;
@@ -195,8 +202,11 @@ __device__ __forceinline__ void roles_init(Roles& r, const TcSmem& S, const TcAr
 __device__ __forceinline__ void roles_stats(const Roles& r, const TcArgs& a, long long t_start) {
     if (!a.stats) return;
     long long* st = a.stats + (size_t)blockIdx.x * 16;
-    if (r.is_ctrl && (threadIdx.x & 31) == 0) { st[0] = clock64() - t_start; st[1] = r.C.t_aready; st[2] = 0; st[3] = r.C.n_ops; st[7] = r.C.t_issue; st[8] = r.C.t_accw; }
-    if (threadIdx.x == 0) { st[4] = r.P.t_accw; st[5] = r.P.t_epi; st[6] = r.P.t_hid; }
+    if (r.is_ctrl && (threadIdx.x & 31) == 0) {
+        st[0] = clock64() - t_start; st[3] = r.C.n_ops;
+        TC_STAT(st[1] = r.C.t_aready; st[2] = 0; st[7] = r.C.t_issue; st[8] = r.C.t_accw;)
+    }
+    TC_STAT(if (threadIdx.x == 0) { st[4] = r.P.t_accw; st[5] = r.P.t_epi; st[6] = r.P.t_hid; })
 }
 
 // sum over the 128 path threads of per-thread accumulators acc[0..n) -> atomicAdd into dst (kernel end)
@@ -256,12 +266,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) critic_tc_kernel(const TcArgs a
     KLOOP(k, DPX) { sxV[k] = 0.f; s0V[k] = 0.f; sxG[k] = 0.f; s0G[k] = 0.f; }
 
     float loss0 = 0.f, loss1 = 0.f;
+    TC_STAT(long long ph_roll = 0, ph_val = 0, ph_grad = 0;)          // cycles per phase (diagnostics)
+    TC_STAT(long long seg_dw = 0, seg_A = 0, seg_mv = 0, seg_G = 0;)
     const long long ntiles = (a.B_local + TC_PATHS - 1) / TC_PATHS;
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const long long base = tile * TC_PATHS;
         const long long gp = base + row;                          // local path index of this thread
         const bool valid = is_path && gp < a.B_local;
         const bool wr = valid && primary;               // this thread does the global stores of its path
+        TC_STAT(const long long tp0 = clock64();)
         float x[DPX], u[DPX], dwv[DPX], sdw[DPX], g[DPX], raw[DPX];
         int flag = 0, nacc = 0;
         float disc = 1.f, y = 0.f;
@@ -288,10 +301,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) critic_tc_kernel(const TcArgs a
                 if (td1) ctrl_net_forward(C, nG, nG.L);
             } else if (is_path) {
                 // per-path arithmetic is placed where the tensor pipe is busy with a first layer
+                TC_STAT(const long long q0 = clock64();)
                 if (!cheat) path_net_begin(P, nA, S.vecA, x);
+                TC_STAT(const long long q1 = clock64();)
                 path_dw(a, gp, valid, t, dwv);
                 float dt, sqdt, xn; int dtg;
                 fwd_dt<float, DP, EQN, MV>(E, x, flag, 1, 0, dt, sqdt, xn, dtg);
+                TC_STAT(seg_dw += clock64() - q1;)
                 if (cheat) {
                     eq_u_true<float, DP, EQN, MV>(E, x, u, 1, 0);
                 } else {
@@ -299,6 +315,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) critic_tc_kernel(const TcArgs a
                     if (nA.ekn_head) ekn_head_fwd<float, DP, EQN, MV>(raw, u, nA.mctrl, 1, 0);
                     else KLOOP(j, E.m) u[j] = raw[j];
                 }
+                TC_STAT(const long long q3 = clock64(); seg_A += q3 - q0;)
                 if (td1) path_net_begin(P, nG, S.vecG, x);                        // NN_value_grad at x_t (before the move)
                 float* tr = traj + (size_t)t * 2 * sr * TC_PATHS;
                 if (need_grad && td1 && primary)
@@ -307,7 +324,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) critic_tc_kernel(const TcArgs a
                 if (!prop_only) w = eq_w<float, DP, EQN, MV>(E, x, u, 1, 0);
                 const int coef = fwd_move<float, DP, EQN, MV>(E, x, u, dwv, dt, sqdt, xn, flag, sdw, 1, 0);
                 const float cf = (float)coef;
+                TC_STAT(const long long q4 = clock64(); seg_mv += q4 - q3;)
                 if (td1) path_net_finish(P, nG, S.vecG, g);
+                TC_STAT(seg_G += clock64() - q4;)
                 y = y + w * disc * cf * dt;                                       // solver.py:170-174
                 if (td1) {
                     float dif = 0.f;
@@ -338,6 +357,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) critic_tc_kernel(const TcArgs a
             }
             if (a.o_exit) a.o_exit[gp] = nacc;
         }
+        TC_STAT(const long long tp1 = clock64(); ph_roll += tp1 - tp0;)
         if (prop_only) continue;
         // ------------------------------------------------------------------ NN_value at x_0, x_N, x_bdry
         float rho_v = 0.f, rho_b = 0.f, rhog = 0.f;
@@ -392,6 +412,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) critic_tc_kernel(const TcArgs a
         }
         loss0 += tc_block_sum(rho_v, S.red);
         loss1 += tc_block_sum(rho_b, S.red);
+        TC_STAT(const long long tp2 = clock64(); ph_val += tp2 - tp1;)
         // ------------------------------------------------------------------ sweep 2: NN_value_grad backward
         if (need_grad && td1) {
             if (is_ctrl) {
@@ -416,7 +437,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) critic_tc_kernel(const TcArgs a
                 }
             }
         }
+        TC_STAT(ph_grad += clock64() - tp2;)
     }
+    TC_STAT(if (a.stats && tid == 0) { long long* st = a.stats + (size_t)blockIdx.x * 16; st[9] = ph_roll; st[10] = ph_val; st[11] = ph_grad; st[12] = seg_dw; st[13] = seg_A; st[14] = seg_mv; st[15] = seg_G; })
     if (is_ctrl) { ctrl_flush(C); C.pc->quit = 1; }
     if (need_grad) {
         reduce_rows_to(gsV + gV.gX, sxV, d, primary);

@@ -87,7 +87,7 @@ inline bool tcnet_supported(const TcNet& t) {
 
 // ------------------------------------------------------------------------------------------- pack
 // flat FP32 parameters -> bf16 hi/lo operand images + the FP32 vector block (gamma*c, beta, ...)
-__global__ void tc_pack_kernel(TcNet t, const float* __restrict__ th, unsigned char* __restrict__ img, float* __restrict__ vec, float c) {
+static __global__ void tc_pack_kernel(TcNet t, const float* __restrict__ th, unsigned char* __restrict__ img, float* __restrict__ vec, float c) {
     const NetDev& nd = t.flat;
     const long long stride = (long long)gridDim.x * blockDim.x;
     const long long t0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -132,6 +132,14 @@ __global__ void tc_pack_kernel(TcNet t, const float* __restrict__ th, unsigned c
     }
 }
 
+// cycle-counter diagnostics (tools/time_forward.py): compiled in only with -DDPB_TC_STATS -- the counters live in
+// per-thread local memory across the noinline helpers and cost ~6 % of the kernel when enabled
+#ifdef DPB_TC_STATS
+#define TC_STAT(...) __VA_ARGS__
+#else
+#define TC_STAT(...)
+#endif
+
 // ------------------------------------------------------------------------------ control-thread side
 struct Sched {                       // cyclic chunk schedule of the current phase (shared memory)
     const unsigned char* ptr[MAXOPS];
@@ -156,7 +164,8 @@ struct Ctrl {
     uint32_t n_req, n_consumed, op_count, act_count, tmem, gen;
     uint32_t mm_slot, mm_use;        // ring cursor (slot index, wrap count) of the MMA issuer
     unsigned char *act, *dz;         // shared-memory operand images of the dW products (128 paths x K16 features, bf16)
-    long long t_aready, t_issue, t_accw, n_ops;   // cycle counters (diagnostics)
+    long long n_ops;
+    TC_STAT(long long t_aready, t_issue, t_accw;)   // cycle counters (diagnostics)
 };
 
 // let the producer run up to nslot chunks ahead of the MMAs (one shared-memory store, never waits)
@@ -238,10 +247,9 @@ __device__ __forceinline__ void ctrl_gemm_ts(Ctrl& cref, int nchunks_, int R_) {
     uint32_t mm_slot = warp_uniform(c.mm_slot), mm_use = warp_uniform(c.mm_use);
     const uint32_t idesc = idesc_bf16(128, R, 0, 0);
     ctrl_request(c);
-    const long long t0 = clock64();
+    TC_STAT(const long long t0 = clock64();)
     mbar_wait(c.a_ready, c.op_count & 1);
-    const long long ti0 = clock64();
-    c.t_aready += ti0 - t0;
+    TC_STAT(const long long ti0 = clock64(); c.t_aready += ti0 - t0;)
     ++c.n_ops;
     tc_fence_after();
     const uint32_t lbo = (R >> 3) * 128;
@@ -262,24 +270,24 @@ __device__ __forceinline__ void ctrl_gemm_ts(Ctrl& cref, int nchunks_, int R_) {
         ctrl_request(c);
     }
     if (elect_one()) tc_commit_u32(accf);
-    c.t_issue += clock64() - ti0;
+    TC_STAT(c.t_issue += clock64() - ti0;)
     ++c.op_count;
     c.mm_slot = mm_slot; c.mm_use = mm_use;
     cref = c;
 }
 
-__device__ __noinline__ void ctrl_net_forward(Ctrl& c, const TcNet& t, int upto) {
+static __device__ __noinline__ void ctrl_net_forward(Ctrl& c, const TcNet& t, int upto) {
     for (int l = 0; l <= upto; ++l) ctrl_gemm_ts(c, t.ly[l].K16 / 16, t.ly[l].N16);
 }
 
 // ---------------------------------------------------------------------------------- path-thread side
 struct PathCtx {
     uint32_t tl;                   // TMEM address of this thread's lane (column 0)
-    uint64_t *acc_full, *a_ready;
+    uint32_t acc_full, a_ready;    // shared-memory addresses of the two hand-off barriers
     uint32_t op_count;
     int grp;                       // 0: threads 0..127, 1: threads 128..255 (chunk parity this thread handles)
-    long long t_accw, t_mark;      // cycles spent waiting for the tensor pipe; time of the last wake-up (diagnostics)
-    long long t_epi, t_hid;        // t_hid: cycles inside hidden-layer epilogues only
+    TC_STAT(long long t_accw, t_mark;)      // cycles spent waiting for the tensor pipe; time of the last wake-up
+    TC_STAT(long long t_epi, t_hid;)        // t_hid: cycles inside hidden-layer epilogues only
 };
 
 // A planes written and accumulator drained: one arrival per path warp (a_ready counts the 8 path warps)
@@ -287,14 +295,13 @@ __device__ __forceinline__ void path_publish(PathCtx& p) {
     tmem_st_wait();
     tc_fence_before();
     __syncwarp();
-    if ((threadIdx.x & 31) == 0) mbar_arrive(p.a_ready);
-    p.t_epi += clock64() - p.t_mark;
+    if ((threadIdx.x & 31) == 0) mbar_arrive_u32(p.a_ready);
+    TC_STAT(p.t_epi += clock64() - p.t_mark;)
 }
 __device__ __forceinline__ void path_wait_acc(PathCtx& p) {
-    const long long t0 = clock64();
-    mbar_wait(p.acc_full, p.op_count & 1);
-    p.t_mark = clock64();
-    p.t_accw += p.t_mark - t0;
+    TC_STAT(const long long t0 = clock64();)
+    mbar_wait_u32(p.acc_full, p.op_count & 1);
+    TC_STAT(p.t_mark = clock64(); p.t_accw += p.t_mark - t0;)
     tc_fence_after();
     ++p.op_count;
 }
@@ -396,7 +403,7 @@ __device__ __forceinline__ void path_put_y0(PathCtx& p, const TcNet& t, const fl
 // hidden layer epilogue: a = z + relu(z), z = acc * gc + bb (solver.py:267-269) -> planes
 __device__ __forceinline__ void path_epi_hidden(PathCtx& p, const float* gcbb, int N16) {
     path_wait_acc(p);
-    const long long th0 = clock64();
+    TC_STAT(const long long th0 = clock64();)
     const float* gc = gcbb;
     const float* bb = gcbb + N16;
     for_acc_chunks(p.tl, p.grp, N16 / 16, [&](int c, const uint32_t* r) {
@@ -407,7 +414,7 @@ __device__ __forceinline__ void path_epi_hidden(PathCtx& p, const float* gcbb, i
         put16(p.tl, c, v);
     });
     path_publish(p);
-    p.t_hid += clock64() - th0;
+    TC_STAT(p.t_hid += clock64() - th0;)
 }
 
 // last layer: out[n] = acc * gc + bb (solver.py:270-271), n < nl <= 32; static indexing
@@ -432,7 +439,7 @@ __device__ __forceinline__ void path_last(PathCtx& p, const float* gcbb, int N16
 }
 
 // all hidden-layer epilogues of a forward-only evaluation (no per-path arrays involved)
-__device__ __noinline__ void path_hidden(PathCtx& p, const TcNet& t, const float* vec) {
+static __device__ __noinline__ void path_hidden(PathCtx& p, const TcNet& t, const float* vec) {
     for (int l = 0; l < t.L; ++l) path_epi_hidden(p, vec + t.ly[l].vec, t.ly[l].N16);
 }
 
@@ -459,12 +466,15 @@ namespace tc {
 
 // ===================================================================================== backward pass
 // Gradient slab of one network on the tensor path (per CTA, FP32):
-//   layer l: (kl + 1) x nl, row-major; rows 0..kl-1 = G_l = a_l^T dz_l, row kl = column sums of dz_l
-//   (the activation copies carry a constant 1 in feature kl), then SX[in] = sum x*dy0, S0[in] = sum dy0.
+//   layer l: (kl + 1) rows x nl columns; rows 0..kl-1 = G_l = a_l^T dz_l, row kl = column sums of dz_l (the
+//   activation copies carry a constant 1 in feature kl), stored as [column group of 4][row][4] (tcslab_idx) so that the
+//   32 lanes of a warp -- 32 consecutive rows of the accumulator -- reduce 512 contiguous bytes per instruction;
+//   then SX[in] = sum x*dy0, S0[in] = sum dy0.
 struct TcSlab { long long gW[MAXLIN], gX, g0, gtotal; };
+__host__ __device__ __forceinline__ long long tcslab_idx(int k, int n, int kl) { return ((long long)(n >> 2) * (kl + 1) + k) * 4 + (n & 3); }
 inline void tcslab_init(TcSlab& g, const TcNet& t) {
     long long o = 0;
-    for (int l = 0; l <= t.L; ++l) { g.gW[l] = o; o += ((long long)(t.ly[l].kl + 1) * t.ly[l].nl + 3) & ~3LL; }
+    for (int l = 0; l <= t.L; ++l) { g.gW[l] = o; o += (long long)(t.ly[l].kl + 1) * ((t.ly[l].nl + 3) & ~3); }
     g.gX = o; o += (t.in + 3) & ~3; g.g0 = o; o += (t.in + 3) & ~3;
     g.gtotal = o;
 }
@@ -477,7 +487,7 @@ inline __host__ __device__ long long tc_copy_off(const TcNet& t, int l) {
 inline __host__ __device__ long long tc_copy_bytes(const TcNet& t) { return tc_copy_off(t, t.L); }
 
 // raw slab -> flat gradient (same formulas as finalize_grad_kernel of the exact path)
-__global__ void tc_finalize_grad_kernel(TcNet t, TcSlab g, const float* __restrict__ th, const float* __restrict__ raw, float* __restrict__ grad, float c) {
+static __global__ void tc_finalize_grad_kernel(TcNet t, TcSlab g, const float* __restrict__ th, const float* __restrict__ raw, float* __restrict__ grad, float c) {
     const NetDev& nd = t.flat;
     const long long stride = (long long)gridDim.x * blockDim.x;
     const long long t0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -489,12 +499,12 @@ __global__ void tc_finalize_grad_kernel(TcNet t, TcSlab g, const float* __restri
         const int kl = t.ly[l].kl, nl = t.ly[l].nl;
         for (long long i = t0; i < (long long)kl * nl; i += stride) {
             int n = (int)(i % nl);
-            grad[nd.fW[l] + i] = raw[g.gW[l] + i] * (th[nd.fg[l] + n] * c);
+            grad[nd.fW[l] + i] = raw[g.gW[l] + tcslab_idx((int)(i / nl), n, kl)] * (th[nd.fg[l] + n] * c);
         }
         for (long long n = t0; n < nl; n += stride) {
             float s = 0.f;
-            for (int k = 0; k < kl; ++k) s = fmaf(th[nd.fW[l] + (long long)k * nl + n], raw[g.gW[l] + (long long)k * nl + n], s);
-            const float C = raw[g.gW[l] + (long long)kl * nl + n];
+            for (int k = 0; k < kl; ++k) s = fmaf(th[nd.fW[l] + (long long)k * nl + n], raw[g.gW[l] + tcslab_idx(k, n, kl)], s);
+            const float C = raw[g.gW[l] + tcslab_idx(kl, n, kl)];
             if (l == t.L) {
                 s = s + th[nd.fbias + n] * C;
                 grad[nd.fbias + n] = (th[nd.fg[l] + n] * c) * C;
@@ -543,7 +553,7 @@ __device__ __forceinline__ void ctrl_gemm_dw(Ctrl& c, int blk_, int N16_) {
 
 // backward of one network evaluation.  need_w: dW products (+ drains on the path side);
 // copies: per-CTA global scratch holding the bf16 copies of a_0..a_{L-1} (a_L is already in ACT).
-__device__ __noinline__ void ctrl_net_backward(Ctrl& c, const TcNet& t, bool need_w, const unsigned char* copies) {
+static __device__ __noinline__ void ctrl_net_backward(Ctrl& c, const TcNet& t, bool need_w, const unsigned char* copies) {
     for (int l = t.L; l >= 0; --l) {
         if (need_w) {
             if (l < t.L) ctrl_act_wait(c);
@@ -565,7 +575,7 @@ struct Masks { uint32_t m[MAXLIN][8]; };     // m[l] bit k: a_l[k] > 0  (l = 1..
 // a_1..a_{L-1} (global scratch `copies`, NULL: none) and of a_L (shared ACT image, NULL: none).
 // skip_last: the raw output is not needed -- the last hidden epilogue does not publish (the caller writes
 // dz_L and publishes).
-__device__ __noinline__ void path_hidden_keep(PathCtx& p, const TcNet& t, const float* vec, Masks& mk, unsigned char* copies,
+static __device__ __noinline__ void path_hidden_keep(PathCtx& p, const TcNet& t, const float* vec, Masks& mk, unsigned char* copies,
                                               unsigned char* act, int row, bool skip_last) {
     for (int l = 0; l <= t.L; ++l)
 #pragma unroll
@@ -609,31 +619,23 @@ __device__ __forceinline__ void path_net_forward_keep(PathCtx& p, const TcNet& t
 __device__ __forceinline__ void path_drain(PathCtx& p, int blk, int row, int kl, int nl, int N16, float* slab) {
     path_wait_acc(p);
     const int f = 128 * blk + row;
-    float* dst = slab + (long long)f * nl;
+    float* dst = slab + (long long)f * 4;
+    const long long gstride = (long long)(kl + 1) * 4;                  // next column group
     const bool rowok = f <= kl;
-    const bool vec4 = (nl & 3) == 0;
     for (int c = p.grp; c < N16 / 16; c += 2) {
         uint32_t r[16];
         tmem_ld16(p.tl + COL_ACC + 16 * c, r);
         tmem_ld_wait();
         if (!rowok) continue;
-        if (vec4) {
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const int n = 16 * c + 4 * q;
-                if (n < nl) red_add_v4(dst + n, __uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]), __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3]));
-            }
-        } else {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                const int n = 16 * c + j;
-                if (n < nl) atomicAdd(dst + n, __uint_as_float(r[j]));
-            }
+        for (int q = 0; q < 4; ++q) {                                     // (columns >= nl of the accumulator are zero)
+            const int n = 16 * c + 4 * q;
+            if (n < nl) red_add_v4(dst + (n >> 2) * gstride, __uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]), __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3]));
         }
     }
     tc_fence_before();
     __syncwarp();
-    if ((threadIdx.x & 31) == 0) mbar_arrive(p.a_ready);   // accumulator drained
+    if ((threadIdx.x & 31) == 0) mbar_arrive_u32(p.a_ready);   // accumulator drained
 }
 
 // cotangent of the raw output (nl <= 32 values, static indexing) -> planes (+ DZ image), publish
@@ -660,7 +662,7 @@ __device__ __forceinline__ void path_put_dz(PathCtx& p, const TcNet& t, const fl
 
 // middle of the backward: for l = L..0 the dW drains (need_w), and for l >= 1 the dX epilogue
 // dz_{l-1} = dA_l (.) slope(a_l) -> planes (+ DZ).  Ends before the result of the last product (dy0) is read.
-__device__ __noinline__ void path_backward_mid(PathCtx& p, const TcNet& t, const TcSlab& g, const Masks& mk, bool need_w, float* slab,
+static __device__ __noinline__ void path_backward_mid(PathCtx& p, const TcNet& t, const TcSlab& g, const Masks& mk, bool need_w, float* slab,
                                                unsigned char* dzimg, int row) {
     for (int l = t.L; l >= 0; --l) {
         if (need_w) {
