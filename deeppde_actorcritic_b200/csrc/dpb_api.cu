@@ -405,7 +405,7 @@ static int tc_ring(dpb_handle* h, tc::TcArgs& a, bool grads) {
 static void tc_fill(dpb_handle* h, tc::TcArgs& a, const Layout& L, char* ws, const dpb_inputs* in, int64_t B_local, int64_t path_offset,
                     int64_t B_global, int32_t N, double T, uint32_t flags, const dpb_path_outputs* outs) {
     memset(&a, 0, sizeof(a));
-    fill_eqn(h->cfg, N, T, a.eq);
+    { EqnD e; fill_eqn(h->cfg, N, T, e); a.eqf = Eq<float>(e); }
     a.nA = h->tA; a.nV = h->tV; a.nG = h->tG;
     a.gA = h->sA; a.gV = h->sV; a.gG = h->sG;
     a.imgA = (const unsigned char*)(ws + L.imgA); a.imgV = (const unsigned char*)(ws + L.imgV); a.imgG = (const unsigned char*)(ws + L.imgG);

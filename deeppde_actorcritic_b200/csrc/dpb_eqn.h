@@ -62,6 +62,7 @@ struct Eq {
     real R, R2, gamma, sig, p, q, beta, k, a, eps, a2, a3, cu, wconst, ZR, C0;
     real lv_num, lv_den, lv_un, lv_ud, lv_ue, lv_gk;
     real delta_t, sqrt_delta_t, hb, c3, hmin;
+    Eq() = default;
     DPB_HD explicit Eq(const EqnD& e)
         : eqn(e.eqn), d(e.d), m(e.m), scheme(e.scheme), td(e.td),
           R((real)e.R), R2((real)e.R2), gamma((real)e.gamma), sig((real)e.sig), p((real)e.p), q((real)e.q),
@@ -303,12 +304,10 @@ DPB_HD int fwd_move(const Eq<real>& E, real* x, const real* u, const real* dw, r
         cc = eq_drift_c<real, DMAX, EQN, MV>(E, r);
     }
     real n2 = (real)0;
-    real dx[DMAX > 0 ? DMAX : 32];
     DPB_LOOP(k, d) {
         real sd = eq_sigma<real, DMAX, EQN, MV>(E, x, u, k, ld, p) * DPB_AT(dw, k);
         if (sdw_out) DPB_AT(sdw_out, k) = sd;
         real dk = eq_drift<real, DMAX, EQN, MV>(E, cc, x, u, k, ld, p) * dt + sd * sqdt;
-        dx[k] = dk;
         real pk = DPB_AT(x, k) + dk;
         n2 = n2 + pk * pk;
     }
@@ -323,7 +322,14 @@ DPB_HD int fwd_move(const Eq<real>& E, real* x, const real* u, const real* dw, r
         coef = (flag > 0 && newflag > 0) ? 1 : 0;           // sign(flag) * sign(new_flag)
     }
     if (coef) {
-        DPB_LOOP(k, d) DPB_AT(x, k) = DPB_AT(x, k) + dx[k];
+        // the increment is evaluated again (same expression, same bits) rather than kept in d registers; every
+        // component reads the OLD state, so the new one is staged before it is written back
+        real xn[DMAX > 0 ? DMAX : 32];
+        DPB_LOOP(k, d) {
+            real sd = eq_sigma<real, DMAX, EQN, MV>(E, x, u, k, ld, p) * DPB_AT(dw, k);
+            xn[k] = DPB_AT(x, k) + (eq_drift<real, DMAX, EQN, MV>(E, cc, x, u, k, ld, p) * dt + sd * sqdt);
+        }
+        DPB_LOOP(k, d) DPB_AT(x, k) = xn[k];
     }
     flag = newflag;
     return coef;

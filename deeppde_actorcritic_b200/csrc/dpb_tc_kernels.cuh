@@ -13,7 +13,7 @@ namespace dpb {
 namespace tc {
 
 struct TcArgs {
-    EqnD eq;
+    Eq<float> eqf;                  // equation + scheme constants in the arithmetic type of the tensor path
     TcNet nA, nV, nG;
     const unsigned char *imgA, *imgV, *imgG;
     const float *vecA, *vecV, *vecG;
@@ -137,7 +137,7 @@ __device__ __forceinline__ float tc_block_sum(float v, float* red) {
 // increments of step t for one path (same generator and bits as load_dw of the exact path)
 template <int DPX>
 __device__ __forceinline__ void path_dw(const TcArgs& a, long long gpath_local, bool valid, int t, float (&dw)[DPX]) {
-    const int d = a.eq.d;
+    const int d = a.eqf.d;
     if (a.dw_mode == DW_EXTERNAL) {
         KLOOP(k, d) dw[k] = valid ? a.dw[(gpath_local * d + k) * (long long)a.N + t] : 0.f;
         return;
@@ -251,7 +251,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) critic_tc_kernel(const TcArgs a
     const int tid = threadIdx.x, warp = tid >> 5;
     const bool is_path = R.is_path, is_ctrl = R.is_ctrl, primary = R.primary;
     const int row = R.row;
-    const Eq<float> E(a.eq);
+    const Eq<float>& E = a.eqf;                                   // kernel-parameter space: fields are constant-bank operands
     const int d = E.d, N = a.N, sr = a.sr;
     const bool cheat = a.flags & F_CHEAT_CONTROL, prop_only = a.flags & F_PROPAGATE_ONLY;
     const bool need_grad = (a.flags & F_NEED_GRAD) && !prop_only;
@@ -302,16 +302,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) critic_tc_kernel(const TcArgs a
             } else if (is_path) {
                 // per-path arithmetic is placed where the tensor pipe is busy with a first layer
                 TC_STAT(const long long q0 = clock64();)
-                if (!cheat) path_net_begin(P, nA, S.vecA, x);
+                // (the increments and the step size are computed while the tensor pipe works on the two wide layers)
+                if (!cheat) { path_net_begin(P, nA, S.vecA, x); path_hidden_range(P, nA, S.vecA, 0, 1); }
                 TC_STAT(const long long q1 = clock64();)
                 path_dw(a, gp, valid, t, dwv);
+                if (!cheat) path_hidden_range(P, nA, S.vecA, 1, 2);
                 float dt, sqdt, xn; int dtg;
                 fwd_dt<float, DP, EQN, MV>(E, x, flag, 1, 0, dt, sqdt, xn, dtg);
                 TC_STAT(seg_dw += clock64() - q1;)
                 if (cheat) {
                     eq_u_true<float, DP, EQN, MV>(E, x, u, 1, 0);
                 } else {
-                    path_net_finish(P, nA, S.vecA, raw);
+                    path_net_finish(P, nA, S.vecA, raw, 2);
                     if (nA.ekn_head) ekn_head_fwd<float, DP, EQN, MV>(raw, u, nA.mctrl, 1, 0);
                     else KLOOP(j, E.m) u[j] = raw[j];
                 }
@@ -322,10 +324,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) critic_tc_kernel(const TcArgs a
                     KLOOP(k, d) __stcs(&tr[k * TC_PATHS + row], x[k]);
                 float w = 0.f;
                 if (!prop_only) w = eq_w<float, DP, EQN, MV>(E, x, u, 1, 0);
+                if (td1) path_hidden_range(P, nG, S.vecG, 0, 1);
                 const int coef = fwd_move<float, DP, EQN, MV>(E, x, u, dwv, dt, sqdt, xn, flag, sdw, 1, 0);
                 const float cf = (float)coef;
                 TC_STAT(const long long q4 = clock64(); seg_mv += q4 - q3;)
-                if (td1) path_net_finish(P, nG, S.vecG, g);
+                if (td1) path_net_finish(P, nG, S.vecG, g, 1);
                 TC_STAT(seg_G += clock64() - q4;)
                 y = y + w * disc * cf * dt;                                       // solver.py:170-174
                 if (td1) {
@@ -488,7 +491,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) actor_tc_kernel(const TcArgs a)
     const int tid = threadIdx.x, warp = tid >> 5;
     const bool is_path = R.is_path, is_ctrl = R.is_ctrl, primary = R.primary;
     const int row = R.row;
-    const Eq<float> E(a.eq);
+    const Eq<float>& E = a.eqf;                                   // kernel-parameter space: fields are constant-bank operands
     const int d = E.d, m = E.m, N = a.N, sr = a.sr;
     const bool cheat = a.flags & F_CHEAT_CONTROL, cheat_v = a.flags & F_CHEAT_VALUE;
     const bool need_grad = (a.flags & F_NEED_GRAD) && !cheat;
@@ -530,14 +533,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) actor_tc_kernel(const TcArgs a)
             if (is_ctrl) {
                 if (!cheat) ctrl_net_forward(C, nA, nA.L);
             } else if (is_path) {
-                if (!cheat) path_net_begin(P, nA, S.vecA, x);
+                if (!cheat) { path_net_begin(P, nA, S.vecA, x); path_hidden_range(P, nA, S.vecA, 0, 1); }
                 path_dw(a, gp, valid, t, dwv);
+                if (!cheat) path_hidden_range(P, nA, S.vecA, 1, 2);
                 float dt, sqdt, xn; int dtg;
                 fwd_dt<float, DP, EQN, MV>(E, x, flag, 1, 0, dt, sqdt, xn, dtg);
                 if (cheat) {
                     eq_u_true<float, DP, EQN, MV>(E, x, u, 1, 0);
                 } else {
-                    path_net_finish(P, nA, S.vecA, raw);
+                    path_net_finish(P, nA, S.vecA, raw, 2);
                     if (nA.ekn_head) ekn_head_fwd<float, DP, EQN, MV>(raw, u, nA.mctrl, 1, 0);
                     else KLOOP(j, m) u[j] = raw[j];
                 }

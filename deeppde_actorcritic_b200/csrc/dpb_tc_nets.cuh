@@ -438,9 +438,10 @@ __device__ __forceinline__ void path_last(PathCtx& p, const float* gcbb, int N16
     }
 }
 
-// all hidden-layer epilogues of a forward-only evaluation (no per-path arrays involved)
-static __device__ __noinline__ void path_hidden(PathCtx& p, const TcNet& t, const float* vec) {
-    for (int l = 0; l < t.L; ++l) path_epi_hidden(p, vec + t.ly[l].vec, t.ly[l].N16);
+// hidden-layer epilogues l0 .. l1-1 of a forward-only evaluation (no per-path arrays involved).  The caller places its
+// own per-path arithmetic between two ranges: it then runs while the tensor pipe works on the layer just published.
+static __device__ __noinline__ void path_hidden_range(PathCtx& p, const TcNet& t, const float* vec, int l0, int l1) {
+    for (int l = l0; l < l1 && l < t.L; ++l) path_epi_hidden(p, vec + t.ly[l].vec, t.ly[l].N16);
 }
 
 // forward-only evaluation:  begin (y0 -> planes)  ...caller's own arithmetic...  finish (-> raw output)
@@ -448,9 +449,10 @@ template <int NX>
 __device__ __forceinline__ void path_net_begin(PathCtx& p, const TcNet& t, const float* vec, const float (&x)[NX]) {
     path_put_y0(p, t, vec, x, nullptr, 0);
 }
+// layers `from`.. and the raw output
 template <int NO>
-__device__ __forceinline__ void path_net_finish(PathCtx& p, const TcNet& t, const float* vec, float (&out)[NO]) {
-    path_hidden(p, t, vec);
+__device__ __forceinline__ void path_net_finish(PathCtx& p, const TcNet& t, const float* vec, float (&out)[NO], int from = 0) {
+    path_hidden_range(p, t, vec, from, t.L);
     path_last(p, vec + t.ly[t.L].vec, t.ly[t.L].N16, t.ly[t.L].nl, out);
 }
 template <int NX, int NO>
