@@ -152,6 +152,11 @@ def main():
     ap.add_argument("--dtype", default="float32")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    # stdout carries exactly one JSON line: keep a private handle to it and point file descriptor 1 at stderr, so that
+    # nothing a library prints (NCCL's version banner goes to fd 1) can end up in front of the line
+    sys.stdout.flush()
+    json_out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -173,7 +178,7 @@ def main():
                 "config": config_desc, "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
                 "cpu_model": cpu_model_name(), "iters_per_sec": 1.0 / r["sec_per_iter"],
                 "e2e": {"value": r["value"], "unit": "path-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=json_out, flush=True)
         return
 
     import numpy as np
@@ -322,7 +327,7 @@ def main():
                 "scaling": "strong", "vs_baseline": None, "dtype": ("f32 (bf16x3 tensor-core products, FP32 accumulate)" if impl == "tensor" else "f32" if args.dtype == "float32" else "f64"), "data": "synthetic",
                 "config": config_desc, "impl": impl, "iters_per_sec": args.steps / (ms * 1e-3), "clocks": clocks, "e2e": e2e,
                 "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "last_losses": losses}
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=json_out, flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -1,7 +1,8 @@
 // dpb_tc_kernels.cuh -- the fused rollout + TD kernels with the MLP layers on tcgen05 (impl = tensor).
 // Same algorithm and per-path arithmetic (dpb_eqn.h) as dpb_kernels.cuh.  CTA = one tile of 128 paths = the 128
 // TMEM lanes; warps 0-7: path threads (t and t+128 own path t, state in registers, epilogue chunks split between
-// them); warp 8 lane 0: control thread (issues every tcgen05.mma); warp 9 lane 0: weight-stream producer.
+// them); warp 8: control warp (all lanes run the protocol, the elected lane issues every tcgen05.mma); warp 9 lane 0:
+// weight-stream producer.
 // Phases per tile -- critic: rollout (actor + NN_value_grad forward) -> NN_value at x_N, x_0, x_bdry (+ backward)
 // -> second sweep re-evaluating NN_value_grad at the stored x_t and back-propagating; actor: rollout -> terminal
 // value (+ input gradient) -> reverse sweep (re-evaluate the actor, adjoint step, back-propagate).
