@@ -210,13 +210,28 @@ __device__ __forceinline__ void roles_stats(const Roles& r, const TcArgs& a, lon
     TC_STAT(if (threadIdx.x == 0) { st[4] = r.P.t_accw; st[5] = r.P.t_epi; st[6] = r.P.t_hid; })
 }
 
-// sum over the 128 path threads of per-thread accumulators acc[0..n) -> atomicAdd into dst (kernel end)
-__device__ __forceinline__ void reduce_rows_to(float* dst, const float* acc, int n, bool primary) {
-    for (int k = 0; k < n; ++k) {
-        float v = primary ? acc[k] : 0.f;
+// Input-layer sums SX[k] = sum x_k dy0_k, S0[k] = sum dy0_k.  The two threads of a path split the components: group g
+// (0: threads 0..127, 1: threads 128..255) accumulates k in [g*DH, g*DH + DH), DH = DPX/2, in DH registers each (all
+// indices static -- a run-time index anywhere would put the accumulators in local memory).
+template <int DPX>
+__device__ __forceinline__ void acc_input_sums(float (&sx)[DPX / 2], float (&s0)[DPX / 2], const float (&x)[DPX], const float (&dy0)[DPX], int grp, int d) {
+    constexpr int DH = DPX / 2;
+#pragma unroll
+    for (int j = 0; j < DH; ++j) {
+        const float xs = grp ? x[DH + j] : x[j], ds = grp ? dy0[DH + j] : dy0[j];
+        if (grp * DH + j < d) { sx[j] += xs * ds; s0[j] += ds; }
+    }
+}
+// kernel end: sum over the path threads of each group -> atomicAdd into dst[g*DH + j]
+template <int DH>
+__device__ __forceinline__ void reduce_rows_to(float* dst, const float (&acc)[DH], int d, int grp, bool is_path) {
+#pragma unroll
+    for (int j = 0; j < DH; ++j) {
+        float v = is_path ? acc[j] : 0.f;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        if (primary && (threadIdx.x & 31) == 0) atomicAdd(dst + k, v);
+        const int k = grp * DH + j;
+        if (is_path && k < d && (threadIdx.x & 31) == 0) atomicAdd(dst + k, v);
     }
 }
 
@@ -263,8 +278,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) critic_tc_kernel(const TcArgs a
     unsigned char* copies = a.copies ? a.copies + (size_t)blockIdx.x * a.copies_per_cta : nullptr;
     float* gsV = a.slabV ? a.slabV + (size_t)(blockIdx.x % a.nslab) * gV.gtotal : nullptr;
     float* gsG = a.slabG ? a.slabG + (size_t)(blockIdx.x % a.nslab) * gG.gtotal : nullptr;
-    float sxV[DPX], s0V[DPX], sxG[DPX], s0G[DPX];
-    KLOOP(k, DPX) { sxV[k] = 0.f; s0V[k] = 0.f; sxG[k] = 0.f; s0G[k] = 0.f; }
+    float sxV[DPX / 2], s0V[DPX / 2], sxG[DPX / 2], s0G[DPX / 2];
+#pragma unroll
+    for (int k = 0; k < DPX / 2; ++k) { sxV[k] = 0.f; s0V[k] = 0.f; sxG[k] = 0.f; s0G[k] = 0.f; }
 
     float loss0 = 0.f, loss1 = 0.f;
     TC_STAT(long long ph_roll = 0, ph_val = 0, ph_grad = 0;)          // cycles per phase (diagnostics)
@@ -394,16 +410,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) critic_tc_kernel(const TcArgs a
                 rhog = valid ? rho_grad(delta, 50.f) * scale : 0.f;
                 cot[0] = -rhog * disc;
                 path_net_backward(P, nV, gV, mk, cot, true, gsV, S.dz, row, dy0);
-                KLOOP(k, d) { sxV[k] += x[k] * dy0[k]; s0V[k] += dy0[k]; }
+                acc_input_sums<DPX>(sxV, s0V, x, dy0, P.grp, d);
                 path_net_forward_keep(P, nV, S.vecV, x0v, v0, mk, copies, S.act, row, false);
                 cot[0] = rhog;
                 path_net_backward(P, nV, gV, mk, cot, true, gsV, S.dz, row, dy0);
-                KLOOP(k, d) { sxV[k] += x0v[k] * dy0[k]; s0V[k] += dy0[k]; }
+                acc_input_sums<DPX>(sxV, s0V, x0v, dy0, P.grp, d);
                 path_net_forward_keep(P, nV, S.vecV, xbv, vb, mk, copies, S.act, row, false);
                 const float dbb = vb[0] - eq_Z<float, DP, EQN, MV>(E, xbv, 1, 0);
                 cot[0] = valid ? rho_grad(dbb, 50.f) * scale : 0.f;
                 path_net_backward(P, nV, gV, mk, cot, true, gsV, S.dz, row, dy0);
-                KLOOP(k, d) { sxV[k] += xbv[k] * dy0[k]; s0V[k] += dy0[k]; }
+                acc_input_sums<DPX>(sxV, s0V, xbv, dy0, P.grp, d);
             }
             const float delta = v0[0] - y - vN[0] * disc;                         // solver.py:189
             const float db = vb[0] - eq_Z<float, DP, EQN, MV>(E, xbv, 1, 0);                          // solver.py:190
@@ -437,7 +453,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) critic_tc_kernel(const TcArgs a
                     float unused[1];
                     path_net_forward_keep(P, nG, S.vecG, xt, unused, mk, copies, S.act, row, true);
                     path_net_backward(P, nG, gG, mk, cot, true, gsG, S.dz, row, dy0);
-                    KLOOP(k, d) { sxG[k] += xt[k] * dy0[k]; s0G[k] += dy0[k]; }
+                    acc_input_sums<DPX>(sxG, s0G, xt, dy0, P.grp, d);
                 }
             }
         }
@@ -446,11 +462,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) critic_tc_kernel(const TcArgs a
     TC_STAT(if (a.stats && tid == 0) { long long* st = a.stats + (size_t)blockIdx.x * 16; st[9] = ph_roll; st[10] = ph_val; st[11] = ph_grad; st[12] = seg_dw; st[13] = seg_A; st[14] = seg_mv; st[15] = seg_G; })
     if (is_ctrl) { ctrl_flush(C); C.pc->quit = 1; }
     if (need_grad) {
-        reduce_rows_to(gsV + gV.gX, sxV, d, primary);
-        reduce_rows_to(gsV + gV.g0, s0V, d, primary);
+        reduce_rows_to(gsV + gV.gX, sxV, d, P.grp, is_path);
+        reduce_rows_to(gsV + gV.g0, s0V, d, P.grp, is_path);
         if (td1) {
-            reduce_rows_to(gsG + gG.gX, sxG, d, primary);
-            reduce_rows_to(gsG + gG.g0, s0G, d, primary);
+            reduce_rows_to(gsG + gG.gX, sxG, d, P.grp, is_path);
+            reduce_rows_to(gsG + gG.g0, s0G, d, P.grp, is_path);
         }
     }
     if (tid == 0 && a.loss_part) {
@@ -501,8 +517,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) actor_tc_kernel(const TcArgs a)
     float* traj = a.scratch + (size_t)blockIdx.x * a.scratch_per_cta;               // [N][2*sr + A_NSCAL][128]
     unsigned char* copies = a.copies ? a.copies + (size_t)blockIdx.x * a.copies_per_cta : nullptr;
     float* gsA = a.slabA ? a.slabA + (size_t)(blockIdx.x % a.nslab) * gA.gtotal : nullptr;
-    float sxA[DPX], s0A[DPX];
-    KLOOP(k, DPX) { sxA[k] = 0.f; s0A[k] = 0.f; }
+    float sxA[DPX / 2], s0A[DPX / 2];
+#pragma unroll
+    for (int k = 0; k < DPX / 2; ++k) { sxA[k] = 0.f; s0A[k] = 0.f; }
 
     float loss0 = 0.f;
     const long long ntiles = (a.B_local + TC_PATHS - 1) / TC_PATHS;
@@ -652,17 +669,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) actor_tc_kernel(const TcArgs a)
                 }
                 path_net_backward(P, nA, gA, mk, cot, true, gsA, S.dz, row, dy0);
                 const float* g0c = S.vecA + nA.vec_g0;
-                KLOOP(k, d) {
-                    sxA[k] += xt[k] * dy0[k]; s0A[k] += dy0[k];
-                    lam[k] = lam[k] + dy0[k] * g0c[k];
-                }
+                acc_input_sums<DPX>(sxA, s0A, xt, dy0, P.grp, d);
+                KLOOP(k, d) lam[k] = lam[k] + dy0[k] * g0c[k];
             }
         }
     }
     if (is_ctrl) { ctrl_flush(C); C.pc->quit = 1; }
     if (need_grad) {
-        reduce_rows_to(gsA + gA.gX, sxA, d, primary);
-        reduce_rows_to(gsA + gA.g0, s0A, d, primary);
+        reduce_rows_to(gsA + gA.gX, sxA, d, P.grp, is_path);
+        reduce_rows_to(gsA + gA.g0, s0A, d, P.grp, is_path);
     }
     if (tid == 0 && a.loss_part) {
         a.loss_part[blockIdx.x * 2] = loss0;
