@@ -396,7 +396,7 @@ __device__ __forceinline__ void path_put_y0(PathCtx& p, const TcNet& t, const fl
             if (copies) copy16h(copies, row, c, h, t.ly[0].kl);
         }
     }
-    if (copies) fence_proxy_async_all();
+    if (copies) fence_proxy_async_global();
     path_publish(p);
 }
 
@@ -604,7 +604,10 @@ static __device__ __noinline__ void path_hidden_keep(PathCtx& p, const TcNet& t,
             put16h(p.tl, c, v, h);
             if (dst) copy16h(dst, row, c, h, one_at);
         });
-        if (dst) fence_proxy_async_all();
+        if (dst) {
+            if (last_hidden) fence_proxy_async();                    // shared ACT image
+            else fence_proxy_async_global();                         // global copy scratch
+        }
         if (!(last_hidden && skip_last)) path_publish(p);
     }
 }
