@@ -100,7 +100,7 @@ static Layout make_layout(const dpb_handle* h, long long B_local, int N) {
         if (tc::tc_copy_bytes(h->tG) > cb) cb = tc::tc_copy_bytes(h->tG);
         L.copies_per_cta = (long long)a256((size_t)cb);
         L.copies = o; o += a256((size_t)L.grid * L.copies_per_cta);
-        L.stats = o; o += a256((size_t)L.grid * 16 * 8);
+        L.stats = o; o += a256((size_t)L.grid * 16 * 8 + 64);           // + the tile counter of the dynamic tile scheduler
     }
     const long long gc = tensor ? h->sV.gtotal + h->sG.gtotal : h->nV.gtotal + h->nG.gtotal, ga = tensor ? h->sA.gtotal : h->nA.gtotal;
     const long long gmax = gc > ga ? gc : ga;
@@ -420,6 +420,7 @@ static void tc_fill(dpb_handle* h, tc::TcArgs& a, const Layout& L, char* ws, con
     a.copies = (unsigned char*)(ws + L.copies);
     a.copies_per_cta = L.copies_per_cta;
     a.stats = (long long*)(ws + L.stats);
+    a.tile_counter = (int*)(ws + L.stats + (size_t)L.grid * 16 * 8);
     a.nslab = L.nslab;
     a.sr = h->sr;
     if (outs) {
@@ -477,6 +478,7 @@ static int critic_step_tc(dpb_handle* h, const void* thA, const void* thV, const
         }
     }
     DPB_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    DPB_CUDA(h, cudaMemsetAsync(a.tile_counter, 0, sizeof(int), st));
     ev_begin(h, st);
     kern<<<L.grid, tc::TC_THREADS, smem, st>>>(a);
     ev_end(h, st);
@@ -531,6 +533,7 @@ static int actor_step_tc(dpb_handle* h, const void* thA, const void* thV, const 
         }
     }
     DPB_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    DPB_CUDA(h, cudaMemsetAsync(a.tile_counter, 0, sizeof(int), st));
     ev_begin(h, st);
     kern<<<L.grid, tc::TC_THREADS, smem, st>>>(a);
     ev_end(h, st);

@@ -38,6 +38,7 @@ struct TcArgs {
     float *o_x, *o_dt, *o_coef, *o_delta, *o_delta_b;
     int* o_exit;
     long long* stats;               // [grid][16] cycle counters (diagnostics), may be NULL
+    int* tile_counter;              // zeroed before the launch: CTAs take tile blockIdx.x first, then gridDim.x + counter++
 };
 
 // the kernels are instantiated in their own translation units (dpb_tc_inst_*.cu)
@@ -52,6 +53,7 @@ struct TcSmem {
     float *vecA, *vecV, *vecG;
     uint64_t *full, *empty, *acc_full, *a_ready, *act_full;
     uint32_t* tslot;
+    int* tile;                       // the tile a CTA works on next (dynamic tile scheduler)
     Sched* sch;
     ProdCtl* pc;
     float* red;
@@ -81,7 +83,7 @@ __device__ __forceinline__ void tc_carve(TcSmem& s, unsigned char* base, const T
     s.acc_full = reinterpret_cast<uint64_t*>(p); p += 8;
     s.a_ready = reinterpret_cast<uint64_t*>(p); p += 8;
     s.act_full = reinterpret_cast<uint64_t*>(p); p += 8;
-    s.tslot = reinterpret_cast<uint32_t*>(p); p += 64;
+    s.tslot = reinterpret_cast<uint32_t*>(p); s.tile = reinterpret_cast<int*>(p) + 4; p += 64;
     s.sch = reinterpret_cast<Sched*>(p); p += sizeof(Sched);
     s.pc = reinterpret_cast<ProdCtl*>(p); p += 64;
     s.red = reinterpret_cast<float*>(((uintptr_t)p + 15) & ~(uintptr_t)15);
@@ -130,6 +132,15 @@ __device__ __forceinline__ float tc_block_sum(float v, float* red) {
     if (threadIdx.x == 0)
         for (int i = 0; i < TC_WORK_THREADS / 32; ++i) s += red[i];
     return s;
+}
+
+// next tile of this CTA (all work threads call it): tiles are handed out through a global counter, so a CTA whose tiles
+// ended early (every path of a tile can leave the domain before step N) takes more of them
+__device__ __forceinline__ long long tc_next_tile(const TcSmem& S, const TcArgs& a) {
+    bar_work_sync(TC_WORK_THREADS);
+    if (threadIdx.x == 0) *S.tile = (int)gridDim.x + atomicAdd(a.tile_counter, 1);
+    bar_work_sync(TC_WORK_THREADS);
+    return *S.tile;
 }
 
 // loop over the first n (<= DPX) components with static indices
@@ -286,7 +297,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) critic_tc_kernel(const TcArgs a
     TC_STAT(long long ph_roll = 0, ph_val = 0, ph_grad = 0;)          // cycles per phase (diagnostics)
     TC_STAT(long long seg_dw = 0, seg_A = 0, seg_mv = 0, seg_G = 0;)
     const long long ntiles = (a.B_local + TC_PATHS - 1) / TC_PATHS;
-    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    for (long long tile = blockIdx.x; tile < ntiles; tile = tc_next_tile(S, a)) {
         const long long base = tile * TC_PATHS;
         const long long gp = base + row;                          // local path index of this thread
         const bool valid = is_path && gp < a.B_local;
@@ -523,7 +534,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) actor_tc_kernel(const TcArgs a)
 
     float loss0 = 0.f;
     const long long ntiles = (a.B_local + TC_PATHS - 1) / TC_PATHS;
-    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    for (long long tile = blockIdx.x; tile < ntiles; tile = tc_next_tile(S, a)) {
         const long long base = tile * TC_PATHS;
         const long long gp = base + row;
         const bool valid = is_path && gp < a.B_local;
