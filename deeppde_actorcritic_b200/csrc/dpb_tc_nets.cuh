@@ -627,7 +627,10 @@ __device__ __forceinline__ void path_drain(PathCtx& p, int blk, int row, int kl,
     float* dst = slab + (long long)f * 4;
     const long long gstride = (long long)(kl + 1) * 4;                  // next column group
     const bool rowok = f <= kl;
-    for (int c = p.grp; c < N16 / 16; c += 2) {
+    // a warp whose 32 rows all lie past the last feature row skips its TMEM loads altogether (the TMEM->register path
+    // is the bound of the drain): block 1 of a 200-wide layer has 73 live rows, the input layer's block 21
+    const bool warp_live = (128 * blk + (row & ~31)) <= kl;
+    for (int c = p.grp; warp_live && c < N16 / 16; c += 2) {
         uint32_t r[16];
         tmem_ld16(p.tl + COL_ACC + 16 * c, r);
         tmem_ld_wait();
