@@ -399,6 +399,8 @@ static int tc_ring(dpb_handle* h, tc::TcArgs& a, bool grads) {
     if (fixed + 4 * (size_t)a.slot_bytes > avail) return fail(h, DPB_ERR_ARG, "tensor path: networks too wide for the shared-memory operand images");
     size_t ns = (avail - fixed) / a.slot_bytes;
     a.nslot = (int)(ns > tc::MAX_NSLOT ? tc::MAX_NSLOT : ns);
+    // experiment knob: fewer ring slots leave more of the 256 KB unified array to L1 (local-memory traffic of the path threads)
+    if (const char* e = getenv("DPB_TC_NSLOT")) { const int v = atoi(e); if (v >= 2 && v < a.nslot) a.nslot = v; }
     return DPB_OK;
 }
 
@@ -478,9 +480,12 @@ static int critic_step_tc(dpb_handle* h, const void* thA, const void* thV, const
         }
     }
     DPB_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    DPB_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, (int)((smem + 1024) * 100 / (228 * 1024) + 1 > 100 ? 100 : (smem + 1024) * 100 / (228 * 1024) + 1)));
     DPB_CUDA(h, cudaMemsetAsync(a.tile_counter, 0, sizeof(int), st));
     ev_begin(h, st);
-    kern<<<L.grid, tc::TC_THREADS, smem, st>>>(a);
+    cudaFuncAttributes fa;                                       // threads per CTA = the launch bound of the instantiation
+    DPB_CUDA(h, cudaFuncGetAttributes(&fa, kern));               // (its translation unit chooses the number of path-thread groups)
+    kern<<<L.grid, fa.maxThreadsPerBlock, smem, st>>>(a);
     ev_end(h, st);
     h->launches++;
     DPB_CUDA(h, cudaGetLastError());
@@ -533,9 +538,12 @@ static int actor_step_tc(dpb_handle* h, const void* thA, const void* thV, const 
         }
     }
     DPB_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    DPB_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, (int)((smem + 1024) * 100 / (228 * 1024) + 1 > 100 ? 100 : (smem + 1024) * 100 / (228 * 1024) + 1)));
     DPB_CUDA(h, cudaMemsetAsync(a.tile_counter, 0, sizeof(int), st));
     ev_begin(h, st);
-    kern<<<L.grid, tc::TC_THREADS, smem, st>>>(a);
+    cudaFuncAttributes fa;                                       // threads per CTA = the launch bound of the instantiation
+    DPB_CUDA(h, cudaFuncGetAttributes(&fa, kern));               // (its translation unit chooses the number of path-thread groups)
+    kern<<<L.grid, fa.maxThreadsPerBlock, smem, st>>>(a);
     ev_end(h, st);
     h->launches++;
     DPB_CUDA(h, cudaGetLastError());

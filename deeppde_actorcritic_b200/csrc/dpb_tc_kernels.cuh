@@ -202,10 +202,10 @@ __device__ __forceinline__ void roles_init(Roles& r, const TcSmem& S, const TcAr
     C.pc = S.pc; C.n_req = 0; C.n_consumed = 0; C.op_count = 0; C.tmem = warp_uniform(tmem); C.gen = 0;
     C.act_full = S.act_full; C.act_count = 0; C.nslot = a.nslot; C.slot_bytes = a.slot_bytes; C.act = S.act; C.dz = S.dz;
     r.P.tl = tmem + ((uint32_t)((warp & 3) * 32) << 16);
-    r.P.grp = (warp >> 2) & 1;
+    r.P.grp = (warp >> 2) % TC_NGRP;
     r.P.acc_full = smem_u32(S.acc_full); r.P.a_ready = smem_u32(S.a_ready); r.P.op_count = 0;
-    TC_STAT(r.P.t_accw = 0; r.P.t_epi = 0; r.P.t_hid = 0; r.P.t_mark = clock64();)
-    TC_STAT(C.t_aready = 0; C.t_issue = 0; C.t_accw = 0;)
+    TC_STAT(r.P.t_accw = 0; r.P.t_epi = 0; r.P.t_hid = 0; r.P.t_drain = 0; r.P.t_mark = clock64();)
+    TC_STAT(C.t_aready = 0; C.t_issue = 0; C.t_accw = 0; C.t_dw_ready = 0; C.t_act = 0;)
     C.n_ops = 0;
     C.mm_slot = 0; C.mm_use = 0;
 }
@@ -216,7 +216,7 @@ __device__ __forceinline__ void roles_stats(const Roles& r, const TcArgs& a, lon
     long long* st = a.stats + (size_t)blockIdx.x * 16;
     if (r.is_ctrl && (threadIdx.x & 31) == 0) {
         st[0] = clock64() - t_start; st[3] = r.C.n_ops;
-        TC_STAT(st[1] = r.C.t_aready; st[2] = 0; st[7] = r.C.t_issue; st[8] = r.C.t_accw;)
+        TC_STAT(st[1] = r.C.t_aready; st[2] = r.C.t_dw_ready; st[7] = r.C.t_issue; st[8] = r.C.t_accw;)
     }
     TC_STAT(if (threadIdx.x == 0) { st[4] = r.P.t_accw; st[5] = r.P.t_epi; st[6] = r.P.t_hid; })
 }
@@ -225,11 +225,11 @@ __device__ __forceinline__ void roles_stats(const Roles& r, const TcArgs& a, lon
 // (0: threads 0..127, 1: threads 128..255) accumulates k in [g*DH, g*DH + DH), DH = DPX/2, in DH registers each (all
 // indices static -- a run-time index anywhere would put the accumulators in local memory).
 template <int DPX>
-__device__ __forceinline__ void acc_input_sums(float (&sx)[DPX / 2], float (&s0)[DPX / 2], const float (&x)[DPX], const float (&dy0)[DPX], int grp, int d) {
-    constexpr int DH = DPX / 2;
+__device__ __forceinline__ void acc_input_sums(float (&sx)[DPX / TC_NGRP], float (&s0)[DPX / TC_NGRP], const float (&x)[DPX], const float (&dy0)[DPX], int grp, int d) {
+    constexpr int DH = DPX / TC_NGRP;
 #pragma unroll
     for (int j = 0; j < DH; ++j) {
-        const float xs = grp ? x[DH + j] : x[j], ds = grp ? dy0[DH + j] : dy0[j];
+        const float xs = (TC_NGRP > 1 && grp) ? x[(DH + j) % DPX] : x[j], ds = (TC_NGRP > 1 && grp) ? dy0[(DH + j) % DPX] : dy0[j];
         if (grp * DH + j < d) { sx[j] += xs * ds; s0[j] += ds; }
     }
 }
@@ -289,9 +289,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) critic_tc_kernel(const TcArgs a
     unsigned char* copies = a.copies ? a.copies + (size_t)blockIdx.x * a.copies_per_cta : nullptr;
     float* gsV = a.slabV ? a.slabV + (size_t)(blockIdx.x % a.nslab) * gV.gtotal : nullptr;
     float* gsG = a.slabG ? a.slabG + (size_t)(blockIdx.x % a.nslab) * gG.gtotal : nullptr;
-    float sxV[DPX / 2], s0V[DPX / 2], sxG[DPX / 2], s0G[DPX / 2];
+    float sxV[DPX / TC_NGRP], s0V[DPX / TC_NGRP], sxG[DPX / TC_NGRP], s0G[DPX / TC_NGRP];
 #pragma unroll
-    for (int k = 0; k < DPX / 2; ++k) { sxV[k] = 0.f; s0V[k] = 0.f; sxG[k] = 0.f; s0G[k] = 0.f; }
+    for (int k = 0; k < DPX / TC_NGRP; ++k) { sxV[k] = 0.f; s0V[k] = 0.f; sxG[k] = 0.f; s0G[k] = 0.f; }
 
     float loss0 = 0.f, loss1 = 0.f;
     TC_STAT(long long ph_roll = 0, ph_val = 0, ph_grad = 0;)          // cycles per phase (diagnostics)
@@ -329,15 +329,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) critic_tc_kernel(const TcArgs a
                 if (td1) ctrl_net_forward(C, nG, nG.L);
             } else if (is_path) {
                 // per-path arithmetic is placed where the tensor pipe is busy with a first layer
-                TC_STAT(const long long q0 = clock64();)
-                // (the increments and the step size are computed while the tensor pipe works on the two wide layers)
                 if (!cheat) { path_net_begin(P, nA, S.vecA, x); path_hidden_range(P, nA, S.vecA, 0, 1); }
                 TC_STAT(const long long q1 = clock64();)
                 path_dw(a, gp, valid, t, dwv);
+                TC_STAT(const long long q1b = clock64(); seg_dw += q1b - q1;)
                 if (!cheat) path_hidden_range(P, nA, S.vecA, 1, 2);
                 float dt, sqdt, xn; int dtg;
+                TC_STAT(const long long q2 = clock64();)
                 fwd_dt<float, DP, EQN, MV>(E, x, flag, 1, 0, dt, sqdt, xn, dtg);
-                TC_STAT(seg_dw += clock64() - q1;)
+                TC_STAT(seg_A += clock64() - q2;)
                 if (cheat) {
                     eq_u_true<float, DP, EQN, MV>(E, x, u, 1, 0);
                 } else {
@@ -345,19 +345,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) critic_tc_kernel(const TcArgs a
                     if (nA.ekn_head) ekn_head_fwd<float, DP, EQN, MV>(raw, u, nA.mctrl, 1, 0);
                     else KLOOP(j, E.m) u[j] = raw[j];
                 }
-                TC_STAT(const long long q3 = clock64(); seg_A += q3 - q0;)
                 if (td1) path_net_begin(P, nG, S.vecG, x);                        // NN_value_grad at x_t (before the move)
+                TC_STAT(const long long q3 = clock64();)
                 float* tr = traj + (size_t)t * 2 * sr * TC_PATHS;
                 if (need_grad && td1 && primary)
                     KLOOP(k, d) __stcs(&tr[k * TC_PATHS + row], x[k]);
                 float w = 0.f;
                 if (!prop_only) w = eq_w<float, DP, EQN, MV>(E, x, u, 1, 0);
+                TC_STAT(const long long q3b = clock64(); seg_mv += q3b - q3;)
                 if (td1) path_hidden_range(P, nG, S.vecG, 0, 1);
+                TC_STAT(const long long q3c = clock64();)
                 const int coef = fwd_move<float, DP, EQN, MV>(E, x, u, dwv, dt, sqdt, xn, flag, sdw, 1, 0);
                 const float cf = (float)coef;
-                TC_STAT(const long long q4 = clock64(); seg_mv += q4 - q3;)
+                TC_STAT(const long long q4 = clock64(); seg_mv += q4 - q3c;)
                 if (td1) path_net_finish(P, nG, S.vecG, g, 1);
-                TC_STAT(seg_G += clock64() - q4;)
+                TC_STAT(const long long q5 = clock64();)
                 y = y + w * disc * cf * dt;                                       // solver.py:170-174
                 if (td1) {
                     float dif = 0.f;
@@ -370,6 +372,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) critic_tc_kernel(const TcArgs a
                     }
                 }
                 disc = disc * expf(-E.gamma * dt * cf);                          // solver.py:187
+                TC_STAT(seg_G += clock64() - q5;)
                 nacc += coef;
                 if (wr) {
                     if (a.o_dt) a.o_dt[gp * N + t] = dt;
@@ -528,16 +531,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) actor_tc_kernel(const TcArgs a)
     float* traj = a.scratch + (size_t)blockIdx.x * a.scratch_per_cta;               // [N][2*sr + A_NSCAL][128]
     unsigned char* copies = a.copies ? a.copies + (size_t)blockIdx.x * a.copies_per_cta : nullptr;
     float* gsA = a.slabA ? a.slabA + (size_t)(blockIdx.x % a.nslab) * gA.gtotal : nullptr;
-    float sxA[DPX / 2], s0A[DPX / 2];
+    float sxA[DPX / TC_NGRP], s0A[DPX / TC_NGRP];
 #pragma unroll
-    for (int k = 0; k < DPX / 2; ++k) { sxA[k] = 0.f; s0A[k] = 0.f; }
+    for (int k = 0; k < DPX / TC_NGRP; ++k) { sxA[k] = 0.f; s0A[k] = 0.f; }
 
     float loss0 = 0.f;
+    TC_STAT(long long seg_fk = 0, seg_adj = 0, seg_bwd = 0, seg_fwd = 0;)   // reverse step: forward_keep / adjoint step / backward; forward rollout
     const long long ntiles = (a.B_local + TC_PATHS - 1) / TC_PATHS;
     for (long long tile = blockIdx.x; tile < ntiles; tile = tc_next_tile(S, a)) {
         const long long base = tile * TC_PATHS;
         const long long gp = base + row;
         const bool valid = is_path && gp < a.B_local;
+        TC_STAT(const long long f0 = clock64();)
         const bool wr = valid && primary;               // this thread does the global stores of its path
         float x[DPX], u[DPX], dwv[DPX], raw[DPX];
         int flag = 0, nacc = 0;
@@ -605,6 +610,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) actor_tc_kernel(const TcArgs a)
             }
             if (a.o_exit) a.o_exit[gp] = nacc;
         }
+        TC_STAT(seg_fwd += clock64() - f0;)
         // ------------------------------------------------------------------ terminal value (+ its input gradient)
         float yv = 0.f;
         float lam[DPX];
@@ -665,8 +671,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) actor_tc_kernel(const TcArgs a)
             } else if (is_path) {
                 Masks mk;
                 float xt[DPX], ubar[DPX], cot[DPX], dy0[DPX];
+                TC_STAT(const long long r0 = clock64();)
                 KLOOP(k, d) { xt[k] = __ldcs(&tr[k * TC_PATHS + row]); dwv[k] = __ldcs(&tr[(sr + k) * TC_PATHS + row]); }
                 path_net_forward_keep(P, nA, S.vecA, xt, raw, mk, copies, S.act, row, false);
+                TC_STAT(const long long r1 = clock64(); seg_fk += r1 - r0;)
                 if (nA.ekn_head) ekn_head_fwd<float, DP, EQN, MV>(raw, u, nA.mctrl, 1, 0);
                 else KLOOP(j, m) u[j] = raw[j];
                 const int coef = (valid && sc[A_COEF * TC_PATHS + row] > 0.f) ? 1 : 0;
@@ -678,7 +686,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) actor_tc_kernel(const TcArgs a)
                 } else {
                     KLOOP(j, m) cot[j] = ubar[j];
                 }
+                TC_STAT(const long long r2 = clock64(); seg_adj += r2 - r1;)
                 path_net_backward(P, nA, gA, mk, cot, true, gsA, S.dz, row, dy0);
+                TC_STAT(seg_bwd += clock64() - r2;)
                 const float* g0c = S.vecA + nA.vec_g0;
                 acc_input_sums<DPX>(sxA, s0A, xt, dy0, P.grp, d);
                 KLOOP(k, d) lam[k] = lam[k] + dy0[k] * g0c[k];
@@ -695,6 +705,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) actor_tc_kernel(const TcArgs a)
         a.loss_part[blockIdx.x * 2 + 1] = 0.f;
     }
     roles_stats(R, a, t_start);
+    TC_STAT(if (a.stats) { long long* st = a.stats + (size_t)blockIdx.x * 16;
+                           if (is_ctrl && (tid & 31) == 0) st[9] = C.t_act;
+                           if (tid == 0) { st[11] = P.t_drain; st[12] = seg_fwd; st[13] = seg_fk; st[14] = seg_adj; st[15] = seg_bwd; } })
     tc_fence_before();
     __syncthreads();
     if (warp == TC_CTRL_WARP) tmem_dealloc(tmem, 512);

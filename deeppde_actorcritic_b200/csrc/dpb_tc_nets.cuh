@@ -27,12 +27,17 @@ namespace dpb {
 namespace tc {
 
 constexpr int TC_PATHS = 128;
-constexpr int TC_PATH_THREADS = 256;            // two groups of 4 path warps: thread t and t+128 own the same path (TMEM lane)
-                                                // and split the 16-column chunks of every epilogue between them
-constexpr int TC_CTRL_WARP = 8;                 // lane 0: waits for operands, issues every tcgen05.mma
-constexpr int TC_PROD_WARP = 9;                 // lane 0: streams the weight chunks (bulk copies) on its own
-constexpr int TC_WORK_THREADS = 288;            // warps 0..8 take part in the in-loop CTA barriers (named barrier 1)
-constexpr int TC_THREADS = 320;
+#ifndef DPB_TC_NGRP
+#define DPB_TC_NGRP 2
+#endif
+constexpr int TC_NGRP = DPB_TC_NGRP;            // groups of 4 path warps.  2: thread t and t+128 own the same path (TMEM lane)
+                                                // and split the 16-column chunks of every epilogue between them (168 registers
+                                                // per thread); 1: one thread per path (255 registers, no duplicated per-path work)
+constexpr int TC_PATH_THREADS = 128 * TC_NGRP;
+constexpr int TC_CTRL_WARP = 4 * TC_NGRP;       // waits for operands, issues every tcgen05.mma
+constexpr int TC_PROD_WARP = TC_CTRL_WARP + 1;  // lane 0: streams the weight chunks (bulk copies) on its own
+constexpr int TC_WORK_THREADS = 32 * (TC_CTRL_WARP + 1);   // path + control warps take part in the in-loop CTA barriers (named barrier 1)
+constexpr int TC_THREADS = TC_WORK_THREADS + 32;
 constexpr int MAX_NSLOT = 16;                   // ring slots (runtime count: whatever shared memory is left)
 constexpr uint32_t COL_ACC = 0, COL_AHI = 256, COL_ALO = 384;
 constexpr int MAXOPS = 40;
@@ -166,6 +171,7 @@ struct Ctrl {
     unsigned char *act, *dz;         // shared-memory operand images of the dW products (128 paths x K16 features, bf16)
     long long n_ops;
     TC_STAT(long long t_aready, t_issue, t_accw;)   // cycle counters (diagnostics)
+    TC_STAT(long long t_dw_ready, t_act;)           // dW products: waiting for their operands / for the ACT bulk copy
 };
 
 // let the producer run up to nslot chunks ahead of the MMAs (one shared-memory store, never waits)
@@ -288,6 +294,7 @@ struct PathCtx {
     int grp;                       // 0: threads 0..127, 1: threads 128..255 (chunk parity this thread handles)
     TC_STAT(long long t_accw, t_mark;)      // cycles spent waiting for the tensor pipe; time of the last wake-up
     TC_STAT(long long t_epi, t_hid;)        // t_hid: cycles inside hidden-layer epilogues only
+    TC_STAT(long long t_drain;)             // cycles inside the dW drains (after the accumulator wait)
 };
 
 // A planes written and accumulator drained: one arrival per path warp (a_ready counts the 8 path warps)
@@ -341,7 +348,7 @@ __device__ __forceinline__ void for_acc_chunks(uint32_t tl, int first, int nchun
     // (the TMEM->register path is the bound of every epilogue -- 64 B/clk/SM, see DESIGN.md -- so a plain loop does as
     //  well as a software-pipelined one and needs 16 registers fewer)
     uint32_t ra[16];
-    for (int c = first; c < nchunks; c += 2) {
+    for (int c = first; c < nchunks; c += TC_NGRP) {
         tmem_ld16(tl + COL_ACC + 16 * c, ra);
         tmem_ld_wait();
         f(c, ra);
@@ -384,7 +391,7 @@ __device__ __forceinline__ void path_put_y0(PathCtx& p, const TcNet& t, const fl
     const float* b0 = g0c + K0;
 #pragma unroll
     for (int c = 0; c < 2; ++c) {
-        if (c < K0 / 16 && (c & 1) == p.grp) {
+        if (c < K0 / 16 && (c % TC_NGRP) == p.grp) {
             float v[16];
             uint32_t h[8];
 #pragma unroll
@@ -530,7 +537,9 @@ __device__ __forceinline__ void ctrl_act_load(Ctrl& c, const unsigned char* src,
     }
 }
 __device__ __forceinline__ void ctrl_act_wait(Ctrl& c) {
+    TC_STAT(const long long t0 = clock64();)
     mbar_wait(c.act_full, c.act_count & 1);
+    TC_STAT(c.t_act += clock64() - t0;)
     ++c.act_count;
 }
 
@@ -538,7 +547,9 @@ __device__ __forceinline__ void ctrl_act_wait(Ctrl& c) {
 __device__ __forceinline__ void ctrl_gemm_dw(Ctrl& c, int blk_, int N16_) {
     const int blk = (int)warp_uniform((uint32_t)blk_), N16 = (int)warp_uniform((uint32_t)N16_);
     const uint32_t idesc = idesc_bf16(128, N16, 1, 1);
+    TC_STAT(const long long t0 = clock64();)
     mbar_wait(c.a_ready, c.op_count & 1);
+    TC_STAT(c.t_dw_ready += clock64() - t0;)
     tc_fence_after();
     const uint32_t a0 = warp_uniform(smem_u32(c.act)) + blk * 16 * 2048, b0 = warp_uniform(smem_u32(c.dz));
     const uint32_t tmem = warp_uniform(c.tmem), accf = warp_uniform(smem_u32(c.acc_full));
@@ -562,7 +573,9 @@ static __device__ __noinline__ void ctrl_net_backward(Ctrl& c, const TcNet& t, b
             const int nblk = (t.ly[l].kl + 1 + 127) >> 7;
             for (int b = 0; b < nblk; ++b) ctrl_gemm_dw(c, b, t.ly[l].N16);
             if (l > 0) {
+                TC_STAT(const long long t0 = clock64();)
                 mbar_wait(c.acc_full, (c.op_count - 1) & 1);           // the MMAs reading ACT are done
+                TC_STAT(c.t_accw += clock64() - t0;)
                 ctrl_act_load(c, copies + tc_copy_off(t, l - 1), (uint32_t)(TC_PATHS * t.ly[l - 1].K16 * 2));
             }
         }
@@ -623,6 +636,7 @@ __device__ __forceinline__ void path_net_forward_keep(PathCtx& p, const TcNet& t
 // this thread's row of a dW block -> RED into the slab:  rows f = 128*blk + row (f <= kl), cols n < nl
 __device__ __forceinline__ void path_drain(PathCtx& p, int blk, int row, int kl, int nl, int N16, float* slab) {
     path_wait_acc(p);
+    TC_STAT(const long long td0 = clock64();)
     const int f = 128 * blk + row;
     float* dst = slab + (long long)f * 4;
     const long long gstride = (long long)(kl + 1) * 4;                  // next column group
@@ -630,7 +644,7 @@ __device__ __forceinline__ void path_drain(PathCtx& p, int blk, int row, int kl,
     // a warp whose 32 rows all lie past the last feature row skips its TMEM loads altogether (the TMEM->register path
     // is the bound of the drain): block 1 of a 200-wide layer has 73 live rows, the input layer's block 21
     const bool warp_live = (128 * blk + (row & ~31)) <= kl;
-    for (int c = p.grp; warp_live && c < N16 / 16; c += 2) {
+    for (int c = p.grp; warp_live && c < N16 / 16; c += TC_NGRP) {
         uint32_t r[16];
         tmem_ld16(p.tl + COL_ACC + 16 * c, r);
         tmem_ld_wait();
@@ -644,6 +658,7 @@ __device__ __forceinline__ void path_drain(PathCtx& p, int blk, int row, int kl,
     tc_fence_before();
     __syncwarp();
     if ((threadIdx.x & 31) == 0) mbar_arrive_u32(p.a_ready);   // accumulator drained
+    TC_STAT(p.t_drain += clock64() - td0;)
 }
 
 // cotangent of the raw output (nl <= 32 values, static indexing) -> planes (+ DZ image), publish
@@ -652,7 +667,7 @@ __device__ __forceinline__ void path_put_dz(PathCtx& p, const TcNet& t, const fl
     const int N16 = t.ly[t.L].N16, nl = t.ly[t.L].nl;
 #pragma unroll
     for (int c = 0; c < 2; ++c) {
-        if (c < N16 / 16 && (c & 1) == p.grp) {
+        if (c < N16 / 16 && (c % TC_NGRP) == p.grp) {
             float v[16];
             uint32_t h[8];
 #pragma unroll
