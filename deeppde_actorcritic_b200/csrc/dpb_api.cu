@@ -399,6 +399,13 @@ static int tc_ring(dpb_handle* h, tc::TcArgs& a, bool grads) {
     if (fixed + 4 * (size_t)a.slot_bytes > avail) return fail(h, DPB_ERR_ARG, "tensor path: networks too wide for the shared-memory operand images");
     size_t ns = (avail - fixed) / a.slot_bytes;
     a.nslot = (int)(ns > tc::MAX_NSLOT ? tc::MAX_NSLOT : ns);
+    // Five slots already keep the weight stream ahead of the MMAs; if that fits in 196 KB the SM's unified array is carved
+    // 196 KB shared / 60 KB L1 instead of 228 / 28, which the path threads' local-memory traffic (register spills, relu
+    // masks) feels: critic 68.0 -> 66.5 ms, actor 66.9 -> 65.6 ms at 2^17 paths (3 or 4 slots: slower again).
+    {
+        const size_t cap = (size_t)196 * 1024 - 1024;
+        if (fixed + 5 * (size_t)a.slot_bytes <= cap) { const int v = (int)((cap - fixed) / a.slot_bytes); if (v < a.nslot) a.nslot = v; }
+    }
     // experiment knob: fewer ring slots leave more of the 256 KB unified array to L1 (local-memory traffic of the path threads)
     if (const char* e = getenv("DPB_TC_NSLOT")) { const int v = atoi(e); if (v >= 2 && v < a.nslot) a.nslot = v; }
     return DPB_OK;

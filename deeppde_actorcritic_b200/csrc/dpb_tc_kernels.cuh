@@ -289,9 +289,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) critic_tc_kernel(const TcArgs a
     unsigned char* copies = a.copies ? a.copies + (size_t)blockIdx.x * a.copies_per_cta : nullptr;
     float* gsV = a.slabV ? a.slabV + (size_t)(blockIdx.x % a.nslab) * gV.gtotal : nullptr;
     float* gsG = a.slabG ? a.slabG + (size_t)(blockIdx.x % a.nslab) * gG.gtotal : nullptr;
-    float sxV[DPX / TC_NGRP], s0V[DPX / TC_NGRP], sxG[DPX / TC_NGRP], s0G[DPX / TC_NGRP];
+    float sxG[DPX / TC_NGRP], s0G[DPX / TC_NGRP];
 #pragma unroll
-    for (int k = 0; k < DPX / TC_NGRP; ++k) { sxV[k] = 0.f; s0V[k] = 0.f; sxG[k] = 0.f; s0G[k] = 0.f; }
+    for (int k = 0; k < DPX / TC_NGRP; ++k) { sxG[k] = 0.f; s0G[k] = 0.f; }
 
     float loss0 = 0.f, loss1 = 0.f;
     TC_STAT(long long ph_roll = 0, ph_val = 0, ph_grad = 0;)          // cycles per phase (diagnostics)
@@ -418,6 +418,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) critic_tc_kernel(const TcArgs a
                 path_net_forward(P, nV, S.vecV, xbv, vb);
             } else {
                 Masks mk;
+                // (the input-layer sums of NN_value are flushed once per tile: three updates do not justify registers that
+                //  stay live through both sweeps)
+                float sxV[DPX / TC_NGRP], s0V[DPX / TC_NGRP];
+#pragma unroll
+                for (int k = 0; k < DPX / TC_NGRP; ++k) { sxV[k] = 0.f; s0V[k] = 0.f; }
                 path_net_forward(P, nV, S.vecV, x0v, v0);
                 path_net_forward_keep(P, nV, S.vecV, x, vN, mk, copies, S.act, row, false);
                 const float delta = v0[0] - y - vN[0] * disc;
@@ -434,6 +439,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) critic_tc_kernel(const TcArgs a
                 cot[0] = valid ? rho_grad(dbb, 50.f) * scale : 0.f;
                 path_net_backward(P, nV, gV, mk, cot, true, gsV, S.dz, row, dy0);
                 acc_input_sums<DPX>(sxV, s0V, xbv, dy0, P.grp, d);
+                reduce_rows_to(gsV + gV.gX, sxV, d, P.grp, true);
+                reduce_rows_to(gsV + gV.g0, s0V, d, P.grp, true);
             }
             const float delta = v0[0] - y - vN[0] * disc;                         // solver.py:189
             const float db = vb[0] - eq_Z<float, DP, EQN, MV>(E, xbv, 1, 0);                          // solver.py:190
@@ -476,8 +483,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) critic_tc_kernel(const TcArgs a
     TC_STAT(if (a.stats && tid == 0) { long long* st = a.stats + (size_t)blockIdx.x * 16; st[9] = ph_roll; st[10] = ph_val; st[11] = ph_grad; st[12] = seg_dw; st[13] = seg_A; st[14] = seg_mv; st[15] = seg_G; })
     if (is_ctrl) { ctrl_flush(C); C.pc->quit = 1; }
     if (need_grad) {
-        reduce_rows_to(gsV + gV.gX, sxV, d, P.grp, is_path);
-        reduce_rows_to(gsV + gV.g0, s0V, d, P.grp, is_path);
         if (td1) {
             reduce_rows_to(gsG + gG.gX, sxG, d, P.grp, is_path);
             reduce_rows_to(gsG + gG.g0, s0G, d, P.grp, is_path);
