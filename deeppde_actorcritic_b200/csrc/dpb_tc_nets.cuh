@@ -297,6 +297,15 @@ struct PathCtx {
     TC_STAT(long long t_drain;)             // cycles inside the dW drains (after the accumulator wait)
 };
 
+// The out-of-line helpers take the context BY VALUE (registers) and return the one field they change: passed by reference it
+// lives in local memory, and with 28-60 KB of L1 every epilogue then starts with a chain of L2-latency loads.  (The
+// cycle-counter build keeps the reference: its counters are updated inside the helpers.)
+#ifdef DPB_TC_STATS
+typedef PathCtx& PathArg;
+#else
+typedef PathCtx PathArg;
+#endif
+
 // A planes written and accumulator drained: one arrival per path warp (a_ready counts the 8 path warps)
 __device__ __forceinline__ void path_publish(PathCtx& p) {
     tmem_st_wait();
@@ -447,9 +456,11 @@ __device__ __forceinline__ void path_last(PathCtx& p, const float* gcbb, int N16
 
 // hidden-layer epilogues l0 .. l1-1 of a forward-only evaluation (no per-path arrays involved).  The caller places its
 // own per-path arithmetic between two ranges: it then runs while the tensor pipe works on the layer just published.
-static __device__ __noinline__ void path_hidden_range(PathCtx& p, const TcNet& t, const float* vec, int l0, int l1) {
+static __device__ __noinline__ uint32_t path_hidden_range_(PathArg p, const TcNet& t, const float* vec, int l0, int l1) {
     for (int l = l0; l < l1 && l < t.L; ++l) path_epi_hidden(p, vec + t.ly[l].vec, t.ly[l].N16);
+    return p.op_count;
 }
+__device__ __forceinline__ void path_hidden_range(PathCtx& p, const TcNet& t, const float* vec, int l0, int l1) { p.op_count = path_hidden_range_(p, t, vec, l0, l1); }
 
 // forward-only evaluation:  begin (y0 -> planes)  ...caller's own arithmetic...  finish (-> raw output)
 template <int NX>
@@ -590,7 +601,7 @@ struct Masks { uint32_t m[MAXLIN][8]; };     // m[l] bit k: a_l[k] > 0  (l = 1..
 // a_1..a_{L-1} (global scratch `copies`, NULL: none) and of a_L (shared ACT image, NULL: none).
 // skip_last: the raw output is not needed -- the last hidden epilogue does not publish (the caller writes
 // dz_L and publishes).
-static __device__ __noinline__ void path_hidden_keep(PathCtx& p, const TcNet& t, const float* vec, Masks& mk, unsigned char* copies,
+static __device__ __noinline__ uint32_t path_hidden_keep_(PathArg p, const TcNet& t, const float* vec, Masks& mk, unsigned char* copies,
                                               unsigned char* act, int row, bool skip_last) {
     for (int l = 0; l <= t.L; ++l)
 #pragma unroll
@@ -623,6 +634,11 @@ static __device__ __noinline__ void path_hidden_keep(PathCtx& p, const TcNet& t,
         }
         if (!(last_hidden && skip_last)) path_publish(p);
     }
+    return p.op_count;
+}
+__device__ __forceinline__ void path_hidden_keep(PathCtx& p, const TcNet& t, const float* vec, Masks& mk, unsigned char* copies,
+                                                 unsigned char* act, int row, bool skip_last) {
+    p.op_count = path_hidden_keep_(p, t, vec, mk, copies, act, row, skip_last);
 }
 // x -> (masks, copies) [-> raw output]
 template <int NX, int NO>
@@ -685,7 +701,7 @@ __device__ __forceinline__ void path_put_dz(PathCtx& p, const TcNet& t, const fl
 
 // middle of the backward: for l = L..0 the dW drains (need_w), and for l >= 1 the dX epilogue
 // dz_{l-1} = dA_l (.) slope(a_l) -> planes (+ DZ).  Ends before the result of the last product (dy0) is read.
-static __device__ __noinline__ void path_backward_mid(PathCtx& p, const TcNet& t, const TcSlab& g, const Masks& mk, bool need_w, float* slab,
+static __device__ __noinline__ uint32_t path_backward_mid_(PathArg p, const TcNet& t, const TcSlab& g, const Masks& mk, bool need_w, float* slab,
                                                unsigned char* dzimg, int row) {
     for (int l = t.L; l >= 0; --l) {
         if (need_w) {
@@ -710,6 +726,11 @@ static __device__ __noinline__ void path_backward_mid(PathCtx& p, const TcNet& t
         if (need_w) fence_proxy_async();
         path_publish(p);
     }
+    return p.op_count;
+}
+__device__ __forceinline__ void path_backward_mid(PathCtx& p, const TcNet& t, const TcSlab& g, const Masks& mk, bool need_w, float* slab,
+                                                  unsigned char* dzimg, int row) {
+    p.op_count = path_backward_mid_(p, t, g, mk, need_w, slab, dzimg, row);
 }
 // cotangent of y0 (in <= 31 values, static indexing)
 template <int NX>
