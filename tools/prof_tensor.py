@@ -19,10 +19,14 @@ for k in ("actor", "critic", "critic_grad"):
     th[k] = eng.tensor(RS.init_params(i, h, o, rng))
 x0, xb = eng.sample_x(5, 1, 0, B)
 kw = dict(dw_mode=1, seed=5, stream_id=3)
-for it in range(3):
+reps = int(sys.argv[3]) if len(sys.argv) > 3 else 8
+kcs, kas = [], []
+for it in range(reps):
     r = eng.critic_step(th["actor"], th["critic"], th["critic_grad"], x0, None, xb, 100, 0.2, need_grad=True, **kw)
-    kc = eng.last_kernel_ms()
+    kcs.append(eng.last_kernel_ms())
     a = eng.actor_step(th["actor"], th["critic"], x0, None, 100, 0.2, need_grad=True, **kw)
-    ka = eng.last_kernel_ms()
+    kas.append(eng.last_kernel_ms())
 torch.cuda.synchronize()
-print(f"{impl} B={B}: critic {kc:.3f} ms actor {ka:.3f} ms loss {float(r['loss'].sum()):.5f} {float(a['loss'][0]):.5f}")
+kcs, kas = kcs[2:], kas[2:]          # two warm-up launches
+print(f"{impl} B={B}: critic {np.mean(kcs):.3f} ms (min {min(kcs):.3f}) actor {np.mean(kas):.3f} ms (min {min(kas):.3f}) over {len(kcs)} launches; "
+      f"loss {float(r['loss'].sum()):.5f} {float(a['loss'][0]):.5f}")
