@@ -322,14 +322,22 @@ __device__ __forceinline__ void path_wait_acc(PathCtx& p) {
     ++p.op_count;
 }
 
+// Packed FP32 pairs (sm_100: FFMA2 / FADD2, one instruction for two IEEE operations -- same bits as the scalar forms).
+// The epilogues are bound by the instructions they issue, so every pairwise step is packed.
+__device__ __forceinline__ uint64_t pk2(float a, float b) { uint64_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ void up2(uint64_t v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) { uint64_t r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) { uint64_t r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ uint64_t sub2(uint64_t a, uint64_t b) { uint64_t r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+
 // 16 floats -> 8 packed hi words + 8 packed lo words (hi = bf16(x), lo = bf16(x - hi); element 2j in bits 0..15)
 __device__ __forceinline__ void split16(const float* v, uint32_t* h, uint32_t* l) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         const __nv_bfloat162 hh = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
         const uint32_t hb = *reinterpret_cast<const uint32_t*>(&hh);
-        const float r0 = v[2 * j] - __uint_as_float(hb << 16);
-        const float r1 = v[2 * j + 1] - __uint_as_float(hb & 0xffff0000u);
+        float r0, r1;
+        up2(sub2(pk2(v[2 * j], v[2 * j + 1]), pk2(__uint_as_float(hb << 16), __uint_as_float(hb & 0xffff0000u))), r0, r1);
         const __nv_bfloat162 ll = __floats2bfloat162_rn(r0, r1);
         h[j] = hb;
         l[j] = *reinterpret_cast<const uint32_t*>(&ll);
@@ -369,10 +377,8 @@ __device__ __forceinline__ void affine16(const uint32_t* r, const float* gc, con
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
         const float4 g = reinterpret_cast<const float4*>(gc)[q], b = reinterpret_cast<const float4*>(bb)[q];
-        z[4 * q] = fmaf(__uint_as_float(r[4 * q]), g.x, b.x);
-        z[4 * q + 1] = fmaf(__uint_as_float(r[4 * q + 1]), g.y, b.y);
-        z[4 * q + 2] = fmaf(__uint_as_float(r[4 * q + 2]), g.z, b.z);
-        z[4 * q + 3] = fmaf(__uint_as_float(r[4 * q + 3]), g.w, b.w);
+        up2(fma2(pk2(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1])), pk2(g.x, g.y), pk2(b.x, b.y)), z[4 * q], z[4 * q + 1]);
+        up2(fma2(pk2(__uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3])), pk2(g.z, g.w), pk2(b.z, b.w)), z[4 * q + 2], z[4 * q + 3]);
     }
 }
 
@@ -426,7 +432,8 @@ __device__ __forceinline__ void path_epi_hidden(PathCtx& p, const float* gcbb, i
         float v[16];
         affine16(r, gc + 16 * c, bb + 16 * c, v);
 #pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = v[j] + fmaxf(v[j], 0.f);
+        for (int j = 0; j < 8; ++j)
+            up2(add2(pk2(v[2 * j], v[2 * j + 1]), pk2(fmaxf(v[2 * j], 0.f), fmaxf(v[2 * j + 1], 0.f))), v[2 * j], v[2 * j + 1]);
         put16(p.tl, c, v);
     });
     path_publish(p);
@@ -620,10 +627,10 @@ static __device__ __noinline__ uint32_t path_hidden_keep_(PathArg p, const TcNet
             affine16(r, gc + 16 * c, bb + 16 * c, v);
             uint32_t bits = 0;
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                bits |= (v[j] > 0.f ? 1u : 0u) << j;
-                v[j] = v[j] + fmaxf(v[j], 0.f);
-            }
+            for (int j = 0; j < 16; ++j) bits |= (v[j] > 0.f ? 1u : 0u) << j;
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                up2(add2(pk2(v[2 * j], v[2 * j + 1]), pk2(fmaxf(v[2 * j], 0.f), fmaxf(v[2 * j + 1], 0.f))), v[2 * j], v[2 * j + 1]);
             mk.m[l + 1][c >> 1] |= (c & 1) ? (bits << 16) : bits;
             put16h(p.tl, c, v, h);
             if (dst) copy16h(dst, row, c, h, one_at);
