@@ -602,7 +602,10 @@ static __device__ __noinline__ void ctrl_net_backward(Ctrl& c, const TcNet& t, b
 }
 
 // ---- path threads ------------------------------------------------------------------------------------
-struct Masks { uint32_t m[MAXLIN][8]; };     // m[l] bit k: a_l[k] > 0  (l = 1..L), K16 <= 256
+// relu masks of one evaluation: h[l][c] bit j: a_l[16c + j] > 0  (l = 1..L, K16 <= 256).  Per-thread local memory; every
+// word is written with a plain store by the thread that reads it back (no read-modify-write, no initialisation), and the
+// backward fetches the word of its next chunk one chunk ahead.
+struct Masks { uint32_t h[MAXLIN][16]; };
 
 // hidden layers of a forward evaluation that keeps what the backward needs: relu masks (bits), bf16 copies of
 // a_1..a_{L-1} (global scratch `copies`, NULL: none) and of a_L (shared ACT image, NULL: none).
@@ -610,9 +613,6 @@ struct Masks { uint32_t m[MAXLIN][8]; };     // m[l] bit k: a_l[k] > 0  (l = 1..
 // dz_L and publishes).
 static __device__ __noinline__ uint32_t path_hidden_keep_(PathArg p, const TcNet& t, const float* vec, Masks& mk, unsigned char* copies,
                                               unsigned char* act, int row, bool skip_last) {
-    for (int l = 0; l <= t.L; ++l)
-#pragma unroll
-        for (int w = 0; w < 8; ++w) mk.m[l][w] = 0u;
     for (int l = 0; l < t.L; ++l) {
         const int N16 = t.ly[l].N16;
         const float* gc = vec + t.ly[l].vec;
@@ -631,7 +631,7 @@ static __device__ __noinline__ uint32_t path_hidden_keep_(PathArg p, const TcNet
 #pragma unroll
             for (int j = 0; j < 8; ++j)
                 up2(add2(pk2(v[2 * j], v[2 * j + 1]), pk2(fmaxf(v[2 * j], 0.f), fmaxf(v[2 * j + 1], 0.f))), v[2 * j], v[2 * j + 1]);
-            mk.m[l + 1][c >> 1] |= (c & 1) ? (bits << 16) : bits;
+            mk.h[l + 1][c] = bits;
             put16h(p.tl, c, v, h);
             if (dst) copy16h(dst, row, c, h, one_at);
         });
@@ -716,10 +716,12 @@ static __device__ __noinline__ uint32_t path_backward_mid_(PathArg p, const TcNe
             for (int b = 0; b < nblk; ++b) path_drain(p, b, row, t.ly[l].kl, t.ly[l].nl, t.ly[l].N16, slab + g.gW[l]);
         }
         if (l == 0) break;
-        path_wait_acc(p);                                                // dA_l in the accumulator (K16_l columns)
         const int K16 = t.ly[l].K16;
+        uint32_t nbits = mk.h[l][p.grp];                                 // (fetched while the product is still running)
+        path_wait_acc(p);                                                // dA_l in the accumulator (K16_l columns)
         for_acc_chunks(p.tl, p.grp, K16 / 16, [&](int c, const uint32_t* r) {
-            const uint32_t bits = mk.m[l][c >> 1] >> ((c & 1) * 16);
+            const uint32_t bits = nbits;
+            if (c + TC_NGRP < K16 / 16) nbits = mk.h[l][c + TC_NGRP];
             float v[16];
             uint32_t h[8];
 #pragma unroll
