@@ -1,8 +1,9 @@
 // dpb_tc_kernels.cuh -- the fused rollout + TD kernels with the MLP layers on tcgen05 (impl = tensor).
 // Same algorithm and per-path arithmetic (dpb_eqn.h) as dpb_kernels.cuh.  CTA = one tile of 128 paths = the 128
-// TMEM lanes; warps 0-7: path threads (t and t+128 own path t, state in registers, epilogue chunks split between
-// them); warp 8: control warp (all lanes run the protocol, the elected lane issues every tcgen05.mma); warp 9 lane 0:
-// weight-stream producer.
+// TMEM lanes; 4 * TC_NGRP path warps (TC_NGRP = 2, critic kernels: threads t and t+128 own path t, state in registers,
+// epilogue chunks split between them; TC_NGRP = 1, actor kernels: one thread per path with 255 registers), then the
+// control warp (all lanes run the protocol, the elected lane issues every tcgen05.mma) and the producer warp (lane 0
+// streams the weights).  The group count is a per-translation-unit constant (DPB_TC_NGRP, dpb_tc_nets.cuh).
 // Phases per tile -- critic: rollout (actor + NN_value_grad forward) -> NN_value at x_N, x_0, x_bdry (+ backward)
 // -> second sweep re-evaluating NN_value_grad at the stored x_t and back-propagating; actor: rollout -> terminal
 // value (+ input gradient) -> reverse sweep (re-evaluate the actor, adjoint step, back-propagate).

@@ -1,9 +1,9 @@
 // dpb_tc_nets.cuh -- DeepNN (reference solver.py:227-278) on the 5th-generation tensor cores.
 //
-// One CTA owns a tile of 128 paths; path t = TMEM lane t is owned by TWO "path threads", t (warps 0-3) and
-// t+128 (warps 4-7): both carry the identical per-path state in registers and each handles every other
-// 16-column chunk of the epilogues; lane 0 of warp 8 (the "control thread") streams the weights and
-// issues every tcgen05.mma.
+// One CTA owns a tile of 128 paths; path t = TMEM lane t is owned by TC_NGRP "path threads" (2: t in warps 0-3 and
+// t+128 in warps 4-7, both carrying the identical per-path state in registers and each handling every other
+// 16-column chunk of the epilogues; 1: a single thread with all chunks); the next warp is the control warp (issues
+// every tcgen05.mma), the last one the producer (streams the weights).
 //
 //   * Precision: FP32 emulated with bf16 pairs.  Every operand x is carried as hi = bf16(x) and
 //     lo = bf16(x - hi) and a product a*w is formed as ah*wh + ah*wl + al*wh with FP32 accumulation in
@@ -363,7 +363,8 @@ __device__ __forceinline__ void put16h(uint32_t tl, int c, const float* v, uint3
 template <class F>
 __device__ __forceinline__ void for_acc_chunks(uint32_t tl, int first, int nchunks, F f) {
     // (the TMEM->register path is the bound of every epilogue -- 64 B/clk/SM, see DESIGN.md -- so a plain loop does as
-    //  well as a software-pipelined one and needs 16 registers fewer)
+    //  well as a software-pipelined one and needs 16 registers fewer; re-measured with one thread per path and 255
+    //  registers: the double-buffered loop spills twice as much and the actor kernel runs 12 % slower)
     uint32_t ra[16];
     for (int c = first; c < nchunks; c += TC_NGRP) {
         tmem_ld16(tl + COL_ACC + 16 * c, ra);
