@@ -290,9 +290,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) critic_tc_kernel(const TcArgs a
     unsigned char* copies = a.copies ? a.copies + (size_t)blockIdx.x * a.copies_per_cta : nullptr;
     float* gsV = a.slabV ? a.slabV + (size_t)(blockIdx.x % a.nslab) * gV.gtotal : nullptr;
     float* gsG = a.slabG ? a.slabG + (size_t)(blockIdx.x % a.nslab) * gG.gtotal : nullptr;
-    float sxG[DPX / TC_NGRP], s0G[DPX / TC_NGRP];
-#pragma unroll
-    for (int k = 0; k < DPX / TC_NGRP; ++k) { sxG[k] = 0.f; s0G[k] = 0.f; }
 
     float loss0 = 0.f, loss1 = 0.f;
     TC_STAT(long long ph_roll = 0, ph_val = 0, ph_grad = 0;)          // cycles per phase (diagnostics)
@@ -469,6 +466,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) critic_tc_kernel(const TcArgs a
             } else if (is_path) {
                 Masks mk;
                 float xt[DPX], cot[DPX], dy0[DPX];
+                // (input-layer sums of this tile: live in this sweep only, flushed into the slab at its end)
+                float sxG[DPX / TC_NGRP], s0G[DPX / TC_NGRP];
+#pragma unroll
+                for (int k = 0; k < DPX / TC_NGRP; ++k) { sxG[k] = 0.f; s0G[k] = 0.f; }
                 for (int t = 0; t < tlive; ++t) {
                     const float* tr = traj + (size_t)t * 2 * sr * TC_PATHS;
                     KLOOP(k, d) { xt[k] = __ldcs(&tr[k * TC_PATHS + row]); cot[k] = __ldcs(&tr[(sr + k) * TC_PATHS + row]) * rhog; }
@@ -477,18 +478,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) critic_tc_kernel(const TcArgs a
                     path_net_backward(P, nG, gG, mk, cot, true, gsG, S.dz, row, dy0);
                     acc_input_sums<DPX>(sxG, s0G, xt, dy0, P.grp, d);
                 }
+                reduce_rows_to(gsG + gG.gX, sxG, d, P.grp, true);
+                reduce_rows_to(gsG + gG.g0, s0G, d, P.grp, true);
             }
         }
         TC_STAT(ph_grad += clock64() - tp2;)
     }
     TC_STAT(if (a.stats && tid == 0) { long long* st = a.stats + (size_t)blockIdx.x * 16; st[9] = ph_roll; st[10] = ph_val; st[11] = ph_grad; st[12] = seg_dw; st[13] = seg_A; st[14] = seg_mv; st[15] = seg_G; })
     if (is_ctrl) { ctrl_flush(C); C.pc->quit = 1; }
-    if (need_grad) {
-        if (td1) {
-            reduce_rows_to(gsG + gG.gX, sxG, d, P.grp, is_path);
-            reduce_rows_to(gsG + gG.g0, s0G, d, P.grp, is_path);
-        }
-    }
     if (tid == 0 && a.loss_part) {
         a.loss_part[blockIdx.x * 2] = loss0;
         a.loss_part[blockIdx.x * 2 + 1] = loss1;
@@ -537,6 +534,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) actor_tc_kernel(const TcArgs a)
     float* traj = a.scratch + (size_t)blockIdx.x * a.scratch_per_cta;               // [N][2*sr + A_NSCAL][128]
     unsigned char* copies = a.copies ? a.copies + (size_t)blockIdx.x * a.copies_per_cta : nullptr;
     float* gsA = a.slabA ? a.slabA + (size_t)(blockIdx.x % a.nslab) * gA.gtotal : nullptr;
+
+    // (kept for the whole kernel: scoping them to the reverse sweep of a tile, as the critic does with its sums, made the
+    //  actor 1.6 % slower)
     float sxA[DPX / TC_NGRP], s0A[DPX / TC_NGRP];
 #pragma unroll
     for (int k = 0; k < DPX / TC_NGRP; ++k) { sxA[k] = 0.f; s0A[k] = 0.f; }
