@@ -251,22 +251,12 @@ __device__ __forceinline__ void reduce_rows_to(float* dst, const float (&acc)[DH
 // DP > 0: instantiation for dim (and control_dim + 1) <= DP with equation EQN fixed at compile time -- the
 // per-path vectors are register arrays and every d-loop is unrolled (MV > 0: VDP with control_dim = MV, which makes its
 // cyclic neighbour indices static); <0,-1,0>: generic run-time version.
-template <int DP, int EQN, int MV>
-__global__ void __launch_bounds__(TC_THREADS, 1) critic_tc_kernel(const TcArgs a) {
+// The body is compiled once per role (IS_PATH: a path warp, otherwise the control warp): the same source, so both roles run
+// the same sequence of CTA barriers by construction, but each role's code is a branch of its own -- its registers are
+// allocated separately, which is what lets `setmaxnreg` give the path warps more than the launch bound.
+template <int DP, int EQN, int MV, bool IS_PATH>
+__device__ __forceinline__ void critic_tc_body(const TcArgs& a, const TcSmem& S, Roles& R) {
     constexpr int DPX = DP > 0 ? DP : 32;
-    extern __shared__ __align__(1024) unsigned char smem_raw[];
-    TcSmem S;
-    tc_carve(S, smem_raw, a);
-    const uint32_t tmem = tc_setup(S, a);
-    Roles R;
-    roles_init(R, S, a, tmem);
-    const long long t_start = clock64();
-    if ((threadIdx.x >> 5) == TC_PROD_WARP) {                       // producer warp: lane 0 streams weights until told to quit
-        if ((threadIdx.x & 31) == 0) producer_loop(S.ring, S.full, S.empty, S.sch, S.pc, a.nslot, a.slot_bytes);
-        tc_fence_before();
-        __syncthreads();
-        return;
-    }
     Ctrl& C = R.C;
     PathCtx& P = R.P;
     const TcNet& nA = *S.nA;
@@ -277,7 +267,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) critic_tc_kernel(const TcArgs a
     const TcSlab& gG = *S.gG;
     (void)gA; (void)gV; (void)gG;
     const int tid = threadIdx.x, warp = tid >> 5;
-    const bool is_path = R.is_path, is_ctrl = R.is_ctrl, primary = R.primary;
+    constexpr bool is_path = IS_PATH, is_ctrl = !IS_PATH;
+    const bool primary = R.primary;
     const int row = R.row;
     const Eq<float>& E = a.eqf;                                   // kernel-parameter space: fields are constant-bank operands
     const int d = E.d, N = a.N, sr = a.sr;
@@ -490,29 +481,44 @@ __global__ void __launch_bounds__(TC_THREADS, 1) critic_tc_kernel(const TcArgs a
         a.loss_part[blockIdx.x * 2] = loss0;
         a.loss_part[blockIdx.x * 2 + 1] = loss1;
     }
-    roles_stats(R, a, t_start);
-    tc_fence_before();
-    __syncthreads();
-    if (warp == TC_CTRL_WARP) tmem_dealloc(tmem, 512);
 }
 
-// =================================================================================== actor (tensor)
-template <int DP, int EQN, int MV>
-__global__ void __launch_bounds__(TC_THREADS, 1) actor_tc_kernel(const TcArgs a) {
-    constexpr int DPX = DP > 0 ? DP : 32;
-    extern __shared__ __align__(1024) unsigned char smem_raw[];
-    TcSmem S;
-    tc_carve(S, smem_raw, a);
-    const uint32_t tmem = tc_setup(S, a);
-    Roles R;
-    roles_init(R, S, a, tmem);
-    const long long t_start = clock64();
-    if ((threadIdx.x >> 5) == TC_PROD_WARP) {                       // producer warp: lane 0 streams weights until told to quit
-        if ((threadIdx.x & 31) == 0) producer_loop(S.ring, S.full, S.empty, S.sch, S.pc, a.nslot, a.slot_bytes);
-        tc_fence_before();
-        __syncthreads();
-        return;
+// common prologue / role dispatch / epilogue of both kernels
+#define DPB_TC_KERNEL(NAME)                                                                                                   \
+    template <int DP, int EQN, int MV>                                                                                        \
+    __global__ void __launch_bounds__(TC_THREADS, 1) NAME##_tc_kernel(const TcArgs a) {                                       \
+        extern __shared__ __align__(1024) unsigned char smem_raw[];                                                           \
+        TcSmem S;                                                                                                             \
+        tc_carve(S, smem_raw, a);                                                                                             \
+        const uint32_t tmem = tc_setup(S, a);                                                                                 \
+        Roles R;                                                                                                              \
+        roles_init(R, S, a, tmem);                                                                                            \
+        const long long t_start = clock64();                                                                                  \
+        const int warp = threadIdx.x >> 5;                                                                                    \
+        if (warp >= TC_CTRL_WARP) {                      /* control, producer (lane 0 streams the weights), idle warps */     \
+            tc_regs_release();                                                                                                \
+            if (warp == TC_PROD_WARP) {                                                                                       \
+                if ((threadIdx.x & 31) == 0) producer_loop(S.ring, S.full, S.empty, S.sch, S.pc, a.nslot, a.slot_bytes);      \
+            } else if (warp == TC_CTRL_WARP) {                                                                                \
+                NAME##_tc_body<DP, EQN, MV, false>(a, S, R);                                                                  \
+            }                                                                                                                 \
+        } else {                                                                                                              \
+            tc_regs_take();                                                                                                   \
+            NAME##_tc_body<DP, EQN, MV, true>(a, S, R);                                                                       \
+        }                                                                                                                     \
+        roles_stats(R, a, t_start);                                                                                           \
+        tc_fence_before();                                                                                                    \
+        __syncthreads();                                                                                                      \
+        if (warp == TC_CTRL_WARP) tmem_dealloc(tmem, 512);                                                                    \
     }
+
+// =================================================================================== actor (tensor)
+// The body is compiled once per role (IS_PATH: a path warp, otherwise the control warp): the same source, so both roles run
+// the same sequence of CTA barriers by construction, but each role's code is a branch of its own -- its registers are
+// allocated separately, which is what lets `setmaxnreg` give the path warps more than the launch bound.
+template <int DP, int EQN, int MV, bool IS_PATH>
+__device__ __forceinline__ void actor_tc_body(const TcArgs& a, const TcSmem& S, Roles& R) {
+    constexpr int DPX = DP > 0 ? DP : 32;
     Ctrl& C = R.C;
     PathCtx& P = R.P;
     const TcNet& nA = *S.nA;
@@ -523,7 +529,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) actor_tc_kernel(const TcArgs a)
     const TcSlab& gG = *S.gG;
     (void)gA; (void)gV; (void)gG;
     const int tid = threadIdx.x, warp = tid >> 5;
-    const bool is_path = R.is_path, is_ctrl = R.is_ctrl, primary = R.primary;
+    constexpr bool is_path = IS_PATH, is_ctrl = !IS_PATH;
+    const bool primary = R.primary;
     const int row = R.row;
     const Eq<float>& E = a.eqf;                                   // kernel-parameter space: fields are constant-bank operands
     const int d = E.d, m = E.m, N = a.N, sr = a.sr;
@@ -710,14 +717,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) actor_tc_kernel(const TcArgs a)
         a.loss_part[blockIdx.x * 2] = loss0;
         a.loss_part[blockIdx.x * 2 + 1] = 0.f;
     }
-    roles_stats(R, a, t_start);
     TC_STAT(if (a.stats) { long long* st = a.stats + (size_t)blockIdx.x * 16;
                            if (is_ctrl && (tid & 31) == 0) st[9] = C.t_act;
                            if (tid == 0) { st[11] = P.t_drain; st[12] = seg_fwd; st[13] = seg_fk; st[14] = seg_adj; st[15] = seg_bwd; } })
-    tc_fence_before();
-    __syncthreads();
-    if (warp == TC_CTRL_WARP) tmem_dealloc(tmem, 512);
 }
+
+DPB_TC_KERNEL(critic)
+DPB_TC_KERNEL(actor)
 
 }  // namespace tc
 }  // namespace dpb

@@ -38,6 +38,12 @@ constexpr int TC_CTRL_WARP = 4 * TC_NGRP;       // waits for operands, issues ev
 constexpr int TC_PROD_WARP = TC_CTRL_WARP + 1;  // lane 0: streams the weight chunks (bulk copies) on its own
 constexpr int TC_WORK_THREADS = 32 * (TC_CTRL_WARP + 1);   // path + control warps take part in the in-loop CTA barriers (named barrier 1)
 constexpr int TC_THREADS = TC_WORK_THREADS + 32;
+// (`setmaxnreg`: with 12 warps -- path, path, control + producer + two idle warps -- the third warpgroup could hand its
+//  registers to the path warps, 168 -> 224 per thread.  The kernels are structured for it, one body per role, but ptxas does
+//  not spill inside a region whose budget was raised and the path code does not fit 232 registers without spilling:
+//  "register allocation failed with register count of 224".  Left as hooks until the per-path state shrinks.)
+__device__ __forceinline__ void tc_regs_release() {}
+__device__ __forceinline__ void tc_regs_take() {}
 constexpr int MAX_NSLOT = 16;                   // ring slots (runtime count: whatever shared memory is left)
 constexpr uint32_t COL_ACC = 0, COL_AHI = 256, COL_ALO = 384;
 constexpr int MAXOPS = 40;
