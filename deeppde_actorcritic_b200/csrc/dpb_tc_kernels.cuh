@@ -266,7 +266,7 @@ __device__ __forceinline__ void critic_tc_body(const TcArgs& a, const TcSmem& S,
     const TcSlab& gV = *S.gV;
     const TcSlab& gG = *S.gG;
     (void)gA; (void)gV; (void)gG;
-    const int tid = threadIdx.x, warp = tid >> 5;
+    const int tid = threadIdx.x;
     constexpr bool is_path = IS_PATH, is_ctrl = !IS_PATH;
     const bool primary = R.primary;
     const int row = R.row;
@@ -527,8 +527,8 @@ __device__ __forceinline__ void actor_tc_body(const TcArgs& a, const TcSmem& S, 
     const TcSlab& gA = *S.gA;
     const TcSlab& gV = *S.gV;
     const TcSlab& gG = *S.gG;
-    (void)gA; (void)gV; (void)gG;
-    const int tid = threadIdx.x, warp = tid >> 5;
+    (void)gA; (void)gV; (void)gG; (void)nG;
+    const int tid = threadIdx.x;
     constexpr bool is_path = IS_PATH, is_ctrl = !IS_PATH;
     const bool primary = R.primary;
     const int row = R.row;
