@@ -84,6 +84,7 @@ SYMBOLS = {
     "dpb_tc_handshake_cycles": (C.c_int, [_P, C.c_int]),
     "dpb_tc_epilogue_cycles": (C.c_int, [_P, C.c_int, C.c_int]),
     "dpb_tc_stats": (C.c_int, [_P, _P, _I64, _I32, _P]),
+    "dpb_tc_mma_cycles": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int]),
 }
 
 _lib = None

@@ -159,6 +159,9 @@ int dpb_create(dpb_handle** out, const dpb_config* cfg) {
     if (c.impl == DPB_IMPL_TENSOR) {
         if (c.dtype != DPB_F32) { delete h; return fail(nullptr, DPB_ERR_ARG, "the tensor path computes in float32 (bf16x3 products, FP32 accumulation): dtype must be DPB_F32"); }
         if (!tc::tcnet_supported(h->tA) || !tc::tcnet_supported(h->tV) || !tc::tcnet_supported(h->tG)) { delete h; return fail(nullptr, DPB_ERR_ARG, "tensor path: layer width must be <= 255"); }
+        // longest load schedule of a phase: V forward + 3 x (V forward + backward), one entry per product (dpb_tc_kernels.cuh)
+        const int lmx = c.n_hidden_actor > c.n_hidden_critic ? c.n_hidden_actor : c.n_hidden_critic;
+        if (7 * (lmx + 1) > tc::MAXOPS) { delete h; return fail(nullptr, DPB_ERR_ARG, "tensor path: too many layers for the chunk schedule"); }
     }
     const int mx = c.dim > c.control_dim + 1 ? c.dim : c.control_dim + 1;
     h->sr = round8(mx);
@@ -393,7 +396,7 @@ static bool tc_specialised(const dpb_handle* h) {
 // ring geometry for a launch: slots of `slot_bytes` (largest chunk of the images used) in what is left of 227 KB
 static int tc_ring(dpb_handle* h, tc::TcArgs& a, bool grads) {
     a.actdz_bytes = grads ? tc::TC_PATHS * h->tc_maxw16 * 2 : 0;
-    a.slot_bytes = h->tc_maxw16 * 64;
+    a.slot_bytes = h->tc_maxw16 * 64;                              // largest chunk: 16 contraction rows x the widest output, hi + lo
     const size_t fixed = tc::tc_smem_fixed(h->tA.vec_floats, h->tV.vec_floats, h->tG.vec_floats, a.actdz_bytes);
     const size_t avail = (size_t)227 * 1024;
     if (fixed + 4 * (size_t)a.slot_bytes > avail) return fail(h, DPB_ERR_ARG, "tensor path: networks too wide for the shared-memory operand images");
@@ -809,5 +812,19 @@ extern "C" int dpb_tc_epilogue_cycles(int64_t* out_host, int rounds, int ngroups
     cudaError_t e = cudaMemcpy(out_host, d, 16, cudaMemcpyDeviceToHost);
     cudaFree(d);
     if (e != cudaSuccess) return fail(nullptr, DPB_ERR_CUDA, std::string("dpb_tc_epilogue_cycles: ") + cudaGetErrorString(e));
+    return DPB_OK;
+}
+
+extern "C" int dpb_tc_mma_cycles(int64_t* out_host, int n, int rounds, int ts, int per_commit) {
+    if (!out_host || n < 16 || n > 256 || (n % 16) || rounds < 1 || per_commit < 1) return fail(nullptr, DPB_ERR_ARG, "dpb_tc_mma_cycles: bad argument");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) { cudaGetLastError(); return fail(nullptr, DPB_ERR_CUDA, "dpb_tc_mma_cycles: no CUDA device"); }
+    long long* d = nullptr;
+    DPB_CUDA(nullptr, cudaMalloc(&d, 16));
+    const int smem = 4096 + n * 32 + 1024;
+    tc::tc_mma_bench_kernel<<<1, 128, smem>>>(d, n, rounds, ts, per_commit);
+    cudaError_t e = cudaMemcpy(out_host, d, 16, cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    if (e != cudaSuccess) return fail(nullptr, DPB_ERR_CUDA, std::string("dpb_tc_mma_cycles: ") + cudaGetErrorString(e));
     return DPB_OK;
 }

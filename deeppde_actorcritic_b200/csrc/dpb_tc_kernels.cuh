@@ -52,7 +52,7 @@ struct TcSmem {
     unsigned char *act, *dz;
     unsigned char* ring;
     float *vecA, *vecV, *vecG;
-    uint64_t *full, *empty, *acc_full, *a_ready, *act_full;
+    uint64_t *full, *empty, *acc_full, *a_all, *a_chunk, *act_full;
     uint32_t* tslot;
     int* tile;                       // the tile a CTA works on next (dynamic tile scheduler)
     Sched* sch;
@@ -64,7 +64,7 @@ struct TcSmem {
 
 // everything except the ring
 __host__ __device__ inline size_t tc_smem_fixed(int vfA, int vfV, int vfG, int actdz_bytes) {
-    return 2 * (size_t)actdz_bytes + (size_t)(vfA + vfV + vfG) * 4 + (2 * MAX_NSLOT + 3) * 8 + 64 + sizeof(Sched) + 64 + 64 + 3 * sizeof(TcNet) + 3 * sizeof(TcSlab) + 64 + 1024;
+    return 2 * (size_t)actdz_bytes + (size_t)(vfA + vfV + vfG) * 4 + (2 * MAX_NSLOT + 3 + MAX_CHUNK) * 8 + 64 + sizeof(Sched) + 64 + 64 + 3 * sizeof(TcNet) + 3 * sizeof(TcSlab) + 64 + 1024;
 }
 __host__ __device__ inline size_t tc_smem_bytes(int vfA, int vfV, int vfG, int actdz_bytes, int nslot, int slot_bytes) {
     return tc_smem_fixed(vfA, vfV, vfG, actdz_bytes) + (size_t)nslot * slot_bytes;
@@ -81,8 +81,9 @@ __device__ __forceinline__ void tc_carve(TcSmem& s, unsigned char* base, const T
     s.vecG = reinterpret_cast<float*>(p); p += (size_t)vfG * 4;
     s.full = reinterpret_cast<uint64_t*>(p); p += MAX_NSLOT * 8;
     s.empty = reinterpret_cast<uint64_t*>(p); p += MAX_NSLOT * 8;
-    s.acc_full = reinterpret_cast<uint64_t*>(p); p += 8;
-    s.a_ready = reinterpret_cast<uint64_t*>(p); p += 8;
+    s.acc_full = reinterpret_cast<uint64_t*>(p); p += 8;           // acc_full, a_all, a_chunk[16]: contiguous (PathCtx::bars)
+    s.a_all = reinterpret_cast<uint64_t*>(p); p += 8;
+    s.a_chunk = reinterpret_cast<uint64_t*>(p); p += 8 * MAX_CHUNK;
     s.act_full = reinterpret_cast<uint64_t*>(p); p += 8;
     s.tslot = reinterpret_cast<uint32_t*>(p); s.tile = reinterpret_cast<int*>(p) + 4; p += 64;
     s.sch = reinterpret_cast<Sched*>(p); p += sizeof(Sched);
@@ -108,7 +109,9 @@ __device__ __forceinline__ uint32_t tc_setup(TcSmem& s, const TcArgs& a) {
     if (tid == 0) {
         for (int i = 0; i < MAX_NSLOT; ++i) { mbar_init(&s.full[i], 1); mbar_init(&s.empty[i], 1); }
         mbar_init(s.acc_full, 1);
-        mbar_init(s.a_ready, TC_PATH_THREADS / 32);
+        mbar_init(s.a_all, TC_PATH_THREADS / 32);
+        mbar_init(&s.a_chunk[0], TC_PATH_THREADS / 32);                      // chunk 0: every path warp (see for_acc_chunks)
+        for (int i = 1; i < MAX_CHUNK; ++i) mbar_init(&s.a_chunk[i], 4);     // the four warps of the group that owns the chunk
         mbar_init(s.act_full, 1);
         s.sch->nops = 0;
         s.pc->req = 0; s.pc->gen = 0; s.pc->quit = 0;
@@ -199,12 +202,12 @@ __device__ __forceinline__ void roles_init(Roles& r, const TcSmem& S, const TcAr
     r.primary = warp < 4;
     r.row = tid & 127;
     Ctrl& C = r.C;
-    C.ring = S.ring; C.full = S.full; C.empty = S.empty; C.acc_full = S.acc_full; C.a_ready = S.a_ready; C.sch = S.sch;
-    C.pc = S.pc; C.n_req = 0; C.n_consumed = 0; C.op_count = 0; C.tmem = warp_uniform(tmem); C.gen = 0;
+    C.ring = S.ring; C.full = S.full; C.empty = S.empty; C.acc_full = S.acc_full; C.a_all = S.a_all; C.a_chunk = S.a_chunk; C.sch = S.sch;
+    C.pc = S.pc; C.n_req = 0; C.n_consumed = 0; C.op_count = 0; C.sync = 0; C.tmem = warp_uniform(tmem); C.gen = 0;
     C.act_full = S.act_full; C.act_count = 0; C.nslot = a.nslot; C.slot_bytes = a.slot_bytes; C.act = S.act; C.dz = S.dz;
     r.P.tl = tmem + ((uint32_t)((warp & 3) * 32) << 16);
     r.P.grp = (warp >> 2) % TC_NGRP;
-    r.P.acc_full = smem_u32(S.acc_full); r.P.a_ready = smem_u32(S.a_ready); r.P.op_count = 0;
+    r.P.bars = smem_u32(S.acc_full); r.P.sync = 0;
     TC_STAT(r.P.t_accw = 0; r.P.t_epi = 0; r.P.t_hid = 0; r.P.t_drain = 0; r.P.t_mark = clock64();)
     TC_STAT(C.t_aready = 0; C.t_issue = 0; C.t_accw = 0; C.t_dw_ready = 0; C.t_act = 0;)
     C.n_ops = 0;
@@ -303,8 +306,8 @@ __device__ __forceinline__ void critic_tc_body(const TcArgs& a, const TcSmem& S,
         }
         if (is_ctrl) {                                            // schedule of the rollout
             ctrl_flush(C);
-            if (!cheat) sched_add_fwd(C.sch, nA, a.imgA, nA.L);
-            if (td1) sched_add_fwd(C.sch, nG, a.imgG, nG.L);
+            if (!cheat) sched_add_fwd(C, nA, a.imgA, nA.L);
+            if (td1) sched_add_fwd(C, nG, a.imgG, nG.L);
             ctrl_sched_ready(C);
         }
         // ------------------------------------------------------------------ sweep 1: rollout
@@ -387,12 +390,12 @@ __device__ __forceinline__ void critic_tc_body(const TcArgs& a, const TcSmem& S,
         if (is_ctrl) {
             ctrl_flush(C);
             if (!need_grad) {
-                sched_add_fwd(C.sch, nV, a.imgV, nV.L);
+                sched_add_fwd(C, nV, a.imgV, nV.L);
                 ctrl_sched_ready(C);
                 for (int i = 0; i < 3; ++i) ctrl_net_forward(C, nV, nV.L);
             } else {
-                sched_add_fwd(C.sch, nV, a.imgV, nV.L);                       // V(x_0), forward only
-                for (int i = 0; i < 3; ++i) { sched_add_fwd(C.sch, nV, a.imgV, nV.L); sched_add_bwd(C.sch, nV, a.imgV); }
+                sched_add_fwd(C, nV, a.imgV, nV.L);                       // V(x_0), forward only
+                for (int i = 0; i < 3; ++i) { sched_add_fwd(C, nV, a.imgV, nV.L); sched_add_bwd(C, nV, a.imgV); }
                 ctrl_sched_ready(C);
                 ctrl_net_forward(C, nV, nV.L);
                 for (int i = 0; i < 3; ++i) { ctrl_net_forward(C, nV, nV.L); ctrl_net_backward(C, nV, true, copies); }
@@ -447,8 +450,8 @@ __device__ __forceinline__ void critic_tc_body(const TcArgs& a, const TcSmem& S,
         if (need_grad && td1) {
             if (is_ctrl) {
                 ctrl_flush(C);
-                sched_add_fwd(C.sch, nG, a.imgG, nG.L - 1);
-                sched_add_bwd(C.sch, nG, a.imgG);
+                sched_add_fwd(C, nG, a.imgG, nG.L - 1);
+                sched_add_bwd(C, nG, a.imgG);
                 ctrl_sched_ready(C);
                 for (int t = 0; t < tlive; ++t) {
                     ctrl_net_forward(C, nG, nG.L - 1);
@@ -568,7 +571,7 @@ __device__ __forceinline__ void actor_tc_body(const TcArgs& a, const TcSmem& S, 
         }
         if (is_ctrl) {
             ctrl_flush(C);
-            if (!cheat) sched_add_fwd(C.sch, nA, a.imgA, nA.L);
+            if (!cheat) sched_add_fwd(C, nA, a.imgA, nA.L);
             ctrl_sched_ready(C);
         }
         // ------------------------------------------------------------------ forward rollout
@@ -631,8 +634,8 @@ __device__ __forceinline__ void actor_tc_body(const TcArgs& a, const TcSmem& S, 
         if (is_ctrl) {
             ctrl_flush(C);
             if (!cheat_v) {
-                sched_add_fwd(C.sch, nV, a.imgV, nV.L);
-                if (need_grad) sched_add_bwd(C.sch, nV, a.imgV);
+                sched_add_fwd(C, nV, a.imgV, nV.L);
+                if (need_grad) sched_add_bwd(C, nV, a.imgV);
                 ctrl_sched_ready(C);
                 ctrl_net_forward(C, nV, nV.L);
                 if (need_grad) ctrl_net_backward(C, nV, false, nullptr);
@@ -669,8 +672,8 @@ __device__ __forceinline__ void actor_tc_body(const TcArgs& a, const TcSmem& S, 
         // ------------------------------------------------------------------ reverse sweep
         if (is_ctrl) {
             ctrl_flush(C);
-            sched_add_fwd(C.sch, nA, a.imgA, nA.L);
-            sched_add_bwd(C.sch, nA, a.imgA);
+            sched_add_fwd(C, nA, a.imgA, nA.L);
+            sched_add_bwd(C, nA, a.imgA);
             ctrl_sched_ready(C);
         }
         for (int t = tlive - 1; t >= 0; --t) {

@@ -18,7 +18,19 @@
 //     completion on an mbarrier); a slot is released by the tcgen05.commit of the MMAs that read it.
 //     The chunk sequence of a phase is a cyclic schedule known in advance, so the stream runs ahead of
 //     the MMAs across layers, networks and time steps.
-//   * TMEM columns: [0,256) accumulator (N <= 256), [256,384) A hi plane, [384,512) A lo plane (K <= 256).
+//   * TMEM columns: two regions of 256 columns.  A product reads its A planes from one region and accumulates into the
+//     other; the epilogue converts the FP32 accumulator IN PLACE into the planes of the next product (16 accumulator
+//     columns of a chunk -> 8 columns of packed hi pairs + 8 columns of packed lo pairs), so the regions swap roles
+//     from layer to layer.
+//   * Chunk-granular hand-off: the epilogue publishes every 16-column chunk on its own mbarrier (a_chunk[c]) and the
+//     next product starts on contraction chunk c as soon as it is there -- the tensor pipe works on layer l+1 while
+//     the path threads are still converting the rest of layer l.  (Splitting the OUTPUT columns of a product into
+//     two halves with separate commits was tried first: parity-green but slower -- a tcgen05.commit stalls the issuing
+//     thread for ~300 cycles, which three N=112 MMAs (68 cycles each) do not cover, and one MMA costs 22 + 0.45 N
+//     cycles, not N/2: profiles/r02_tcgen05_*.txt.)  Inputs that are written by the path threads themselves (y0, the
+//     output cotangent) or that feed a dW product are published once, on a_all.
+//   * Small weight chunks (narrow outputs: 2 KB for a 32-wide layer) are streamed several per ring slot, so that one
+//     tcgen05.commit releases up to eight of them.
 #pragma once
 #include "dpb_nets.cuh"
 #include "dpb_tc.cuh"
@@ -45,8 +57,16 @@ constexpr int TC_THREADS = TC_WORK_THREADS + 32;
 __device__ __forceinline__ void tc_regs_release() {}
 __device__ __forceinline__ void tc_regs_take() {}
 constexpr int MAX_NSLOT = 16;                   // ring slots (runtime count: whatever shared memory is left)
-constexpr uint32_t COL_ACC = 0, COL_AHI = 256, COL_ALO = 384;
-constexpr int MAXOPS = 40;
+constexpr uint32_t COL_REG = 256;               // TMEM region r = columns [256 r, 256 r + 256)
+constexpr int MAXOPS = 64;                      // schedule entries of one phase: <= 7 (L+1) products, L <= 6 hidden layers
+
+constexpr int MAX_CHUNK = 16;                   // 16-column chunks of the widest layer (256 / 16): one a_chunk barrier each
+constexpr int MAX_GROUP = 8;                    // weight chunks per ring slot (narrow layers)
+// weight chunks streamed per ring slot for a product with R output rows (chunk = R*64 bytes)
+__host__ __device__ __forceinline__ int tc_group(int R, int slot_bytes) {
+    const int g = slot_bytes / (R * 64);
+    return g < 1 ? 1 : (g > MAX_GROUP ? MAX_GROUP : g);
+}
 
 __host__ __device__ inline int round16(int x) { return (x + 15) & ~15; }
 
@@ -56,6 +76,7 @@ struct TcLayer {
                            // turns the bias column sums into one more row of the dW product), N16 = K16 of
                            // the next layer, round16(out) for the last one
     long long img_f;       // byte offset of the forward image  (rows N16, contraction K16): K16/16 chunks of N16*64 B
+                           // (hi plane N16*32 B, then lo plane)
     long long img_b;       // byte offset of the backward image (rows K16, contraction N16): N16/16 chunks of K16*64 B
     int vec;               // float offset of gc[N16], bb[N16] in the vector block
 };
@@ -152,27 +173,34 @@ static __global__ void tc_pack_kernel(TcNet t, const float* __restrict__ th, uns
 #endif
 
 // ------------------------------------------------------------------------------ control-thread side
-struct Sched {                       // cyclic chunk schedule of the current phase (shared memory)
+struct Sched {                       // cyclic schedule of ring-slot loads of the current phase (shared memory)
     const unsigned char* ptr[MAXOPS];
-    int nch[MAXOPS];
-    int cb[MAXOPS];
+    int nld[MAXOPS];                 // loads of this product (each fills one ring slot with `lb` bytes, the last with `lb_last`)
+    int lb[MAXOPS], lb_last[MAXOPS];
     int nops;
 };
 
 // mailbox between the control thread and the producer thread (shared memory)
 struct ProdCtl {
-    volatile uint32_t req;       // chunks requested so far (monotone); the producer loads until loaded == req
+    volatile uint32_t req;       // loads requested so far (monotone); the producer loads until loaded == req
     volatile uint32_t gen;       // bumped whenever a new schedule has been written (the producer restarts its cursor)
     volatile uint32_t quit;
 };
 
+// Hand-off barriers (shared memory, contiguous):  acc_full (count 1: tcgen05.commit of a product), a_all (count = path
+// warps: everything the next product needs is in place / the accumulator has been drained), a_chunk[16] (count 4: the
+// four warps that converted chunk c of the accumulator published its planes; a_chunk[0] counts every path warp).  Every barrier's parity is tracked on both
+// sides in one word: bit c (< 16) a_chunk[c], bit 16 a_all, bit 17 acc_full, bit 31 the TMEM region of the next A planes.
+constexpr uint32_t SY_ALL = 1u << 16, SY_ACC = 1u << 17, SY_REG = 1u << 31;
+
 struct Ctrl {
     unsigned char* ring;
-    uint64_t *full, *empty, *acc_full, *a_ready, *act_full;
+    uint64_t *full, *empty, *acc_full, *a_all, *a_chunk, *act_full;
     Sched* sch;
     ProdCtl* pc;
     uint32_t nslot, slot_bytes;
     uint32_t n_req, n_consumed, op_count, act_count, tmem, gen;
+    uint32_t sync;                   // parity bits (see above); op_count = products committed so far
     uint32_t mm_slot, mm_use;        // ring cursor (slot index, wrap count) of the MMA issuer
     unsigned char *act, *dz;         // shared-memory operand images of the dW products (128 paths x K16 features, bf16)
     long long n_ops;
@@ -180,13 +208,13 @@ struct Ctrl {
     TC_STAT(long long t_dw_ready, t_act;)           // dW products: waiting for their operands / for the ACT bulk copy
 };
 
-// let the producer run up to nslot chunks ahead of the MMAs (one shared-memory store, never waits)
+// let the producer run up to nslot loads ahead of the MMAs (one shared-memory store, never waits)
 __device__ __forceinline__ void ctrl_request(Ctrl& c) {
     const uint32_t want = c.n_consumed + c.nslot;
     if (want != c.n_req) { c.n_req = want; c.pc->req = want; }
 }
 
-// drop every chunk that was requested ahead but will not be used (end of a phase / dead tile)
+// drop every load that was requested ahead but will not be used (end of a phase / dead tile)
 __device__ __forceinline__ void ctrl_flush(Ctrl& c) {
     while (c.n_consumed != c.n_req) {
         mbar_wait(&c.full[c.mm_slot], c.mm_use & 1);
@@ -205,12 +233,12 @@ __device__ __forceinline__ void ctrl_sched_ready(Ctrl& c) {
     __threadfence_block();
 }
 
-// the producer thread: streams the cyclic chunk schedule through the ring as far as requested
+// the producer thread: streams the cyclic load schedule through the ring as far as requested
 __device__ __forceinline__ void producer_loop(unsigned char* ring, uint64_t* full, uint64_t* empty, Sched* sch, ProdCtl* pc,
                                               uint32_t nslot, uint32_t slot_bytes) {
     uint32_t loaded = 0, my_gen = 0, slot = 0, use = 0;
-    int op = 0, ch = 0, nops = 0, cur_nch = 0;
-    uint32_t cur_cb = 0;
+    int op = 0, ld = 0, nops = 0, cur_nld = 0;
+    uint32_t cur_lb = 0, cur_last = 0;
     const unsigned char* cur_ptr = nullptr;
     for (;;) {
         const uint32_t r = pc->req;
@@ -222,17 +250,18 @@ __device__ __forceinline__ void producer_loop(unsigned char* ring, uint64_t* ful
         __threadfence_block();
         const uint32_t g = pc->gen;
         if (g != my_gen) {
-            my_gen = g; op = 0; ch = 0; nops = sch->nops;
-            cur_ptr = sch->ptr[0]; cur_nch = sch->nch[0]; cur_cb = (uint32_t)sch->cb[0];
+            my_gen = g; op = 0; ld = 0; nops = sch->nops;
+            cur_ptr = sch->ptr[0]; cur_nld = sch->nld[0]; cur_lb = (uint32_t)sch->lb[0]; cur_last = (uint32_t)sch->lb_last[0];
         }
         while (loaded != r) {
             if (use > 0) mbar_wait(&empty[slot], (use - 1) & 1);
-            mbar_arrive_expect_tx(&full[slot], cur_cb);
-            bulk_g2s(ring + (size_t)slot * slot_bytes, cur_ptr + (size_t)ch * cur_cb, cur_cb, &full[slot]);
-            if (++ch == cur_nch) {
-                ch = 0;
+            const uint32_t bytes = (ld == cur_nld - 1) ? cur_last : cur_lb;
+            mbar_arrive_expect_tx(&full[slot], bytes);
+            bulk_g2s(ring + (size_t)slot * slot_bytes, cur_ptr + (size_t)ld * cur_lb, bytes, &full[slot]);
+            if (++ld == cur_nld) {
+                ld = 0;
                 if (++op == nops) op = 0;
-                cur_ptr = sch->ptr[op]; cur_nch = sch->nch[op]; cur_cb = (uint32_t)sch->cb[op];
+                cur_ptr = sch->ptr[op]; cur_nld = sch->nld[op]; cur_lb = (uint32_t)sch->lb[op]; cur_last = (uint32_t)sch->lb_last[op];
             }
             ++loaded;
             if (++slot == nslot) { slot = 0; ++use; }
@@ -240,43 +269,72 @@ __device__ __forceinline__ void producer_loop(unsigned char* ring, uint64_t* ful
     }
 }
 
-__device__ __forceinline__ void sched_add(Sched* s, const unsigned char* p, int nch, int cb) {
-    if ((threadIdx.x & 31) == 0) { s->ptr[s->nops] = p; s->nch[s->nops] = nch; s->cb[s->nops] = cb; ++s->nops; }
+// one product with nch_in contraction chunks of R_out rows each: ceil(nch_in / g) loads of g chunks
+__device__ __forceinline__ void sched_add_op(Sched* s, const unsigned char* img, int nch_in, int R_out, int slot_bytes) {
+    if ((threadIdx.x & 31) == 0) {
+        if (s->nops >= MAXOPS) asm volatile("trap;");                 // (dpb_create rejects networks whose phases do not fit)
+        const int g = tc_group(R_out, slot_bytes), nld = (nch_in + g - 1) / g, i = s->nops;
+        s->ptr[i] = img; s->nld[i] = nld; s->lb[i] = g * R_out * 64; s->lb_last[i] = (nch_in - (nld - 1) * g) * R_out * 64;
+        s->nops = i + 1;
+    }
 }
-__device__ __forceinline__ void sched_add_fwd(Sched* s, const TcNet& t, const unsigned char* img, int upto /*layers 0..upto*/) {
-    for (int l = 0; l <= upto; ++l) sched_add(s, img + t.ly[l].img_f, t.ly[l].K16 / 16, t.ly[l].N16 * 64);
+__device__ __forceinline__ void sched_add_fwd(Ctrl& c, const TcNet& t, const unsigned char* img, int upto /*layers 0..upto*/) {
+    for (int l = 0; l <= upto; ++l) sched_add_op(c.sch, img + t.ly[l].img_f, t.ly[l].K16 / 16, t.ly[l].N16, (int)c.slot_bytes);
 }
 
-// D[acc] = A(planes in TMEM) x B(streamed image with R rows): nchunks contraction chunks, 3 split products
-__device__ __forceinline__ void ctrl_gemm_ts(Ctrl& cref, int nchunks_, int R_) {
+// D[acc region] = A(planes in the other region) x B(streamed image with R rows): nchunks contraction chunks, 3 split
+// products per chunk.  chunked: the A planes come chunk by chunk from an in-place epilogue (a_chunk[s]), otherwise they
+// were published at once (a_all).  toggles: the epilogue converts the accumulator in place into the planes of the next
+// product (the regions then swap roles).
+__device__ __forceinline__ void ctrl_gemm_ts(Ctrl& cref, int nchunks_, int R_, bool chunked_, bool toggles) {
     Ctrl c = cref;                                                       // registers for the issue loop
     // everything an MMA / commit operand is computed from goes through a lane-0 broadcast: the compiler then knows the
     // values are warp-uniform (the state lives in per-thread local memory across the noinline callers)
     const int nchunks = (int)warp_uniform((uint32_t)nchunks_), R = (int)warp_uniform((uint32_t)R_);
+    const bool chunked = warp_uniform(chunked_ ? 1u : 0u) != 0;
     const uint32_t tmem = warp_uniform(c.tmem), nslot = warp_uniform(c.nslot), slot_bytes = warp_uniform(c.slot_bytes);
     const uint32_t ring0 = warp_uniform(smem_u32(c.ring)), full0 = warp_uniform(smem_u32(c.full)), empty0 = warp_uniform(smem_u32(c.empty));
-    const uint32_t accf = warp_uniform(smem_u32(c.acc_full));
+    const uint32_t accf = warp_uniform(smem_u32(c.acc_full)), aall = warp_uniform(smem_u32(c.a_all)), achk = warp_uniform(smem_u32(c.a_chunk));
     uint32_t mm_slot = warp_uniform(c.mm_slot), mm_use = warp_uniform(c.mm_use);
+    uint32_t sync = warp_uniform(c.sync);
+    const uint32_t reg = sync >> 31;
+    const uint32_t t_in = tmem + COL_REG * reg, t_out = tmem + COL_REG * (reg ^ 1u);
+    const int g = tc_group(R, (int)slot_bytes);
     const uint32_t idesc = idesc_bf16(128, R, 0, 0);
-    ctrl_request(c);
-    TC_STAT(const long long t0 = clock64();)
-    mbar_wait(c.a_ready, c.op_count & 1);
-    TC_STAT(const long long ti0 = clock64(); c.t_aready += ti0 - t0;)
-    ++c.n_ops;
-    tc_fence_after();
     const uint32_t lbo = (R >> 3) * 128;
     const uint64_t dlo = ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) | ((uint64_t)(128 >> 4) << 32) | (1ull << 46);
-    for (int s = 0; s < nchunks; ++s) {
+    ctrl_request(c);
+    TC_STAT(const long long t0 = clock64();)
+    if (!chunked) {
+        mbar_wait_u32(aall, (sync >> 16) & 1u);
+        sync ^= SY_ALL;
+        tc_fence_after();
+    }
+    TC_STAT(const long long ti0 = clock64(); c.t_aready += ti0 - t0;)
+    ++c.n_ops;
+    for (int s0 = 0; s0 < nchunks; s0 += g) {
         mbar_wait_u32(full0 + mm_slot * 8, mm_use & 1);
-        const uint32_t sb = ring0 + mm_slot * slot_bytes;
-        const uint64_t bhi = dlo | (uint64_t)((sb >> 4) & 0x3FFF), blo = dlo | (uint64_t)(((sb + R * 32) >> 4) & 0x3FFF);
-        const uint32_t ahi = tmem + COL_AHI + s * 8, alo = tmem + COL_ALO + s * 8;
-        if (elect_one()) {
-            mma_ts(tmem + COL_ACC, ahi, bhi, idesc, s > 0);
-            mma_ts(tmem + COL_ACC, ahi, blo, idesc, 1);
-            mma_ts(tmem + COL_ACC, alo, bhi, idesc, 1);
-            tc_commit_u32(empty0 + mm_slot * 8);
+        const uint32_t sb0 = ring0 + mm_slot * slot_bytes;
+        const int n = (nchunks - s0) < g ? (nchunks - s0) : g;
+        for (int j = 0; j < n; ++j) {
+            const int s = s0 + j;
+            if (chunked) {
+                TC_STAT(const long long tw = clock64();)
+                mbar_wait_u32(achk + 8 * s, (sync >> s) & 1u);
+                TC_STAT(c.t_aready += clock64() - tw;)
+                sync ^= 1u << s;
+                tc_fence_after();
+            }
+            const uint32_t sb = sb0 + j * R * 64;
+            const uint64_t bhi = dlo | (uint64_t)((sb >> 4) & 0x3FFF), blo = dlo | (uint64_t)(((sb + R * 32) >> 4) & 0x3FFF);
+            const uint32_t ahi = t_in + s * 16, alo = t_in + s * 16 + 8;
+            if (elect_one()) {
+                mma_ts(t_out, ahi, bhi, idesc, s > 0);
+                mma_ts(t_out, ahi, blo, idesc, 1);
+                mma_ts(t_out, alo, bhi, idesc, 1);
+            }
         }
+        if (elect_one()) tc_commit_u32(empty0 + mm_slot * 8);
         ++c.n_consumed;
         if (++mm_slot == nslot) { mm_slot = 0; ++mm_use; }
         ctrl_request(c);
@@ -284,19 +342,23 @@ __device__ __forceinline__ void ctrl_gemm_ts(Ctrl& cref, int nchunks_, int R_) {
     if (elect_one()) tc_commit_u32(accf);
     TC_STAT(c.t_issue += clock64() - ti0;)
     ++c.op_count;
+    if (toggles) sync ^= SY_REG;
+    c.sync = sync;
     c.mm_slot = mm_slot; c.mm_use = mm_use;
     cref = c;
 }
 
+// forward products of layers 0..upto: the first reads planes the path threads wrote themselves (y0), the others follow
+// an in-place epilogue
 static __device__ __noinline__ void ctrl_net_forward(Ctrl& c, const TcNet& t, int upto) {
-    for (int l = 0; l <= upto; ++l) ctrl_gemm_ts(c, t.ly[l].K16 / 16, t.ly[l].N16);
+    for (int l = 0; l <= upto; ++l) ctrl_gemm_ts(c, t.ly[l].K16 / 16, t.ly[l].N16, l > 0, l < t.L);
 }
 
 // ---------------------------------------------------------------------------------- path-thread side
 struct PathCtx {
     uint32_t tl;                   // TMEM address of this thread's lane (column 0)
-    uint32_t acc_full, a_ready;    // shared-memory addresses of the two hand-off barriers
-    uint32_t op_count;
+    uint32_t bars;                 // shared-memory address of the hand-off barriers: acc_full, a_all, a_chunk[16] (8 bytes each)
+    uint32_t sync;                 // parity bits of the hand-off barriers + TMEM region bit (layout: see SY_* above)
     int grp;                       // 0: threads 0..127, 1: threads 128..255 (chunk parity this thread handles)
     TC_STAT(long long t_accw, t_mark;)      // cycles spent waiting for the tensor pipe; time of the last wake-up
     TC_STAT(long long t_epi, t_hid;)        // t_hid: cycles inside hidden-layer epilogues only
@@ -312,20 +374,33 @@ typedef PathCtx& PathArg;
 typedef PathCtx PathArg;
 #endif
 
-// A planes written and accumulator drained: one arrival per path warp (a_ready counts the 8 path warps)
+__device__ __forceinline__ uint32_t path_planes(const PathCtx& p) { return p.tl + COL_REG * (p.sync >> 31); }             // A planes of the next product
+__device__ __forceinline__ uint32_t path_acc(const PathCtx& p) { return p.tl + COL_REG * ((p.sync >> 31) ^ 1u); }         // its accumulator
+
+// Everything the next product needs is in place (planes written by this thread / accumulator drained): one arrival per
+// path warp on a_all.
 __device__ __forceinline__ void path_publish(PathCtx& p) {
     tmem_st_wait();
     tc_fence_before();
     __syncwarp();
-    if ((threadIdx.x & 31) == 0) mbar_arrive_u32(p.a_ready);
+    if ((threadIdx.x & 31) == 0) mbar_arrive_u32(p.bars + 8);
+    p.sync ^= SY_ALL;
     TC_STAT(p.t_epi += clock64() - p.t_mark;)
 }
+// planes of chunk c of an in-place epilogue are written: one arrival per warp of the group that owns the chunk
+__device__ __forceinline__ void path_publish_chunk(const PathCtx& p, int c) {
+    tmem_st_wait();
+    tc_fence_before();
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) mbar_arrive_u32(p.bars + 16 + 8 * c);
+}
+// wait for the commit of the current product
 __device__ __forceinline__ void path_wait_acc(PathCtx& p) {
     TC_STAT(const long long t0 = clock64();)
-    mbar_wait_u32(p.acc_full, p.op_count & 1);
+    mbar_wait_u32(p.bars, (p.sync >> 17) & 1u);
     TC_STAT(p.t_mark = clock64(); p.t_accw += p.t_mark - t0;)
+    p.sync ^= SY_ACC;
     tc_fence_after();
-    ++p.op_count;
 }
 
 // Packed FP32 pairs (sm_100: FFMA2 / FADD2, one instruction for two IEEE operations -- same bits as the scalar forms).
@@ -349,34 +424,61 @@ __device__ __forceinline__ void split16(const float* v, uint32_t* h, uint32_t* l
         l[j] = *reinterpret_cast<const uint32_t*>(&ll);
     }
 }
-// features 16c .. 16c+15 of this thread's row -> hi / lo planes
-__device__ __forceinline__ void put16(uint32_t tl, int c, const float* v) {
+// 16 features of this thread's row -> hi / lo planes of their chunk: tc = TMEM address of the chunk's 16 columns
+__device__ __forceinline__ void put16(uint32_t tc, const float* v) {
     uint32_t h[8], l[8];
     split16(v, h, l);
-    tmem_st8(tl + COL_AHI + c * 8, h);
-    tmem_st8(tl + COL_ALO + c * 8, l);
+    tmem_st8(tc, h);
+    tmem_st8(tc + 8, l);
 }
 // same, also returning the hi words (for the bf16 copies)
-__device__ __forceinline__ void put16h(uint32_t tl, int c, const float* v, uint32_t* h) {
+__device__ __forceinline__ void put16h(uint32_t tc, const float* v, uint32_t* h) {
     uint32_t l[8];
     split16(v, h, l);
-    tmem_st8(tl + COL_AHI + c * 8, h);
-    tmem_st8(tl + COL_ALO + c * 8, l);
+    tmem_st8(tc, h);
+    tmem_st8(tc + 8, l);
 }
 
-// accumulator columns [0, 16*nchunks) of this thread's lane, 16 at a time, the TMEM load of chunk c+1 in
-// flight while chunk c is processed:  f(c, const uint32_t r[16])
+// In-place epilogue of a product with `nco` output chunks: wait for its commit, hand the chunks of this thread's group
+// (c % TC_NGRP == grp) to f(c, r[16], tc) -- r = the 16 accumulator columns, tc = their TMEM address, where f stores the
+// planes of the next product.  mode: EPI_CHUNKS publishes every chunk on its own barrier (the next product starts on it
+// at once); EPI_ALL publishes once at the end (the next product is a dW product, which needs everything); EPI_NONE leaves
+// the publishing to the caller.  fence: what f wrote besides TMEM and the async proxy reads later (dW operands, bulk
+// copies): 0 nothing, 1 shared memory, 2 global memory; the proxy fence is issued at the end, before the arrival (of this
+// or of a later publish on a_all) that the consumer of those bytes waits for.
+enum { EPI_NONE = 0, EPI_CHUNKS = 1, EPI_ALL = 2 };
 template <class F>
-__device__ __forceinline__ void for_acc_chunks(uint32_t tl, int first, int nchunks, F f) {
+__device__ __forceinline__ void for_acc_chunks(PathCtx& p, int nco, int mode, int fence, F f) {
     // (the TMEM->register path is the bound of every epilogue -- 64 B/clk/SM, see DESIGN.md -- so a plain loop does as
-    //  well as a software-pipelined one and needs 16 registers fewer; re-measured with one thread per path and 255
-    //  registers: the double-buffered loop spills twice as much and the actor kernel runs 12 % slower)
-    uint32_t ra[16];
-    for (int c = first; c < nchunks; c += TC_NGRP) {
-        tmem_ld16(tl + COL_ACC + 16 * c, ra);
-        tmem_ld_wait();
-        f(c, ra);
+    //  well as a software-pipelined one and needs 16 registers fewer)
+    path_wait_acc(p);
+    // Every path warp takes part in the hand-off of chunk 0 (the owners when its planes are written, the others here, as
+    // soon as they have seen the commit): the next product cannot be committed before all warps have observed this one.
+    // Without it a warp that owns no chunk of a narrow output (one chunk: the other group's) could fall two phases behind
+    // on acc_full and wait for a parity that has already come round again.
+    if (TC_NGRP > 1 && mode == EPI_CHUNKS && p.grp != 0) {
+        __syncwarp();
+        if ((threadIdx.x & 31) == 0) mbar_arrive_u32(p.bars + 16);
     }
+    const uint32_t acc = path_acc(p);
+    uint32_t ra[16];
+    int pend = -1;                                      // chunk whose stores are in flight (published after the next load)
+    for (int c = p.grp; c < nco; c += TC_NGRP) {
+        tmem_ld16(acc + 16 * c, ra);
+        tmem_ld_wait();
+        if (pend >= 0) path_publish_chunk(p, pend);     // (its stores completed under the latency of the load)
+        f(c, ra, acc + 16 * c);
+        if (mode == EPI_CHUNKS) {
+            if (c < TC_NGRP) { path_publish_chunk(p, c); pend = -1; }       // first chunk: at once -- the next product starts on it
+            else pend = c;
+        }
+    }
+    if (pend >= 0) path_publish_chunk(p, pend);
+    if (mode == EPI_CHUNKS) p.sync ^= (1u << nco) - 1u;                    // every a_chunk[c], c < nco, completed a phase
+    if (fence == 1) fence_proxy_async(); else if (fence == 2) fence_proxy_async_global();
+    p.sync ^= SY_REG;
+    if (mode == EPI_ALL) path_publish(p);
+    TC_STAT(else p.t_epi += clock64() - p.t_mark;)
 }
 
 // z = acc * gc + bb for 16 features (gc, bb: 16-byte aligned shared memory)
@@ -421,7 +523,7 @@ __device__ __forceinline__ void path_put_y0(PathCtx& p, const TcNet& t, const fl
                 const int k = 16 * c + j;
                 v[j] = (k < NX && k < t.in) ? x[k < NX ? k : 0] * g0c[k] + b0[k] : 0.f;
             }
-            put16h(p.tl, c, v, h);
+            put16h(path_planes(p) + 16 * c, v, h);
             if (copies) copy16h(copies, row, c, h, t.ly[0].kl);
         }
     }
@@ -431,19 +533,17 @@ __device__ __forceinline__ void path_put_y0(PathCtx& p, const TcNet& t, const fl
 
 // hidden layer epilogue: a = z + relu(z), z = acc * gc + bb (solver.py:267-269) -> planes
 __device__ __forceinline__ void path_epi_hidden(PathCtx& p, const float* gcbb, int N16) {
-    path_wait_acc(p);
     TC_STAT(const long long th0 = clock64();)
     const float* gc = gcbb;
     const float* bb = gcbb + N16;
-    for_acc_chunks(p.tl, p.grp, N16 / 16, [&](int c, const uint32_t* r) {
+    for_acc_chunks(p, N16 / 16, EPI_CHUNKS, 0, [&](int c, const uint32_t* r, uint32_t tc) {
         float v[16];
         affine16(r, gc + 16 * c, bb + 16 * c, v);
 #pragma unroll
         for (int j = 0; j < 8; ++j)
             up2(add2(pk2(v[2 * j], v[2 * j + 1]), pk2(fmaxf(v[2 * j], 0.f), fmaxf(v[2 * j + 1], 0.f))), v[2 * j], v[2 * j + 1]);
-        put16(p.tl, c, v);
+        put16(tc, v);
     });
-    path_publish(p);
     TC_STAT(p.t_hid += clock64() - th0;)
 }
 
@@ -451,13 +551,14 @@ __device__ __forceinline__ void path_epi_hidden(PathCtx& p, const float* gcbb, i
 template <int NO>
 __device__ __forceinline__ void path_last(PathCtx& p, const float* gcbb, int N16, int nl, float (&out)[NO]) {
     path_wait_acc(p);
+    const uint32_t acc = path_acc(p);
     const float* gc = gcbb;
     const float* bb = gcbb + N16;
 #pragma unroll
     for (int c = 0; c < 2; ++c) {
         if (c < N16 / 16) {
             uint32_t r[16];
-            tmem_ld16(p.tl + COL_ACC + 16 * c, r);
+            tmem_ld16(acc + 16 * c, r);
             tmem_ld_wait();
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
@@ -472,9 +573,9 @@ __device__ __forceinline__ void path_last(PathCtx& p, const float* gcbb, int N16
 // own per-path arithmetic between two ranges: it then runs while the tensor pipe works on the layer just published.
 static __device__ __noinline__ uint32_t path_hidden_range_(PathArg p, const TcNet& t, const float* vec, int l0, int l1) {
     for (int l = l0; l < l1 && l < t.L; ++l) path_epi_hidden(p, vec + t.ly[l].vec, t.ly[l].N16);
-    return p.op_count;
+    return p.sync;
 }
-__device__ __forceinline__ void path_hidden_range(PathCtx& p, const TcNet& t, const float* vec, int l0, int l1) { p.op_count = path_hidden_range_(p, t, vec, l0, l1); }
+__device__ __forceinline__ void path_hidden_range(PathCtx& p, const TcNet& t, const float* vec, int l0, int l1) { p.sync = path_hidden_range_(p, t, vec, l0, l1); }
 
 // forward-only evaluation:  begin (y0 -> planes)  ...caller's own arithmetic...  finish (-> raw output)
 template <int NX>
@@ -550,8 +651,8 @@ static __global__ void tc_finalize_grad_kernel(TcNet t, TcSlab g, const float* _
 }
 
 // ---- control thread ----------------------------------------------------------------------------------
-__device__ __forceinline__ void sched_add_bwd(Sched* s, const TcNet& t, const unsigned char* img) {
-    for (int l = t.L; l >= 0; --l) sched_add(s, img + t.ly[l].img_b, t.ly[l].N16 / 16, t.ly[l].K16 * 64);
+__device__ __forceinline__ void sched_add_bwd(Ctrl& c, const TcNet& t, const unsigned char* img) {
+    for (int l = t.L; l >= 0; --l) sched_add_op(c.sch, img + t.ly[l].img_b, t.ly[l].N16 / 16, t.ly[l].K16, (int)c.slot_bytes);
 }
 
 // global copy scratch -> ACT (bulk copy; waits until it has landed)
@@ -568,24 +669,29 @@ __device__ __forceinline__ void ctrl_act_wait(Ctrl& c) {
     ++c.act_count;
 }
 
-// D[acc] (rows = features 128*blk .. of ACT, cols = N16 features of DZ) = ACT^T DZ over the 128 paths
+// D[acc] (rows = features 128*blk .. of ACT, cols = N16 features of DZ) = ACT^T DZ over the 128 paths.  The accumulator
+// is the region the next dX product will write (the other one holds the dz planes that product reads).
 __device__ __forceinline__ void ctrl_gemm_dw(Ctrl& c, int blk_, int N16_) {
     const int blk = (int)warp_uniform((uint32_t)blk_), N16 = (int)warp_uniform((uint32_t)N16_);
     const uint32_t idesc = idesc_bf16(128, N16, 1, 1);
+    uint32_t sync = warp_uniform(c.sync);
     TC_STAT(const long long t0 = clock64();)
-    mbar_wait(c.a_ready, c.op_count & 1);
+    mbar_wait(c.a_all, (sync >> 16) & 1u);                              // operands complete / previous block drained
+    sync ^= SY_ALL;
     TC_STAT(c.t_dw_ready += clock64() - t0;)
     tc_fence_after();
     const uint32_t a0 = warp_uniform(smem_u32(c.act)) + blk * 16 * 2048, b0 = warp_uniform(smem_u32(c.dz));
     const uint32_t tmem = warp_uniform(c.tmem), accf = warp_uniform(smem_u32(c.acc_full));
+    const uint32_t dcol = tmem + COL_REG * ((sync >> 31) ^ 1u);
     if (elect_one()) {
 #pragma unroll
         for (int s = 0; s < TC_PATHS / 16; ++s) {
             const uint64_t ad = smem_desc(a0 + s * 256, 128, 2048), bd = smem_desc(b0 + s * 256, 128, 2048);
-            mma_ss(tmem + COL_ACC, ad, bd, idesc, s > 0);
+            mma_ss(dcol, ad, bd, idesc, s > 0);
         }
         tc_commit_u32(accf);
     }
+    c.sync = sync;
     ++c.op_count;
 }
 
@@ -604,7 +710,8 @@ static __device__ __noinline__ void ctrl_net_backward(Ctrl& c, const TcNet& t, b
                 ctrl_act_load(c, copies + tc_copy_off(t, l - 1), (uint32_t)(TC_PATHS * t.ly[l - 1].K16 * 2));
             }
         }
-        ctrl_gemm_ts(c, t.ly[l].N16 / 16, t.ly[l].K16);                  // dA_l = dz_l x (W_l gamma c)^T
+        // dA_l = dz_l x (W_l gamma c)^T; its planes come chunk by chunk only in a chain without dW products
+        ctrl_gemm_ts(c, t.ly[l].N16 / 16, t.ly[l].K16, !need_w && l < t.L, l > 0);
     }
 }
 
@@ -627,8 +734,8 @@ static __device__ __noinline__ uint32_t path_hidden_keep_(PathArg p, const TcNet
         const bool last_hidden = (l == t.L - 1);
         unsigned char* dst = last_hidden ? act : (copies ? copies + tc_copy_off(t, l + 1) : nullptr);
         const int one_at = t.ly[l + 1].kl;
-        path_wait_acc(p);
-        for_acc_chunks(p.tl, p.grp, N16 / 16, [&](int c, const uint32_t* r) {
+        const bool planes = !(last_hidden && skip_last);                 // (skip_last: nothing reads a_L as an MMA operand)
+        for_acc_chunks(p, N16 / 16, planes ? EPI_CHUNKS : EPI_NONE, dst ? (last_hidden ? 1 : 2) : 0, [&](int c, const uint32_t* r, uint32_t tc) {
             float v[16];
             uint32_t h[8];
             affine16(r, gc + 16 * c, bb + 16 * c, v);
@@ -639,20 +746,16 @@ static __device__ __noinline__ uint32_t path_hidden_keep_(PathArg p, const TcNet
             for (int j = 0; j < 8; ++j)
                 up2(add2(pk2(v[2 * j], v[2 * j + 1]), pk2(fmaxf(v[2 * j], 0.f), fmaxf(v[2 * j + 1], 0.f))), v[2 * j], v[2 * j + 1]);
             mk.h[l + 1][c] = bits;
-            put16h(p.tl, c, v, h);
-            if (dst) copy16h(dst, row, c, h, one_at);
+            if (planes) put16h(tc, v, h);
+            else { uint32_t lo[8]; split16(v, h, lo); }
+            if (dst) copy16h(dst, row, c, h, one_at);                    // (shared ACT image / global copy scratch)
         });
-        if (dst) {
-            if (last_hidden) fence_proxy_async();                    // shared ACT image
-            else fence_proxy_async_global();                         // global copy scratch
-        }
-        if (!(last_hidden && skip_last)) path_publish(p);
     }
-    return p.op_count;
+    return p.sync;
 }
 __device__ __forceinline__ void path_hidden_keep(PathCtx& p, const TcNet& t, const float* vec, Masks& mk, unsigned char* copies,
                                                  unsigned char* act, int row, bool skip_last) {
-    p.op_count = path_hidden_keep_(p, t, vec, mk, copies, act, row, skip_last);
+    p.sync = path_hidden_keep_(p, t, vec, mk, copies, act, row, skip_last);
 }
 // x -> (masks, copies) [-> raw output]
 template <int NX, int NO>
@@ -666,6 +769,7 @@ __device__ __forceinline__ void path_net_forward_keep(PathCtx& p, const TcNet& t
 // this thread's row of a dW block -> RED into the slab:  rows f = 128*blk + row (f <= kl), cols n < nl
 __device__ __forceinline__ void path_drain(PathCtx& p, int blk, int row, int kl, int nl, int N16, float* slab) {
     path_wait_acc(p);
+    const uint32_t acc = path_acc(p);
     TC_STAT(const long long td0 = clock64();)
     const int f = 128 * blk + row;
     float* dst = slab + (long long)f * 4;
@@ -676,7 +780,7 @@ __device__ __forceinline__ void path_drain(PathCtx& p, int blk, int row, int kl,
     const bool warp_live = (128 * blk + (row & ~31)) <= kl;
     for (int c = p.grp; warp_live && c < N16 / 16; c += TC_NGRP) {
         uint32_t r[16];
-        tmem_ld16(p.tl + COL_ACC + 16 * c, r);
+        tmem_ld16(acc + 16 * c, r);
         tmem_ld_wait();
         if (!rowok) continue;
 #pragma unroll
@@ -687,7 +791,8 @@ __device__ __forceinline__ void path_drain(PathCtx& p, int blk, int row, int kl,
     }
     tc_fence_before();
     __syncwarp();
-    if ((threadIdx.x & 31) == 0) mbar_arrive_u32(p.a_ready);   // accumulator drained
+    if ((threadIdx.x & 31) == 0) mbar_arrive_u32(p.bars + 8);    // accumulator drained (a_all)
+    p.sync ^= SY_ALL;
     TC_STAT(p.t_drain += clock64() - td0;)
 }
 
@@ -705,7 +810,7 @@ __device__ __forceinline__ void path_put_dz(PathCtx& p, const TcNet& t, const fl
                 const int n = 16 * c + j;
                 v[j] = (n < NO && n < nl) ? dout[n < NO ? n : 0] : 0.f;
             }
-            put16h(p.tl, c, v, h);
+            put16h(path_planes(p) + 16 * c, v, h);
             if (dzimg) copy16h(dzimg, row, c, h, -1);
         }
     }
@@ -724,11 +829,9 @@ static __device__ __noinline__ uint32_t path_backward_mid_(PathArg p, const TcNe
         }
         if (l == 0) break;
         const int K16 = t.ly[l].K16;
-        uint32_t nbits = mk.h[l][p.grp];                                 // (fetched while the product is still running)
-        path_wait_acc(p);                                                // dA_l in the accumulator (K16_l columns)
-        for_acc_chunks(p.tl, p.grp, K16 / 16, [&](int c, const uint32_t* r) {
-            const uint32_t bits = nbits;
-            if (c + TC_NGRP < K16 / 16) nbits = mk.h[l][c + TC_NGRP];
+        // dA_l in the accumulator (K16_l columns) -> dz_{l-1} planes in place (+ DZ image)
+        for_acc_chunks(p, K16 / 16, need_w ? EPI_ALL : EPI_CHUNKS, need_w ? 1 : 0, [&](int c, const uint32_t* r, uint32_t tc) {
+            const uint32_t bits = mk.h[l][c];
             float v[16];
             uint32_t h[8];
 #pragma unroll
@@ -736,28 +839,27 @@ static __device__ __noinline__ uint32_t path_backward_mid_(PathArg p, const TcNe
                 const float a = __uint_as_float(r[j]);
                 v[j] = ((bits >> j) & 1u) ? 2.f * a : a;                     // d(z + relu z)
             }
-            put16h(p.tl, c, v, h);
+            put16h(tc, v, h);
             if (need_w) copy16h(dzimg, row, c, h, -1);
         });
-        if (need_w) fence_proxy_async();
-        path_publish(p);
     }
-    return p.op_count;
+    return p.sync;
 }
 __device__ __forceinline__ void path_backward_mid(PathCtx& p, const TcNet& t, const TcSlab& g, const Masks& mk, bool need_w, float* slab,
                                                   unsigned char* dzimg, int row) {
-    p.op_count = path_backward_mid_(p, t, g, mk, need_w, slab, dzimg, row);
+    p.sync = path_backward_mid_(p, t, g, mk, need_w, slab, dzimg, row);
 }
 // cotangent of y0 (in <= 31 values, static indexing)
 template <int NX>
 __device__ __forceinline__ void path_get_dy0(PathCtx& p, const TcNet& t, float (&dy0)[NX]) {
     path_wait_acc(p);
+    const uint32_t acc = path_acc(p);
     const int K16 = t.ly[0].K16;
 #pragma unroll
     for (int c = 0; c < 2; ++c) {
         if (c < K16 / 16) {
             uint32_t r[16];
-            tmem_ld16(p.tl + COL_ACC + 16 * c, r);
+            tmem_ld16(acc + 16 * c, r);
             tmem_ld_wait();
 #pragma unroll
             for (int j = 0; j < 16; ++j) {

@@ -185,23 +185,64 @@ __global__ void tc_epilogue_bench_kernel(long long* out, int rounds, int ngroups
     }
     __syncthreads();
     const long long t0 = clock64();
-    for (int r = 0; r < rounds; ++r) {
+    for (int r = 0; r < rounds; ++r) {                       // (after round 0 the columns hold bf16 pairs: same work)
         const float* gc = gcbb;
         const float* bb = gcbb + 208;
         uint32_t ra[16];
         for (int c = grp; c < 13; c += ngroups) {
-            tmem_ld16(tl + COL_ACC + 16 * c, ra);
+            tmem_ld16(tl + 16 * c, ra);
             tmem_ld_wait();
             float v[16];
             affine16(ra, gc + 16 * c, bb + 16 * c, v);
 #pragma unroll
             for (int j = 0; j < 16; ++j) v[j] = v[j] + fmaxf(v[j], 0.f);
-            put16(tl, c, v);
+            put16(tl + 16 * c, v);                           // in place, as the kernels do
         }
         tmem_st_wait();
         __syncthreads();
     }
     if (tid == 0) { out[0] = (clock64() - t0) / rounds; out[1] = rounds; }
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tbase, 512);
+}
+
+// Cost of one tcgen05.mma (kind::f16, M=128, K=16, FP32 accumulation) as a function of N, issued back to back by one thread
+// with both operands in place: ts = 1 reads A from tensor memory, 0 from shared memory.  `per_commit` MMAs are followed by
+// one tcgen05.commit (as the weight-ring loop does).  out[0] = cycles per MMA (issue of the first to completion of the last).
+__global__ void __launch_bounds__(128, 1) tc_mma_bench_kernel(long long* out, int n, int rounds, int ts, int per_commit) {
+    extern __shared__ __align__(1024) unsigned char smem[];            // A image 128 x 16 (4 KB) + B image n x 16
+    __shared__ __align__(8) uint64_t bars[2];
+    __shared__ uint32_t tslot;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    for (int i = tid; i < (4096 + n * 32) / 4; i += 128) reinterpret_cast<uint32_t*>(smem)[i] = 0u;
+    if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); fence_barrier_init(); }
+    if (warp == 0) tmem_alloc(&tslot, 512);
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tbase = tslot;
+    if (warp == 0) {
+        const uint32_t idesc = idesc_bf16(128, n, 0, 0);
+        const uint64_t ad = smem_desc(smem_u32(smem), 2048, 128), bd = smem_desc(smem_u32(smem) + 4096, (n >> 3) * 128, 128);
+        const long long t0 = clock64();
+        for (int r = 0; r < rounds; ++r) {
+            if (elect_one()) {
+                for (int j = 0; j < per_commit; ++j) {
+                    if (ts) mma_ts(tbase, tbase + 256 + (j & 7) * 8, bd, idesc, 1);
+                    else mma_ss(tbase, ad, bd, idesc, 1);
+                }
+                tc_commit(&bars[1]);
+            }
+            __syncwarp();
+        }
+        if (elect_one()) tc_commit(&bars[0]);
+        const long long t1 = clock64();
+        mbar_wait(&bars[0], 0);
+        const long long t2 = clock64();
+        if (tid == 0) { out[0] = (t2 - t0) / ((long long)rounds * per_commit); out[1] = (t1 - t0) / ((long long)rounds * per_commit); }
+    }
+    tc_fence_before();
     __syncthreads();
     if (warp == 0) tmem_dealloc(tbase, 512);
 }

@@ -192,6 +192,11 @@ int dpb_tc_handshake_cycles(int64_t* out_host, int rounds);
  * bf16 hi/lo split, TMEM stores) with `ngroups` (1..4) groups of 4 warps sharing the chunks; out_host[0] = cycles. */
 int dpb_tc_epilogue_cycles(int64_t* out_host, int rounds, int ngroups);
 
+/* Diagnostic (tensor path): cycles per tcgen05.mma (M=128, K=16, bf16, FP32 accumulation) with N = n output columns, issued
+ * back to back by one thread, `per_commit` MMAs per tcgen05.commit; ts = 1: A operand in tensor memory, 0: shared memory.
+ * out_host[0] = cycles per MMA until the last one completed, out_host[1] = cycles per MMA spent issuing. */
+int dpb_tc_mma_cycles(int64_t* out_host, int n, int rounds, int ts, int per_commit);
+
 /* Diagnostic (tensor path): cycle counters of CTA 0 of the last critic/actor launch that used `workspace`
  * (synchronous copy): [0] kernel cycles, [1] control thread waiting for the path threads, [3] tensor-pipe ops,
  * [4] path thread 0 waiting for the tensor pipe, [5] its epilogue cycles, [6] of which hidden-layer epilogues,
