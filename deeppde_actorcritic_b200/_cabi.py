@@ -82,7 +82,7 @@ SYMBOLS = {
     "dpb_last_kernel_ms": (_D, [_P]),
     "dpb_tc_selftest": (C.c_int, [_P, _P, _P, C.c_int, _P]),
     "dpb_tc_handshake_cycles": (C.c_int, [_P, C.c_int]),
-    "dpb_tc_epilogue_cycles": (C.c_int, [_P, C.c_int, C.c_int]),
+    "dpb_tc_epilogue_cycles": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int]),
     "dpb_tc_stats": (C.c_int, [_P, _P, _I64, _I32, _P]),
     "dpb_tc_mma_cycles": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int]),
 }

@@ -802,13 +802,13 @@ extern "C" int dpb_tc_handshake_cycles(int64_t* out_host, int rounds) {
     return DPB_OK;
 }
 
-extern "C" int dpb_tc_epilogue_cycles(int64_t* out_host, int rounds, int ngroups) {
+extern "C" int dpb_tc_epilogue_cycles(int64_t* out_host, int rounds, int ngroups, int with_mma, int publish) {
     if (!out_host || rounds < 1 || ngroups < 1 || ngroups > 4) return fail(nullptr, DPB_ERR_ARG, "dpb_tc_epilogue_cycles: bad argument");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) { cudaGetLastError(); return fail(nullptr, DPB_ERR_CUDA, "dpb_tc_epilogue_cycles: no CUDA device"); }
     long long* d = nullptr;
     DPB_CUDA(nullptr, cudaMalloc(&d, 16));
-    tc::tc_epilogue_bench_kernel<<<1, 128 * ngroups>>>(d, rounds, ngroups);
+    tc::tc_epilogue_bench_kernel<<<1, 128 * ngroups + 32>>>(d, rounds, ngroups, with_mma, publish);
     cudaError_t e = cudaMemcpy(out_host, d, 16, cudaMemcpyDeviceToHost);
     cudaFree(d);
     if (e != cudaSuccess) return fail(nullptr, DPB_ERR_CUDA, std::string("dpb_tc_epilogue_cycles: ") + cudaGetErrorString(e));

@@ -163,45 +163,88 @@ __global__ void __launch_bounds__(288, 1) tc_handshake_kernel(long long* out, in
 
 
 // Cost of one hidden-layer epilogue (13 chunks of 16 columns: TMEM load, affine + y+relu(y), bf16 hi/lo split,
-// two TMEM stores) when `ngroups` groups of 4 warps share the chunks of the 128 lanes.  No MMAs, no barriers:
-// the pure path-thread work.  out[0] = cycles per epilogue.
-__global__ void tc_epilogue_bench_kernel(long long* out, int rounds, int ngroups) {
+// two TMEM stores in place) when `ngroups` groups of 4 warps share the chunks of the 128 lanes.  No hand-off barriers: the
+// pure path-thread work.  with_mma: one more warp issues back-to-back N=208 tcgen05.mma (A and D in the other TMEM region)
+// for the whole time -- what the epilogue costs while the tensor pipe is busy with the next layer.  publish: 1 = every
+// chunk is followed by the publish sequence of the kernels (wait::st, fence, __syncwarp, mbarrier arrive).
+// out[0] = cycles per epilogue.
+__global__ void tc_epilogue_bench_kernel(long long* out, int rounds, int ngroups, int with_mma, int publish) {
     __shared__ __align__(16) float gcbb[2 * 208];
+    __shared__ __align__(1024) unsigned char bimg[208 * 32];
+    __shared__ __align__(8) uint64_t bars[2];
     __shared__ uint32_t tslot;
+    __shared__ volatile int stop;
     const int tid = threadIdx.x, warp = tid >> 5;
+    const int nepi = 4 * ngroups;                            // epilogue warps; warp nepi (if present) issues the MMAs
     for (int i = tid; i < 416; i += blockDim.x) gcbb[i] = 0.5f + 0.001f * i;
+    for (int i = tid; i < 208 * 32 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(bimg)[i] = 0u;
+    if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], (1u << 20) - 1u); stop = 0; fence_barrier_init(); }
     if (warp == 0) tmem_alloc(&tslot, 512);
+    fence_proxy_async();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tbase = tslot;
     const uint32_t tl = tbase + ((uint32_t)((warp & 3) * 32) << 16);
     const int grp = warp >> 2;
-    {   // defined accumulator contents
+    if (warp < nepi) {   // defined accumulator contents
         uint32_t z[8];
         for (int j = 0; j < 8; ++j) z[j] = __float_as_uint(0.25f * (j - 3));
-        for (int c = 0; c < 32; ++c) tmem_st8(tl + 8 * c, z);
+        for (int c = 0; c < 64; ++c) tmem_st8(tl + 8 * c, z);
         tmem_st_wait();
     }
+    tc_fence_before();
     __syncthreads();
-    const long long t0 = clock64();
-    for (int r = 0; r < rounds; ++r) {                       // (after round 0 the columns hold bf16 pairs: same work)
-        const float* gc = gcbb;
-        const float* bb = gcbb + 208;
-        uint32_t ra[16];
-        for (int c = grp; c < 13; c += ngroups) {
-            tmem_ld16(tl + 16 * c, ra);
-            tmem_ld_wait();
-            float v[16];
-            affine16(ra, gc + 16 * c, bb + 16 * c, v);
-#pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = v[j] + fmaxf(v[j], 0.f);
-            put16(tl + 16 * c, v);                           // in place, as the kernels do
+    tc_fence_after();
+    if (warp == nepi) {
+        if (with_mma) {
+            const uint32_t idesc = idesc_bf16(128, 208, 0, 0);
+            const uint64_t bd = smem_desc(smem_u32(bimg), (208 >> 3) * 128, 128);
+            int it = 0;
+            while (!stop) {
+                if (elect_one()) {
+                    for (int j = 0; j < 13; ++j) mma_ts(tbase + 256, tbase + 256 + (j & 7) * 16, bd, idesc, 1);
+                    tc_commit(&bars[0]);
+                }
+                __syncwarp();
+                mbar_wait(&bars[0], it & 1);                 // at most 13 MMAs in flight
+                ++it;
+            }
         }
-        tmem_st_wait();
-        __syncthreads();
+    } else if (warp < nepi) {
+        const long long t0 = clock64();
+        for (int r = 0; r < rounds; ++r) {                       // (after round 0 the columns hold bf16 pairs: same work)
+            const float* gc = gcbb;
+            const float* bb = gcbb + 208;
+            uint32_t ra[16];
+            for (int c = grp; c < 13; c += ngroups) {
+                tmem_ld16(tl + 16 * c, ra);
+                tmem_ld_wait();
+                float v[16];
+                affine16(ra, gc + 16 * c, bb + 16 * c, v);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] = v[j] + fmaxf(v[j], 0.f);
+                if (publish & 2) {                               // round-1 layout: separate plane regions
+                    uint32_t h[8], l[8];
+                    split16(v, h, l);
+                    tmem_st8(tl + 256 + 8 * c, h);
+                    tmem_st8(tl + 384 + 8 * c, l);
+                } else {
+                    put16(tl + 16 * c, v);                       // in place, as the kernels do
+                }
+                if (publish & 1) {
+                    tmem_st_wait();
+                    tc_fence_before();
+                    __syncwarp();
+                    if ((tid & 31) == 0) mbar_arrive(&bars[1]);
+                }
+            }
+            tmem_st_wait();
+            asm volatile("bar.sync 1, %0;" ::"r"(nepi * 32) : "memory");
+        }
+        if (tid == 0) { out[0] = (clock64() - t0) / rounds; out[1] = rounds; stop = 1; }
     }
-    if (tid == 0) { out[0] = (clock64() - t0) / rounds; out[1] = rounds; }
+    tc_fence_before();
     __syncthreads();
     if (warp == 0) tmem_dealloc(tbase, 512);
 }

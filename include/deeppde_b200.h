@@ -189,8 +189,10 @@ int dpb_tc_selftest(const float* A, const float* B, float* D, int K, void* strea
 int dpb_tc_handshake_cycles(int64_t* out_host, int rounds);
 
 /* Diagnostic (tensor path): cycles of one 200-wide hidden-layer epilogue (13 chunks: TMEM load, affine + activation,
- * bf16 hi/lo split, TMEM stores) with `ngroups` (1..4) groups of 4 warps sharing the chunks; out_host[0] = cycles. */
-int dpb_tc_epilogue_cycles(int64_t* out_host, int rounds, int ngroups);
+ * bf16 hi/lo split, TMEM stores in place) with `ngroups` (1..4) groups of 4 warps sharing the chunks; with_mma = 1: while
+ * another warp keeps the tensor pipe busy with N=208 products; publish = 1: with the per-chunk publish sequence of the
+ * kernels.  out_host[0] = cycles. */
+int dpb_tc_epilogue_cycles(int64_t* out_host, int rounds, int ngroups, int with_mma, int publish);
 
 /* Diagnostic (tensor path): cycles per tcgen05.mma (M=128, K=16, bf16, FP32 accumulation) with N = n output columns, issued
  * back to back by one thread, `per_commit` MMAs per tcgen05.commit; ts = 1: A operand in tensor memory, 0: shared memory.

@@ -44,9 +44,11 @@ def test_tcgen05_handshake_latency():
     print("tcgen05 hand-off round trip:", int(out[0]), "cycles")
     assert out[1] == 2000 and 0 < out[0] < 100000
     for g in (1, 2, 3, 4):
-        assert lib.dpb_tc_epilogue_cycles(out.ctypes.data_as(C.c_void_p), 500, g) == 0, lib.dpb_last_error(None)
-        print(f"hidden-layer epilogue (200 wide) with {4 * g} warps: {int(out[0])} cycles")
-        assert 0 < out[0] < 1000000
+        for with_mma, publish in ((0, 2), (0, 0), (0, 1), (1, 2), (1, 0), (1, 1)):
+            assert lib.dpb_tc_epilogue_cycles(out.ctypes.data_as(C.c_void_p), 500, g, with_mma, publish) == 0, lib.dpb_last_error(None)
+            print(f"hidden-layer epilogue (200 wide) with {4 * g} warps, tensor pipe {'busy' if with_mma else 'idle'}, "
+                  f"{'per-chunk publish' if publish & 1 else 'no publish'}, {'separate plane columns' if publish & 2 else 'in place'}: {int(out[0])} cycles")
+            assert 0 < out[0] < 1000000
 
 
 # ------------------------------------------------------------------------------------------------
