@@ -14,10 +14,13 @@ ranks (strong scaling).  value = 2*B*N*K nominal path-steps / max-over-ranks dev
 value : inputs resident in HBM (x0/x_bdry sampled on the device, increments generated in-kernel).
 e2e   : the same iteration through the C-ABI host entry points with x0 / x_bdry coming from pinned
         HOST memory every step and the losses read back to the host inside the timed region.
-roofline : dominant kernel = critic_kernel; achieved = algorithmic FLOPs of SURVEY 8(d) for the live
-        path-steps of that launch / its CUDA-event duration; peak from MEASURED_PEAKS.json.
-cpu_baseline / --impl reference : the float64 torch-CPU restatement of the reference (oracle/), all
-        host threads, on a bounded sample (the config's own batch of 2048 paths).
+roofline : both rollout kernels are measured (roofline_kernels.critic / .actor: algorithmic FLOPs of SURVEY 8(d)
+        for the live path-steps of that launch / its CUDA-event duration, peak from MEASURED_PEAKS.json); `roofline`
+        is the one with the longer launch (the dominant kernel).  `traffic` is reported only when profiles/traffic.json
+        holds an ncu capture taken from exactly the kernel sources of this build (source hash), else null.
+cpu_baseline / --impl reference : the torch-CPU restatement of the reference (oracle/), all host threads, on a
+        bounded sample (the config's own batch of 2048 paths) -- float64 as the reference's configs ask, with the
+        float32 figure of the same port beside it; the reference line's `config` states the batch it really ran.
 """
 from __future__ import annotations
 
@@ -106,9 +109,9 @@ class ClockSampler(threading.Thread):
 
 
 # ----------------------------------------------------------------------------- CPU reference arm
-def cpu_reference(cfg, steps, warmup, sample_B=None):
-    """Times oracle.RefSolver.train_iteration (float64 torch-CPU restatement of solver.py:67-70,
-    host sampling included) on a bounded sample of the workload."""
+def cpu_reference(cfg, steps, warmup, sample_B=None, with_f32=True):
+    """Times oracle.RefSolver.train_iteration (torch-CPU restatement of solver.py:67-70, host sampling
+    included) on a bounded sample of the workload: float64 (the reference's dtype) and, beside it, float32."""
     import torch
     from oracle import ref_equation as RE
     from oracle import ref_solver as RS
@@ -118,17 +121,41 @@ def cpu_reference(cfg, steps, warmup, sample_B=None):
     B = sample_B or min(c["net_config"]["batch_size"], 2048)
     c["net_config"]["batch_size"] = B
     eqn = RE.make_ref_equation(c["eqn_config"])
-    s = RS.RefSolver(c, eqn, seed=0)
     N = c["eqn_config"]["num_time_interval_critic"]
-    for _ in range(warmup):
-        s.train_iteration()
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        s.train_iteration()
-    dt = (time.perf_counter() - t0) / steps
-    return {"value": 2.0 * B * N / dt, "unit": "path-steps/s", "cores": cores, "kind": "port",
-            "sample": f"{steps} train iterations (critic+actor step, host sampling included) at B={B} of the workload's paths, "
-                      f"N={N}, float64, torch {torch.__version__} CPU, {warmup} warm-up", "sec_per_iter": dt}
+
+    def run(dtype, k, w):
+        s = RS.RefSolver(c, eqn, seed=0, dtype=dtype)
+        for _ in range(w):
+            s.train_iteration()
+        t0 = time.perf_counter()
+        for _ in range(k):
+            s.train_iteration()
+        return (time.perf_counter() - t0) / k
+
+    dt = run(torch.float64, steps, warmup)
+    out = {"value": 2.0 * B * N / dt, "unit": "path-steps/s", "cores": cores, "kind": "port", "sample_paths": B,
+           "sample": f"{steps} train iterations (critic+actor step, host sampling included) at B={B} of the workload's paths, "
+                     f"N={N}, float64, torch {torch.__version__} CPU, {warmup} warm-up", "sec_per_iter": dt}
+    if with_f32:
+        try:
+            dt32 = run(torch.float32, max(1, min(steps, 2)), 1)
+            out["value_f32"] = 2.0 * B * N / dt32
+            out["sec_per_iter_f32"] = dt32
+        except Exception as ex:                       # the float32 figure is a courtesy; the float64 one is the baseline
+            out["value_f32"] = None
+            out["f32_error"] = repr(ex)[:200]
+    return out
+
+
+def kernel_source_hash():
+    """sha256 over the CUDA sources of the library: ties an ncu traffic capture to the build it was taken from"""
+    import hashlib
+    h = hashlib.sha256()
+    d = os.path.join(ROOT, "deeppde_actorcritic_b200", "csrc")
+    for f in sorted(os.listdir(d)):
+        h.update(f.encode())
+        h.update(open(os.path.join(d, f), "rb").read())
+    return h.hexdigest()[:16]
 
 
 def cpu_model_name():
@@ -172,10 +199,16 @@ def main():
         if rank != 0:
             return
         r = cpu_reference(cfg, max(1, args.steps), max(1, min(args.warmup, 1)))
+        Bs = r["sample_paths"]
+        config_desc = dict(config_desc, global_paths_per_iteration=Bs, path_steps_per_step=2 * Bs * N,
+                           parallelism=f"{r['cores']} host threads (torch intra-op), no GPU",
+                           sample_of=f"bounded sample: {Bs} of the workload's {B} paths per iteration (the config's own batch); "
+                                     f"path-steps/s is per-path work, so the rate carries over to the full batch",
+                           cache="host memory")
         line = {"impl": "reference", "metric": "path-steps/sec (train iteration: fused rollout + TD grad, critic+actor)", "value": r["value"],
                 "unit": "path-steps/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["sec_per_iter"] * 1e3,
                 "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": config_desc, "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                "config": config_desc, "cpu_baseline": {k: r.get(k) for k in ("value", "unit", "cores", "kind", "sample", "value_f32")},
                 "cpu_model": cpu_model_name(), "iters_per_sec": 1.0 / r["sec_per_iter"],
                 "e2e": {"value": r["value"], "unit": "path-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line), file=json_out, flush=True)
@@ -228,23 +261,23 @@ def main():
     ms = float(tms)
     value = 2.0 * B * N * args.steps / (ms * 1e-3)
 
-    # ---------------------------------------------------------------- roofline of the dominant kernel (critic)
+    # ---------------------------------------------------------------- roofline of the two rollout kernels
     fm = flop_model(cfg)
     lo, nloc = solver._shard(B)
-    kms, kflops = [], []
-    for i in range(max(2, min(args.steps, 3))):
+    thA_, thV_, thG_ = solver.model_actor.NN_control.theta, solver.model_critic.NN_value.theta, solver.model_critic.NN_value_grad.theta
+    meas = {"critic": [], "actor": []}
+    for i in range(max(2, min(args.steps, 3)) + 1):                        # first launch of each: warm-up, dropped
         x0, xb, _, sid = solver._device_batch(B, 0)
-        r = eng.critic_step(solver.model_actor.NN_control.theta, solver.model_critic.NN_value.theta, solver.model_critic.NN_value_grad.theta,
-                            x0, None, xb, solver.N_c, solver.T_c, B_global=B, path_offset=lo, need_grad=True, want=("exit_index",),
-                            dw_mode=solver._dw_mode, seed=solver.seed, stream_id=sid + 1000 + 2 * i)
+        r = eng.critic_step(thA_, thV_, thG_, x0, None, xb, solver.N_c, solver.T_c, B_global=B, path_offset=lo, need_grad=True,
+                            want=("exit_index",), dw_mode=solver._dw_mode, seed=solver.seed, stream_id=sid + 1000 + 2 * i)
         k = eng.last_kernel_ms()
-        nacc = r["exit_index"].to(torch.int64)
-        live = torch.clamp(nacc + 1, max=solver.N_c).sum().item()          # steps with a proposal computed
-        kms.append(k)
-        kflops.append(live * fm["critic_step"] + nloc * fm["critic_path"])
-        live_frac = live / float(nloc * solver.N_c)
-    kms_avg = sum(kms[1:]) / len(kms[1:])
-    kfl_avg = sum(kflops[1:]) / len(kflops[1:])
+        live = torch.clamp(r["exit_index"].to(torch.int64) + 1, max=solver.N_c).sum().item()     # steps with a proposal computed
+        meas["critic"].append((k, live * fm["critic_step"] + nloc * fm["critic_path"], live / float(nloc * solver.N_c)))
+        a = eng.actor_step(thA_, thV_, x0, None, solver.N_a, solver.T_a, B_global=B, path_offset=lo, need_grad=True,
+                           want=("exit_index",), dw_mode=solver._dw_mode, seed=solver.seed, stream_id=sid + 1001 + 2 * i)
+        k = eng.last_kernel_ms()
+        live = torch.clamp(a["exit_index"].to(torch.int64) + 1, max=solver.N_a).sum().item()
+        meas["actor"].append((k, live * fm["actor_step"] + nloc * fm["actor_path"], live / float(nloc * solver.N_a)))
     peaks = {}
     pk_src = "fallback (B200_PROFILING.md)"
     try:
@@ -253,24 +286,38 @@ def main():
     except Exception:
         pass
     peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
-    achieved = kfl_avg / (kms_avg * 1e-3) / 1e12
-    traffic = None                                     # DRAM bytes of one launch of this kernel, from the committed ncu capture
-    try:
-        tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.workload)
-        if tr and impl == "tensor" and world == 1:
-            traffic = tr["dram_bytes_read"] + tr["dram_bytes_write"]
-    except Exception:
-        pass
     sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
     fp32_peak = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12
-    roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
-                "kernel": ("critic_tc_kernel" if impl == "tensor" else "critic_kernel<%s>" % ("float" if args.dtype == "float32" else "double")), "kernel_ms": kms_avg,
-                "algorithmic_flop_per_launch": kfl_avg, "live_fraction": live_frac, "peak_source": pk_src,
-                "note": ("impl=tensor: every product is formed as 3 bf16 MMAs (hi*hi + hi*lo + lo*hi, FP32 accumulation) to hold FP32 tolerance, so the "
-                         "ceiling of this kernel is peak/3 = %.0f TFLOP/s algorithmic; executed/algorithmic MMA work is ~1.3x (recompute in the reverse sweeps)" % (peak / 3.0)
-                         if impl == "tensor" else
-                         "impl=exact: FP32 CUDA-core FMA path; its own ceiling is the FP32 FMA peak %.1f TFLOP/s at the sampled %.0f MHz" % (fp32_peak, sm_mhz)),
-                "frac_of_bf16x3_ceiling": achieved / (peak / 3.0), "frac_of_fp32_peak": achieved / fp32_peak}
+    traffic_db, src_hash = {}, kernel_source_hash()
+    try:
+        traffic_db = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+    except Exception:
+        pass
+    kname = {"critic": "critic_tc_kernel" if impl == "tensor" else "critic_kernel<%s>" % ("float" if args.dtype == "float32" else "double"),
+             "actor": "actor_tc_kernel" if impl == "tensor" else "actor_kernel<%s>" % ("float" if args.dtype == "float32" else "double")}
+    rk = {}
+    for which in ("critic", "actor"):
+        rows = meas[which][1:]
+        kms_avg = sum(r_[0] for r_ in rows) / len(rows)
+        kfl_avg = sum(r_[1] for r_ in rows) / len(rows)
+        achieved = kfl_avg / (kms_avg * 1e-3) / 1e12
+        tr = (traffic_db.get(args.workload) or {}).get(which) if (impl == "tensor" and world == 1) else None
+        fresh = bool(tr) and tr.get("source_hash") == src_hash
+        rk[which] = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                     "traffic": (tr["dram_bytes_read"] + tr["dram_bytes_write"]) if fresh else None,
+                     "traffic_source": (tr.get("capture") if fresh else "no ncu capture of this build's kernel sources (profiles/traffic.json is keyed by source hash)"),
+                     "kernel": kname[which], "kernel_ms": kms_avg, "algorithmic_flop_per_launch": kfl_avg, "live_fraction": rows[-1][2],
+                     "frac_of_bf16x3_ceiling": achieved / (peak / 3.0), "frac_of_fp32_peak": achieved / fp32_peak}
+    dominant = "critic" if rk["critic"]["kernel_ms"] >= rk["actor"]["kernel_ms"] else "actor"
+    tot_ms = rk["critic"]["kernel_ms"] + rk["actor"]["kernel_ms"]
+    tot_fl = rk["critic"]["algorithmic_flop_per_launch"] + rk["actor"]["algorithmic_flop_per_launch"]
+    roofline = dict(rk[dominant], peak_source=pk_src, dominant=dominant,
+                    iteration={"achieved": tot_fl / (tot_ms * 1e-3) / 1e12, "frac": tot_fl / (tot_ms * 1e-3) / 1e12 / peak,
+                               "kernel_ms": tot_ms, "note": "critic + actor rollout kernels of one iteration"},
+                    note=("impl=tensor: every product is formed as 3 bf16 MMAs (hi*hi + hi*lo + lo*hi, FP32 accumulation) to hold FP32 tolerance, so the "
+                          "ceiling of these kernels is peak/3 = %.0f TFLOP/s algorithmic; executed/algorithmic MMA work is ~1.3x (recompute in the reverse sweeps)" % (peak / 3.0)
+                          if impl == "tensor" else
+                          "impl=exact: FP32 CUDA-core FMA path; its own ceiling is the FP32 FMA peak %.1f TFLOP/s at the sampled %.0f MHz" % (fp32_peak, sm_mhz)))
 
     # ---------------------------------------------------------------- e2e: host buffers through the C-ABI host entry points
     pool = 2
@@ -318,7 +365,7 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         r = cpu_reference(cfg, 2, 1)
-        cpu = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        cpu = {k: r.get(k) for k in ("value", "unit", "cores", "kind", "sample", "value_f32")}
         cpu["cpu_model"] = cpu_model_name()
 
     if rank == 0:
@@ -326,7 +373,8 @@ def main():
                 "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": ("f32 (bf16x3 tensor-core products, FP32 accumulate)" if impl == "tensor" else "f32" if args.dtype == "float32" else "f64"), "data": "synthetic",
                 "config": config_desc, "impl": impl, "iters_per_sec": args.steps / (ms * 1e-3), "clocks": clocks, "e2e": e2e,
-                "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "last_losses": losses}
+                "gpu_launches": launches, "roofline": roofline, "roofline_kernels": rk, "cpu_baseline": cpu, "last_losses": losses,
+                "kernel_source_hash": src_hash}
         print(json.dumps(line), file=json_out, flush=True)
     if world > 1:
         dist.barrier()

@@ -19,7 +19,7 @@ DTYPE_IDS = {"float32": 0, "float64": 1}
 NET_ACTOR, NET_CRITIC, NET_CRITIC_GRAD = 0, 1, 2
 DW_EXTERNAL, DW_PHILOX_NORMAL, DW_PHILOX_BOUNDED = 0, 1, 2
 FLAG_CHEAT_CONTROL, FLAG_CHEAT_VALUE, FLAG_NEED_GRAD, FLAG_PROPAGATE_ONLY = 1, 2, 4, 8
-CF_V_TRUE, CF_U_TRUE, CF_V_GRAD_TRUE, CF_Z, CF_W = 0, 1, 2, 3, 4
+CF_V_TRUE, CF_U_TRUE, CF_V_GRAD_TRUE, CF_Z, CF_W, CF_DRIFT, CF_SIGMA = 0, 1, 2, 3, 4, 5, 6
 IMPL_EXACT, IMPL_TENSOR = 0, 1
 
 
@@ -70,6 +70,7 @@ SYMBOLS = {
                                  _P, _P, C.POINTER(dpb_path_outputs), _P, _I64, _P]),
     "dpb_mlp_forward": (C.c_int, [_P, C.c_int, _P, _P, _I64, _P, _P, _I64, _P]),
     "dpb_closed_form": (C.c_int, [_P, C.c_int, _P, _P, _I64, _P, _P]),
+    "dpb_diffusion": (C.c_int, [_P, _P, _P, _P, _I64, _P, _P]),
     "dpb_err_metrics": (C.c_int, [_P, _P, _P, _I64, _P, _P]),
     "dpb_adam_step": (C.c_int, [_P, _P, _P, _P, _P, _I64, _D, _D, _D, _D, _P]),
     "dpb_philox_dw": (C.c_int, [_P, _I32, _U64, _U64, _I64, _I64, _I32, _P, _P]),

@@ -698,7 +698,8 @@ int dpb_mlp_forward(dpb_handle* h, int which, const void* theta, const void* x, 
 
 int dpb_closed_form(dpb_handle* h, int which, const void* x, const void* u, int64_t n, void* out, void* stream) {
     if (!h) return fail(nullptr, DPB_ERR_ARG, "dpb_closed_form: null handle");
-    if (!x || !out || n < 1 || which < 0 || which > 4 || (which == 4 && !u)) return fail(h, DPB_ERR_ARG, "dpb_closed_form: bad argument");
+    if (!x || !out || n < 1 || which < 0 || which > 6 || ((which == 4 || which == 5) && !u)) return fail(h, DPB_ERR_ARG, "dpb_closed_form: bad argument");
+    if (which == 6 && !u && h->cfg.eqn == DPB_EQN_LQR_VAR) return fail(h, DPB_ERR_ARG, "dpb_closed_form: sigma of LQR_var depends on u");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) { cudaGetLastError(); return fail(h, DPB_ERR_CUDA, "dpb_closed_form: no CUDA device (there is no CPU fallback)"); }
     EqnD e;
@@ -706,6 +707,21 @@ int dpb_closed_form(dpb_handle* h, int which, const void* x, const void* u, int6
     const int blocks = (int)((n + 127) / 128);
     if (h->cfg.dtype == DPB_F64) closed_form_kernel<double><<<blocks, 128, 0, (cudaStream_t)stream>>>(e, which, (const double*)x, (const double*)u, n, (double*)out);
     else closed_form_kernel<float><<<blocks, 128, 0, (cudaStream_t)stream>>>(e, which, (const float*)x, (const float*)u, n, (float*)out);
+    h->launches++;
+    DPB_CUDA(h, cudaGetLastError());
+    return DPB_OK;
+}
+
+int dpb_diffusion(dpb_handle* h, const void* x, const void* u, const void* dw, int64_t n, void* out, void* stream) {
+    if (!h) return fail(nullptr, DPB_ERR_ARG, "dpb_diffusion: null handle");
+    if (!x || !dw || !out || n < 1 || (!u && h->cfg.eqn == DPB_EQN_LQR_VAR)) return fail(h, DPB_ERR_ARG, "dpb_diffusion: bad argument");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) { cudaGetLastError(); return fail(h, DPB_ERR_CUDA, "dpb_diffusion: no CUDA device (there is no CPU fallback)"); }
+    EqnD e;
+    fill_eqn(h->cfg, 1, 1.0, e);
+    const int blocks = (int)((n + 127) / 128);
+    if (h->cfg.dtype == DPB_F64) diffusion_kernel<double><<<blocks, 128, 0, (cudaStream_t)stream>>>(e, (const double*)x, (const double*)u, (const double*)dw, n, (double*)out);
+    else diffusion_kernel<float><<<blocks, 128, 0, (cudaStream_t)stream>>>(e, (const float*)x, (const float*)u, (const float*)dw, n, (float*)out);
     h->launches++;
     DPB_CUDA(h, cudaGetLastError());
     return DPB_OK;

@@ -552,7 +552,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_forward_kernel(NetDev nd, con
 }
 
 // closed forms on n points (equation.py:157-167,201-227,252-265,292-302).
-enum { CF_V_TRUE = 0, CF_U_TRUE = 1, CF_V_GRAD_TRUE = 2, CF_Z = 3, CF_W = 4 };
+enum { CF_V_TRUE = 0, CF_U_TRUE = 1, CF_V_GRAD_TRUE = 2, CF_Z = 3, CF_W = 4, CF_DRIFT = 5, CF_SIGMA = 6 };
 template <typename real>
 __global__ void closed_form_kernel(EqnD eq, int which, const real* __restrict__ x, const real* __restrict__ u, long long n, real* __restrict__ out) {
     const Eq<real> E(eq);
@@ -568,10 +568,30 @@ __global__ void closed_form_kernel(EqnD eq, int which, const real* __restrict__ 
         eq_u_true(E, xi, tmp, 1, 0);
         for (int k = 0; k < E.m; ++k) out[i * E.m + k] = tmp[k];
         break;
+    case CF_DRIFT: {                                     // Equation.drift (equation.py:172,232-235,270-273,307)
+        const real cc = (E.eqn == EQ_EKN) ? eq_drift_c(E, dpb_sqrt(norm2_path(xi, E.d, 1, 0))) : (real)0;
+        for (int k = 0; k < E.d; ++k) out[i * E.d + k] = eq_drift(E, cc, xi, u + i * E.m, k, 1, 0);
+        break;
+    }
+    case CF_SIGMA:                                       // Equation.sigma (equation.py:170,230,268,305): [n][d][d], diagonal
+        for (int k = 0; k < E.d; ++k)
+            for (int j = 0; j < E.d; ++j) out[(i * E.d + k) * E.d + j] = (j == k) ? eq_sigma(E, xi, u ? u + i * E.m : xi, k, 1, 0) : (real)0;
+        break;
     default:
         eq_V_grad_true(E, xi, tmp, 1, 0);
         for (int k = 0; k < E.d; ++k) out[i * E.d + k] = tmp[k];
     }
+}
+
+// Equation.diffusion (equation.py:175-176,237-238,275-276,310-311): sigma(x,u) . dw on n points (sigma is diagonal)
+template <typename real>
+__global__ void diffusion_kernel(EqnD eq, const real* __restrict__ x, const real* __restrict__ u, const real* __restrict__ dw, long long n,
+                                 real* __restrict__ out) {
+    const Eq<real> E(eq);
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const real* xi = x + i * E.d;
+    for (int k = 0; k < E.d; ++k) out[i * E.d + k] = eq_sigma(E, xi, u ? u + i * E.m : xi, k, 1, 0) * dw[i * E.d + k];
 }
 
 // error metrics of solver.py:109-130 on n values: out[0] = sum (t-a)^2, out[1] = sum t^2, out[2] = max |t-a|

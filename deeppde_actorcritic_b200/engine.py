@@ -234,9 +234,17 @@ class Engine:
 
     def closed_form(self, which, x, u=None):
         n = x.shape[0]
-        od = {_cabi.CF_V_TRUE: 1, _cabi.CF_Z: 1, _cabi.CF_W: 1, _cabi.CF_U_TRUE: self.control_dim, _cabi.CF_V_GRAD_TRUE: self.dim}[which]
-        out = torch.empty((n, od), dtype=self.dtype, device=self.device)
+        od = {_cabi.CF_V_TRUE: (1,), _cabi.CF_Z: (1,), _cabi.CF_W: (1,), _cabi.CF_U_TRUE: (self.control_dim,), _cabi.CF_V_GRAD_TRUE: (self.dim,),
+              _cabi.CF_DRIFT: (self.dim,), _cabi.CF_SIGMA: (self.dim, self.dim)}[which]
+        out = torch.empty((n,) + od, dtype=self.dtype, device=self.device)
         rc = self.lib.dpb_closed_form(self.handle, which, self._p(x), self._p(u), n, self._p(out), self._stream())
+        self._chk(rc)
+        return out
+
+    def diffusion(self, x, u, dw):
+        """Equation.diffusion: sigma(x,u) . dw (equation.py:175-176,237-238,275-276,310-311)"""
+        out = torch.empty_like(x)
+        rc = self.lib.dpb_diffusion(self.handle, self._p(x), self._p(u), self._p(dw), x.shape[0], self._p(out), self._stream())
         self._chk(rc)
         return out
 

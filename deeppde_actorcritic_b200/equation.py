@@ -105,6 +105,26 @@ class Equation(object):
     def V_grad_true(self, x):
         return self._cf(_cabi.CF_V_GRAD_TRUE, x)
 
+    # ---- SDE coefficients (equation.py:132-142 and the subclasses' :169-176, :229-238, :267-276, :304-311)
+    def sigma(self, x, u, num_sample):
+        """diffusion coefficient, num_sample x dim x dim_w (diagonal for all four equations)"""
+        eng = self.engine()
+        xd = eng.tensor(x)
+        assert xd.shape[0] == num_sample
+        return eng.closed_form(_cabi.CF_SIGMA, xd, None if u is None else eng.tensor(u))
+
+    def drift(self, x, u):
+        """drift in the SDE, num_sample x dim"""
+        eng = self.engine()
+        return eng.closed_form(_cabi.CF_DRIFT, eng.tensor(x), eng.tensor(u))
+
+    def diffusion(self, x, u, dw, num_sample):
+        """sigma(x, u) . dw, num_sample x dim"""
+        eng = self.engine()
+        xd = eng.tensor(x)
+        assert xd.shape[0] == num_sample
+        return eng.diffusion(xd, None if u is None else eng.tensor(u), eng.tensor(dw))
+
     def b_np(self, x):  # equation.py:116-118
         return np.sum(x ** 2, axis=1, keepdims=True) - (self.R ** 2)
 

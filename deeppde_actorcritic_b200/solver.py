@@ -103,6 +103,12 @@ class CriticModel(object):
         self.gamma = _get(self.eqn_config, "discount")
         self.propagate = bsde.propagate_naive if _get(self.train_config, "scheme") == "naive" else bsde.propagate_adaptive
 
+    def control(self, x, cheat_control, model_actor):
+        """solver.py:153-157"""
+        if cheat_control == False:  # noqa: E712  (the reference's own comparison)
+            return model_actor.NN_control(x, training=False, need_grad=False)
+        return self.bsde.u_true(x)
+
     def _step(self, inputs, model_actor, cheat_control, need_grad=False, want=("delta", "delta_bdry"), **kw):
         x0, dw, xb = _unpack(self.engine, inputs)
         return self.engine.critic_step(model_actor.NN_control.theta, self.NN_value.theta, self.NN_value_grad.theta, x0, dw, xb,

@@ -41,7 +41,7 @@ enum { DPB_F32 = 0, DPB_F64 = 1 };
 enum { DPB_NET_ACTOR = 0, DPB_NET_CRITIC = 1, DPB_NET_CRITIC_GRAD = 2 };            /* solver.py:145-146,200 */
 enum { DPB_DW_EXTERNAL = 0, DPB_DW_PHILOX_NORMAL = 1, DPB_DW_PHILOX_BOUNDED = 2 };  /* equation.py:19,31-32 */
 enum { DPB_IMPL_EXACT = 0, DPB_IMPL_TENSOR = 1 };
-enum { DPB_CF_V_TRUE = 0, DPB_CF_U_TRUE = 1, DPB_CF_V_GRAD_TRUE = 2, DPB_CF_Z = 3, DPB_CF_W = 4 };
+enum { DPB_CF_V_TRUE = 0, DPB_CF_U_TRUE = 1, DPB_CF_V_GRAD_TRUE = 2, DPB_CF_Z = 3, DPB_CF_W = 4, DPB_CF_DRIFT = 5, DPB_CF_SIGMA = 6 };
 
 /* flags of dpb_critic_step / dpb_actor_step */
 enum {
@@ -135,8 +135,14 @@ int dpb_mlp_forward(dpb_handle* h, int which_net, const void* theta, const void*
 
 /* Closed forms of the equation on n points (equation.py:157-167,201-227,252-265,292-302):
  *   which = DPB_CF_V_TRUE (out[n]), DPB_CF_U_TRUE (out[n][control_dim]), DPB_CF_V_GRAD_TRUE (out[n][dim]),
- *   DPB_CF_Z (Z_tf, out[n]), DPB_CF_W (w_tf(x,u), out[n]; u[n][control_dim] required, else NULL). */
+ *   DPB_CF_Z (Z_tf, out[n]), DPB_CF_W (w_tf(x,u), out[n]; u[n][control_dim] required, else NULL),
+ *   DPB_CF_DRIFT (Equation.drift(x,u), equation.py:172,232-235,270-273,307: out[n][dim], u required),
+ *   DPB_CF_SIGMA (Equation.sigma(x,u,n), equation.py:170,230,268,305: out[n][dim][dim], diagonal; u required for LQR_var). */
 int dpb_closed_form(dpb_handle* h, int which, const void* x, const void* u, int64_t n, void* out, void* stream);
+
+/* Equation.diffusion(x, u, dw, n) = sigma(x,u) . dw (equation.py:175-176,237-238,275-276,310-311): x[n][dim],
+ * u[n][control_dim] (NULL allowed unless the equation is LQR_var), dw[n][dim] -> out[n][dim]. */
+int dpb_diffusion(dpb_handle* h, const void* x, const void* u, const void* dw, int64_t n, void* out, void* stream);
 
 /* The reductions of err_value / err_control / err_value_grad / err_value_infty (solver.py:109-130) on n
  * values: out3 = { sum (truth-approx)^2, sum truth^2, max |truth-approx| } (device, deterministic). */

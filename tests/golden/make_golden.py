@@ -183,8 +183,17 @@ def run_case(name, cfg, seed):
     for fn in ("V_true", "V_grad_true", "Z_tf"):
         v = getattr(bsde, fn)(xb if fn == "Z_tf" else x0)
         out[fn] = v.numpy() if hasattr(v, "numpy") else np.asarray(v)
-    w = bsde.w_tf(x0, nets["actor"](x0, False, need_grad=False))
+    u_nn = nets["actor"](x0, False, need_grad=False)
+    w = bsde.w_tf(x0, u_nn)
     out["w_tf"] = w.numpy()
+    # SDE coefficients (equation.py:169-176,229-238,267-276,304-311) at (x0, NN control, first increment)
+    npy = lambda v: v.numpy() if hasattr(v, "numpy") else np.asarray(v)
+    out["sigma"] = npy(bsde.sigma(x0, u_nn, B))
+    out["drift"] = npy(bsde.drift(x0, u_nn))
+    out["diffusion"] = npy(bsde.diffusion(x0, u_nn, dw[:, :, 0], B))
+    # CriticModel.control (solver.py:153-157), both settings
+    out["control_nn"] = npy(solver.model_critic.control(x0, False, solver.model_actor))
+    out["control_cheat"] = npy(solver.model_critic.control(x0, True, solver.model_actor))
 
     # propagate (both cheat settings) through the scheme the config selects
     prop = solver.model_critic.propagate

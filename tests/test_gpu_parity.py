@@ -74,6 +74,31 @@ def test_networks_and_closed_forms(name, dtype):
     np.testing.assert_allclose(npy(eng.closed_form(_cabi.CF_Z, xb)), z["Z_tf"], **VTOL[dtype])
     u = eng.mlp_forward("actor", eng.tensor(z["theta_actor"]), x0)
     np.testing.assert_allclose(npy(eng.closed_form(_cabi.CF_W, x0, u)), z["w_tf"], **VTOL[dtype])
+    # SDE coefficients through the C ABI (equation.py:169-176,229-238,267-276,304-311)
+    np.testing.assert_allclose(npy(eng.closed_form(_cabi.CF_SIGMA, x0, u)), z["sigma"], **VTOL[dtype])
+    np.testing.assert_allclose(npy(eng.closed_form(_cabi.CF_DRIFT, x0, u)), z["drift"], **VTOL[dtype])
+    np.testing.assert_allclose(npy(eng.diffusion(x0, u, eng.tensor(z["dw"][:, :, 0]))), z["diffusion"], **VTOL[dtype])
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_equation_and_control_api(name):
+    """the reference's callable surface: Equation.sigma / drift / diffusion (equation.py:132-142 and subclasses) and
+    CriticModel.control (solver.py:153-157), same names and argument order, NumPy in / device tensors out"""
+    from deeppde_actorcritic_b200 import equation, munchify
+    from deeppde_actorcritic_b200.solver import ActorCriticSolver
+    z, cfg = load(name)
+    config = munchify(cfg)
+    bsde = getattr(equation, config.eqn_config.eqn_name)(config.eqn_config)
+    s = ActorCriticSolver(config, bsde, compute_dtype="float64", seed=0)
+    s.model_actor.NN_control.theta.copy_(s.engine.tensor(z["theta_actor"]))
+    x0, dw0 = z["x0"], z["dw"][:, :, 0]
+    n = x0.shape[0]
+    u = s.model_critic.control(x0, False, s.model_actor)
+    np.testing.assert_allclose(npy(u), z["control_nn"], **VTOL["float64"])
+    np.testing.assert_allclose(npy(s.model_critic.control(x0, True, s.model_actor)), z["control_cheat"], **VTOL["float64"])
+    np.testing.assert_allclose(npy(bsde.sigma(x0, u, n)), z["sigma"], **VTOL["float64"])
+    np.testing.assert_allclose(npy(bsde.drift(x0, u)), z["drift"], **VTOL["float64"])
+    np.testing.assert_allclose(npy(bsde.diffusion(x0, u, dw0, n)), z["diffusion"], **VTOL["float64"])
 
 
 @pytest.mark.parametrize("dtype", DTYPES)

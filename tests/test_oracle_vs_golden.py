@@ -45,6 +45,13 @@ def test_networks_and_closed_forms(name):
     np.testing.assert_allclose(eqn.V_grad_true(x0).numpy(), z["V_grad_true"], **TOL)
     np.testing.assert_allclose(eqn.Z(xb).numpy(), z["Z_tf"], **TOL)
     np.testing.assert_allclose(eqn.w(x0, nets("actor", x0)).numpy(), z["w_tf"], **TOL)
+    # SDE coefficients (equation.py:169-176,229-238,267-276,304-311) and CriticModel.control (solver.py:153-157)
+    u = nets("actor", x0)
+    np.testing.assert_allclose(torch.diag_embed(eqn.sigma_diag(x0, u) * torch.ones_like(x0)).numpy(), z["sigma"], **TOL)
+    np.testing.assert_allclose(eqn.drift(x0, u).numpy(), z["drift"], **TOL)
+    np.testing.assert_allclose(eqn.diffusion(x0, u, dw[:, :, 0]).numpy(), z["diffusion"], **TOL)
+    np.testing.assert_allclose(u.numpy(), z["control_nn"], **TOL)
+    np.testing.assert_allclose(eqn.u_true(x0).numpy(), z["control_cheat"], **TOL)
 
 
 @pytest.mark.parametrize("name", CASES)
