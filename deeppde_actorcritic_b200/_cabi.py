@@ -40,7 +40,7 @@ class dpb_inputs(C.Structure):
     _fields_ = [
         ("x0", C.c_void_p), ("dw", C.c_void_p), ("x_bdry", C.c_void_p),
         ("dw_mode", C.c_int32), ("reserved", C.c_int32),
-        ("seed", C.c_uint64), ("stream", C.c_uint64),
+        ("seed", C.c_uint64), ("stream", C.c_uint64), ("stream_base", C.c_void_p),
     ]
 
 
@@ -72,14 +72,15 @@ SYMBOLS = {
     "dpb_closed_form": (C.c_int, [_P, C.c_int, _P, _P, _I64, _P, _P]),
     "dpb_diffusion": (C.c_int, [_P, _P, _P, _P, _I64, _P, _P]),
     "dpb_err_metrics": (C.c_int, [_P, _P, _P, _I64, _P, _P]),
-    "dpb_adam_step": (C.c_int, [_P, _P, _P, _P, _P, _I64, _D, _D, _D, _D, _P]),
+    "dpb_adam_step": (C.c_int, [_P, _P, _P, _P, _P, _I64, _D, _P, _D, _D, _D, _P]),
     "dpb_philox_dw": (C.c_int, [_P, _I32, _U64, _U64, _I64, _I64, _I32, _P, _P]),
-    "dpb_sample_x": (C.c_int, [_P, _U64, _U64, _I64, _I64, _P, _P, _P]),
+    "dpb_sample_x": (C.c_int, [_P, _U64, _U64, _P, _I64, _I64, _P, _P, _P]),
     "dpb_critic_step_host": (C.c_int, [_P, _P, _P, _P, C.POINTER(dpb_inputs), _I64, _I64, _I64, _I32, _D, _U32,
                                        _P, _P, _P, _P, _I64, _P]),
     "dpb_actor_step_host": (C.c_int, [_P, _P, _P, C.POINTER(dpb_inputs), _I64, _I64, _I64, _I32, _D, _U32,
                                       _P, _P, _P, _I64, _P]),
     "dpb_launch_count": (_I64, [_P]),
+    "dpb_set_timing": (C.c_int, [_P, C.c_int]),
     "dpb_last_kernel_ms": (_D, [_P]),
     "dpb_tc_selftest": (C.c_int, [_P, _P, _P, C.c_int, _P]),
     "dpb_tc_handshake_cycles": (C.c_int, [_P, C.c_int]),

@@ -27,10 +27,12 @@ struct dpb_handle {
     long long launches;
     cudaEvent_t ev0, ev1;
     bool have_ev, timed;
+    bool timing;                    // record CUDA events around the rollout kernels (off while a CUDA graph is captured)
     std::string err;
 };
 
 static void ev_begin(dpb_handle* h, cudaStream_t st) {
+    if (!h->timing) return;
     if (!h->have_ev) {
         if (cudaEventCreate(&h->ev0) != cudaSuccess || cudaEventCreate(&h->ev1) != cudaSuccess) { cudaGetLastError(); return; }
         h->have_ev = true;
@@ -38,7 +40,7 @@ static void ev_begin(dpb_handle* h, cudaStream_t st) {
     cudaEventRecord(h->ev0, st);
 }
 static void ev_end(dpb_handle* h, cudaStream_t st) {
-    if (h->have_ev) { cudaEventRecord(h->ev1, st); h->timed = true; }
+    if (h->timing && h->have_ev) { cudaEventRecord(h->ev1, st); h->timed = true; }
 }
 
 static thread_local std::string g_err;
@@ -65,6 +67,7 @@ struct Layout {
     int nslab;              // gradient slabs: one per CTA on the exact path (deterministic), <= 16 shared ones on the tensor path
     size_t pkA, pkV, pkG, loss_part, loss_out, scratch, slabs, raw, total;
     size_t imgA, imgV, imgG, vecA, vecV, vecG, copies, stats;      // tensor path: operand images, vector blocks, activation copies, counters
+    size_t life_nacc, life_perm, life_hist;                        // tensor path, naive scheme: lifetime sort (exit counts, permutation, bins)
     long long scratch_per_cta, copies_per_cta;
 };
 
@@ -93,7 +96,7 @@ static Layout make_layout(const dpb_handle* h, long long B_local, int N) {
     L.loss_out = o; o += 256;
     L.scratch_per_cta = (long long)N * (2 * h->sr + A_NSCAL) * P;
     L.scratch = o; o += a256((size_t)L.grid * L.scratch_per_cta * es);
-    L.copies = 0; L.copies_per_cta = 0; L.stats = 0;
+    L.copies = 0; L.copies_per_cta = 0; L.stats = 0; L.life_nacc = L.life_perm = L.life_hist = 0;
     if (tensor) {
         long long cb = tc::tc_copy_bytes(h->tA);
         if (tc::tc_copy_bytes(h->tV) > cb) cb = tc::tc_copy_bytes(h->tV);
@@ -101,6 +104,9 @@ static Layout make_layout(const dpb_handle* h, long long B_local, int N) {
         L.copies_per_cta = (long long)a256((size_t)cb);
         L.copies = o; o += a256((size_t)L.grid * L.copies_per_cta);
         L.stats = o; o += a256((size_t)L.grid * 16 * 8 + 64);           // + the tile counter of the dynamic tile scheduler
+        L.life_nacc = o; o += a256((size_t)B_local * 4);
+        L.life_perm = o; o += a256((size_t)B_local * 4);
+        L.life_hist = o; o += a256((size_t)(N + 2) * 4);
     }
     const long long gc = tensor ? h->sV.gtotal + h->sG.gtotal : h->nV.gtotal + h->nG.gtotal, ga = tensor ? h->sA.gtotal : h->nA.gtotal;
     const long long gmax = gc > ga ? gc : ga;
@@ -141,6 +147,7 @@ int dpb_create(dpb_handle** out, const dpb_config* cfg) {
     h->launches = 0;
     h->have_ev = false;
     h->timed = false;
+    h->timing = true;
     const int ekn = (c.eqn == DPB_EQN_EKN);
     netdev_init(h->nA, c.dim, c.hidden_actor, c.n_hidden_actor, ekn ? c.control_dim + 1 : c.control_dim, ekn, c.control_dim);   // solver.py:255-258
     netdev_init(h->nV, c.dim, c.hidden_critic, c.n_hidden_critic, 1, 0, 0);                                                  // solver.py:251-252
@@ -218,6 +225,13 @@ int64_t dpb_staging_bytes(const dpb_handle* h, int64_t B_local, int32_t N, int32
 
 int64_t dpb_launch_count(const dpb_handle* h) { return h ? h->launches : -1; }
 
+int dpb_set_timing(dpb_handle* h, int enable) {
+    if (!h) return fail(nullptr, DPB_ERR_ARG, "dpb_set_timing: null handle");
+    h->timing = enable != 0;
+    if (!h->timing) h->timed = false;
+    return DPB_OK;
+}
+
 double dpb_last_kernel_ms(dpb_handle* h) {
     if (!h || !h->timed) return -1.0;
     float ms = -1.f;
@@ -258,7 +272,7 @@ static void fill_common(dpb_handle* h, StepArgs<real>& a, const Layout& L, char*
     a.nA = h->nA; a.nV = h->nV; a.nG = h->nG;
     a.pkA = (const real*)(ws + L.pkA); a.pkV = (const real*)(ws + L.pkV); a.pkG = (const real*)(ws + L.pkG);
     a.x0 = (const real*)in->x0; a.dw = (const real*)in->dw; a.xb = (const real*)in->x_bdry;
-    a.dw_mode = in->dw_mode; a.seed = in->seed; a.stream = in->stream;
+    a.dw_mode = in->dw_mode; a.seed = in->seed; a.stream = in->stream; a.stream_base = (const unsigned long long*)in->stream_base;
     a.B_local = B_local; a.path_offset = path_offset;
     a.invB = (real)(1.0 / (double)B_global);
     a.N = N; a.flags = flags;
@@ -393,6 +407,23 @@ static bool tc_specialised(const dpb_handle* h) {
     return !force_generic && h->cfg.dim <= 23 && h->cfg.control_dim + 1 <= 24;       // VDP: instantiated for control_dim 2, 5, 10
 }
 
+static tc::TcKernelFn tc_pick_critic(const dpb_handle* h) {
+    tc::TcKernelFn kern = tc::tc_get_critic_generic();
+    if (tc_specialised(h)) {
+        switch (h->cfg.eqn) {
+        case DPB_EQN_LQR: kern = tc::tc_get_critic_lqr(); break;
+        case DPB_EQN_EKN: kern = tc::tc_get_critic_ekn(); break;
+        case DPB_EQN_LQR_VAR: kern = tc::tc_get_critic_lqrvar(); break;
+        case DPB_EQN_VDP:
+            if (h->cfg.control_dim == 2) kern = tc::tc_get_critic_vdp2();
+            else if (h->cfg.control_dim == 5) kern = tc::tc_get_critic_vdp5();
+            else if (h->cfg.control_dim == 10) kern = tc::tc_get_critic_vdp10();
+            break;
+        }
+    }
+    return kern;
+}
+
 // ring geometry for a launch: slots of `slot_bytes` (largest chunk of the images used) in what is left of 227 KB
 static int tc_ring(dpb_handle* h, tc::TcArgs& a, bool grads) {
     a.actdz_bytes = grads ? tc::TC_PATHS * h->tc_maxw16 * 2 : 0;
@@ -422,7 +453,7 @@ static void tc_fill(dpb_handle* h, tc::TcArgs& a, const Layout& L, char* ws, con
     a.gA = h->sA; a.gV = h->sV; a.gG = h->sG;
     a.imgA = (const unsigned char*)(ws + L.imgA); a.imgV = (const unsigned char*)(ws + L.imgV); a.imgG = (const unsigned char*)(ws + L.imgG);
     a.x0 = (const float*)in->x0; a.dw = (const float*)in->dw; a.xb = (const float*)in->x_bdry;
-    a.dw_mode = in->dw_mode; a.seed = in->seed; a.stream = in->stream;
+    a.dw_mode = in->dw_mode; a.seed = in->seed; a.stream = in->stream; a.stream_base = (const unsigned long long*)in->stream_base;
     a.B_local = B_local; a.path_offset = path_offset;
     a.invB = (float)(1.0 / (double)B_global);
     a.N = N; a.flags = flags;
@@ -452,6 +483,39 @@ static int tc_finalize(dpb_handle* h, const tc::TcNet& t, const tc::TcSlab& g, c
     return DPB_OK;
 }
 
+// Naive scheme (equation.py:46-71): a path that has left the domain stays frozen for the rest of the N steps, and a tile of 128
+// paths can stop only when all of them have (live fraction 0.2 at lqr_d5, 0.015 expected at d=20: SURVEY 8d).  So the paths are
+// first rolled out forward-only (the actor network alone: ~1/5 of a training step), sorted by their number of accepted steps
+// (longest first) and then tiled in that order: the tiles die as a whole and the dynamic tile scheduler hands the long ones out
+// first.  The permutation is a pure relabelling -- every path sees the same x0 / increments (Philox is keyed by the path index)
+// and writes its outputs at its own index -- so any permutation gives the same per-path results.
+static bool tc_lifetime_sort_wanted(const dpb_handle* h, int64_t B_local, uint32_t flags) {
+    static const bool off = getenv("DPB_NO_LIFETIME_SORT") != nullptr;
+    return !off && !(h->cfg.reserved[0] & 1) && h->cfg.scheme == DPB_SCHEME_NAIVE && !(flags & DPB_FLAG_PROPAGATE_ONLY) && B_local > 2 * tc::TC_PATHS;
+}
+static int tc_lifetime_sort(dpb_handle* h, tc::TcKernelFn critic_kern, tc::TcArgs a /* by value: a forward-only copy */, const Layout& L, char* ws,
+                            size_t smem, int64_t B_local, int32_t N, cudaStream_t st) {
+    a.flags = (a.flags & DPB_FLAG_CHEAT_CONTROL) | DPB_FLAG_PROPAGATE_ONLY;
+    a.o_x = a.o_dt = a.o_coef = a.o_delta = a.o_delta_b = nullptr;
+    a.o_exit = (int*)(ws + L.life_nacc);
+    a.perm = nullptr;
+    a.slabV = a.slabG = a.slabA = nullptr;
+    a.vecV = a.vecG = nullptr;
+    DPB_CUDA(h, cudaMemsetAsync(a.tile_counter, 0, sizeof(int), st));
+    DPB_CUDA(h, cudaMemsetAsync(ws + L.life_hist, 0, (size_t)(N + 2) * 4, st));
+    cudaFuncAttributes fa;
+    DPB_CUDA(h, cudaFuncGetAttributes(&fa, critic_kern));
+    critic_kern<<<L.grid, fa.maxThreadsPerBlock, smem, st>>>(a);
+    int blocks = (int)((B_local + 255) / 256);
+    if (blocks > 592) blocks = 592;
+    lifetime_hist_kernel<<<blocks, 256, 0, st>>>((const int*)(ws + L.life_nacc), B_local, N, (int*)(ws + L.life_hist));
+    lifetime_scan_kernel<<<1, 32, 0, st>>>((int*)(ws + L.life_hist), N + 1);
+    lifetime_scatter_kernel<<<blocks, 256, 0, st>>>((const int*)(ws + L.life_nacc), B_local, N, (int*)(ws + L.life_hist), (int*)(ws + L.life_perm));
+    h->launches += 4;
+    DPB_CUDA(h, cudaGetLastError());
+    return DPB_OK;
+}
+
 static int critic_step_tc(dpb_handle* h, const void* thA, const void* thV, const void* thG, const dpb_inputs* in, int64_t B_local,
                           int64_t path_offset, int64_t B_global, int32_t N, double T, uint32_t flags, void* out_loss, void* grad_V,
                           void* grad_G, const dpb_path_outputs* outs, void* workspace, cudaStream_t st) {
@@ -476,21 +540,13 @@ static int critic_step_tc(dpb_handle* h, const void* thA, const void* thV, const
         DPB_CUDA(h, cudaMemsetAsync(ws + L.slabs, 0, (size_t)L.nslab * (h->sV.gtotal + h->sG.gtotal) * sizeof(float), st));
     }
     const size_t smem = tc::tc_smem_bytes(h->tA.vec_floats, h->tV.vec_floats, h->tG.vec_floats, a.actdz_bytes, a.nslot, a.slot_bytes);
-    tc::TcKernelFn kern = tc::tc_get_critic_generic();
-    if (tc_specialised(h)) {
-        switch (h->cfg.eqn) {
-        case DPB_EQN_LQR: kern = tc::tc_get_critic_lqr(); break;
-        case DPB_EQN_EKN: kern = tc::tc_get_critic_ekn(); break;
-        case DPB_EQN_LQR_VAR: kern = tc::tc_get_critic_lqrvar(); break;
-        case DPB_EQN_VDP:
-            if (h->cfg.control_dim == 2) kern = tc::tc_get_critic_vdp2();
-            else if (h->cfg.control_dim == 5) kern = tc::tc_get_critic_vdp5();
-            else if (h->cfg.control_dim == 10) kern = tc::tc_get_critic_vdp10();
-            break;
-        }
-    }
+    tc::TcKernelFn kern = tc_pick_critic(h);
     DPB_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     DPB_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, (int)((smem + 1024) * 100 / (228 * 1024) + 1 > 100 ? 100 : (smem + 1024) * 100 / (228 * 1024) + 1)));
+    if (tc_lifetime_sort_wanted(h, B_local, flags)) {
+        if ((rc = tc_lifetime_sort(h, kern, a, L, ws, smem, B_local, N, st))) return rc;
+        a.perm = (const int*)(ws + L.life_perm);
+    }
     DPB_CUDA(h, cudaMemsetAsync(a.tile_counter, 0, sizeof(int), st));
     ev_begin(h, st);
     cudaFuncAttributes fa;                                       // threads per CTA = the launch bound of the instantiation
@@ -549,6 +605,12 @@ static int actor_step_tc(dpb_handle* h, const void* thA, const void* thV, const 
     }
     DPB_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     DPB_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, (int)((smem + 1024) * 100 / (228 * 1024) + 1 > 100 ? 100 : (smem + 1024) * 100 / (228 * 1024) + 1)));
+    if (tc_lifetime_sort_wanted(h, B_local, flags)) {
+        tc::TcKernelFn ck = tc_pick_critic(h);                   // the forward-only rollout of the critic kernel (same per-path arithmetic)
+        DPB_CUDA(h, cudaFuncSetAttribute(ck, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if ((rc = tc_lifetime_sort(h, ck, a, L, ws, smem, B_local, N, st))) return rc;
+        a.perm = (const int*)(ws + L.life_perm);
+    }
     DPB_CUDA(h, cudaMemsetAsync(a.tile_counter, 0, sizeof(int), st));
     ev_begin(h, st);
     cudaFuncAttributes fa;                                       // threads per CTA = the launch bound of the instantiation
@@ -727,16 +789,16 @@ int dpb_diffusion(dpb_handle* h, const void* x, const void* u, const void* dw, i
     return DPB_OK;
 }
 
-int dpb_adam_step(dpb_handle* h, void* theta, const void* grad, void* m, void* v, int64_t n, double lr_t, double beta1, double beta2,
-                  double eps, void* stream) {
+int dpb_adam_step(dpb_handle* h, void* theta, const void* grad, void* m, void* v, int64_t n, double lr_t, const double* lr_t_dev,
+                  double beta1, double beta2, double eps, void* stream) {
     if (!h) return fail(nullptr, DPB_ERR_ARG, "dpb_adam_step: null handle");
     if (!theta || !grad || !m || !v || n < 1) return fail(h, DPB_ERR_ARG, "dpb_adam_step: null argument");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) { cudaGetLastError(); return fail(h, DPB_ERR_CUDA, "dpb_adam_step: no CUDA device (there is no CPU fallback)"); }
     int blocks = (int)((n + 255) / 256);
     if (blocks > 1184) blocks = 1184;
-    if (h->cfg.dtype == DPB_F64) adam_kernel<double><<<blocks, 256, 0, (cudaStream_t)stream>>>((double*)theta, (const double*)grad, (double*)m, (double*)v, n, lr_t, beta1, beta2, eps);
-    else adam_kernel<float><<<blocks, 256, 0, (cudaStream_t)stream>>>((float*)theta, (const float*)grad, (float*)m, (float*)v, n, (float)lr_t, (float)beta1, (float)beta2, (float)eps);
+    if (h->cfg.dtype == DPB_F64) adam_kernel<double><<<blocks, 256, 0, (cudaStream_t)stream>>>((double*)theta, (const double*)grad, (double*)m, (double*)v, n, lr_t, lr_t_dev, beta1, beta2, eps);
+    else adam_kernel<float><<<blocks, 256, 0, (cudaStream_t)stream>>>((float*)theta, (const float*)grad, (float*)m, (float*)v, n, (float)lr_t, lr_t_dev, (float)beta1, (float)beta2, (float)eps);
     h->launches++;
     DPB_CUDA(h, cudaGetLastError());
     return DPB_OK;
@@ -759,15 +821,15 @@ int dpb_philox_dw(dpb_handle* h, int32_t dw_mode, uint64_t seed, uint64_t stream
     return DPB_OK;
 }
 
-int dpb_sample_x(dpb_handle* h, uint64_t seed, uint64_t stream_id, int64_t path_offset, int64_t B_local, void* x0_out, void* xb_out,
-                 void* stream) {
+int dpb_sample_x(dpb_handle* h, uint64_t seed, uint64_t stream_id, const uint64_t* stream_base, int64_t path_offset, int64_t B_local,
+                 void* x0_out, void* xb_out, void* stream) {
     if (!h) return fail(nullptr, DPB_ERR_ARG, "dpb_sample_x: null handle");
     if ((!x0_out && !xb_out) || B_local < 1) return fail(h, DPB_ERR_ARG, "dpb_sample_x: bad argument");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) { cudaGetLastError(); return fail(h, DPB_ERR_CUDA, "dpb_sample_x: no CUDA device (there is no CPU fallback)"); }
     const int blocks = (int)((B_local + 127) / 128);
-    if (h->cfg.dtype == DPB_F64) sample_x_kernel<double><<<blocks, 128, 0, (cudaStream_t)stream>>>(seed, stream_id, path_offset, B_local, h->cfg.dim, h->cfg.R, (double*)x0_out, (double*)xb_out);
-    else sample_x_kernel<float><<<blocks, 128, 0, (cudaStream_t)stream>>>(seed, stream_id, path_offset, B_local, h->cfg.dim, (float)h->cfg.R, (float*)x0_out, (float*)xb_out);
+    if (h->cfg.dtype == DPB_F64) sample_x_kernel<double><<<blocks, 128, 0, (cudaStream_t)stream>>>(seed, stream_id, (const unsigned long long*)stream_base, path_offset, B_local, h->cfg.dim, h->cfg.R, (double*)x0_out, (double*)xb_out);
+    else sample_x_kernel<float><<<blocks, 128, 0, (cudaStream_t)stream>>>(seed, stream_id, (const unsigned long long*)stream_base, path_offset, B_local, h->cfg.dim, (float)h->cfg.R, (float*)x0_out, (float*)xb_out);
     h->launches++;
     DPB_CUDA(h, cudaGetLastError());
     return DPB_OK;

@@ -34,6 +34,7 @@ struct StepArgs {
     const real *x0, *dw, *xb;
     int dw_mode;
     unsigned long long seed, stream;
+    const unsigned long long* stream_base;   // optional device word added to `stream` (CUDA-graph replays: the iteration lives in memory)
     long long B_local, path_offset;
     real invB;                      // 1 / B_global
     int N;
@@ -102,7 +103,7 @@ __device__ __forceinline__ void load_dw(const StepArgs<real>& a, long long base,
     } else {
         const int nch = (d + 3) >> 2;
         uint32_t k0, k1;
-        philox_key(a.seed, a.stream, k0, k1);
+        philox_key(a.seed, a.stream + (a.stream_base ? *a.stream_base : 0ull), k0, k1);
         for (int idx = threadIdx.x; idx < nch * P; idx += NTHREADS) {
             int ch = idx / P, p = idx - ch * P;
             unsigned long long gp = (unsigned long long)(a.path_offset + base + p);
@@ -624,7 +625,8 @@ __global__ void err_metrics_kernel(const real* __restrict__ t, const real* __res
 // tf.keras Adam (solver.py:16-21): m,v EMA then theta -= lr_t * m / (sqrt(v) + eps)
 template <typename real>
 __global__ void adam_kernel(real* __restrict__ th, const real* __restrict__ g, real* __restrict__ m, real* __restrict__ v, long long n,
-                            real lr_t, real b1, real b2, real eps) {
+                            real lr_t, const double* __restrict__ lr_t_dev, real b1, real b2, real eps) {
+    if (lr_t_dev) lr_t = (real)*lr_t_dev;                  // (CUDA-graph replays: the host writes this step's rate into device memory)
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         const real gi = g[i];
@@ -632,6 +634,29 @@ __global__ void adam_kernel(real* __restrict__ th, const real* __restrict__ g, r
         const real vi = v[i] + (gi * gi - v[i]) * ((real)1 - b2);
         m[i] = mi; v[i] = vi;
         th[i] = th[i] - lr_t * mi / (dpb_sqrt(vi) + eps);
+    }
+}
+
+// Lifetime sort of the naive scheme (counting sort of the paths by their number of accepted steps, longest first):
+// hist[N - nacc]++  ->  exclusive scan (one block)  ->  perm[offset[bin]++] = path
+static __global__ void lifetime_hist_kernel(const int* __restrict__ nacc, long long B, int N, int* __restrict__ hist) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < B; i += stride) {
+        int k = nacc[i]; k = k < 0 ? 0 : (k > N ? N : k);
+        atomicAdd(&hist[N - k], 1);
+    }
+}
+static __global__ void lifetime_scan_kernel(int* __restrict__ hist, int nbins) {       // in place: counts -> start offsets
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        int run = 0;
+        for (int b = 0; b < nbins; ++b) { const int c = hist[b]; hist[b] = run; run += c; }
+    }
+}
+static __global__ void lifetime_scatter_kernel(const int* __restrict__ nacc, long long B, int N, int* __restrict__ offs, int* __restrict__ perm) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < B; i += stride) {
+        int k = nacc[i]; k = k < 0 ? 0 : (k > N ? N : k);
+        perm[atomicAdd(&offs[N - k], 1)] = (int)i;
     }
 }
 
@@ -672,10 +697,11 @@ __global__ void philox_dw_kernel(int mode, unsigned long long seed, unsigned lon
 // x0 uniform in the ball of radius R, x_bdry uniform on the sphere (equation.py:14-22), from Philox
 // streams keyed by the GLOBAL path index (counter word 2: 0x80000000 | chunk, word 3: 1 = x0, 2 = x_bdry).
 template <typename real>
-__global__ void sample_x_kernel(unsigned long long seed, unsigned long long stream, long long path_offset, long long B, int d, real R,
-                                real* __restrict__ x0, real* __restrict__ xb) {
+__global__ void sample_x_kernel(unsigned long long seed, unsigned long long stream, const unsigned long long* __restrict__ stream_base,
+                                long long path_offset, long long B, int d, real R, real* __restrict__ x0, real* __restrict__ xb) {
     const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= B) return;
+    if (stream_base) stream += *stream_base;
     uint32_t k0, k1;
     philox_key(seed, stream, k0, k1);
     const unsigned long long gp = (unsigned long long)(path_offset + p);

@@ -22,6 +22,7 @@ struct TcArgs {
     const float *x0, *dw, *xb;
     int dw_mode;
     unsigned long long seed, stream;
+    const unsigned long long* stream_base;   // optional device word added to `stream` (CUDA-graph replays)
     long long B_local, path_offset;
     float invB;
     int N;
@@ -40,6 +41,8 @@ struct TcArgs {
     int* o_exit;
     long long* stats;               // [grid][16] cycle counters (diagnostics), may be NULL
     int* tile_counter;              // zeroed before the launch: CTAs take tile blockIdx.x first, then gridDim.x + counter++
+    const int* perm;                // optional: slot i of the tiling works on local path perm[i] (naive scheme: paths sorted by
+                                    // lifetime so that the tiles die as a whole; NULL: identity)
 };
 
 // the kernels are instantiated in their own translation units (dpb_tc_inst_*.cu)
@@ -159,7 +162,7 @@ __device__ __forceinline__ void path_dw(const TcArgs& a, long long gpath_local, 
         return;
     }
     uint32_t k0, k1;
-    philox_key(a.seed, a.stream, k0, k1);
+    philox_key(a.seed, a.stream + (a.stream_base ? *a.stream_base : 0ull), k0, k1);
     const unsigned long long gp = (unsigned long long)(a.path_offset + gpath_local);
 #pragma unroll
     for (int ch = 0; ch < (DPX + 3) / 4; ++ch) {
@@ -291,8 +294,9 @@ __device__ __forceinline__ void critic_tc_body(const TcArgs& a, const TcSmem& S,
     const long long ntiles = (a.B_local + TC_PATHS - 1) / TC_PATHS;
     for (long long tile = blockIdx.x; tile < ntiles; tile = tc_next_tile(S, a)) {
         const long long base = tile * TC_PATHS;
-        const long long gp = base + row;                          // local path index of this thread
-        const bool valid = is_path && gp < a.B_local;
+        const long long slot = base + row;                        // position of this thread's path in the tiling
+        const bool valid = is_path && slot < a.B_local;
+        const long long gp = (valid && a.perm) ? (long long)a.perm[slot] : slot;      // local path index of this thread
         const bool wr = valid && primary;               // this thread does the global stores of its path
         TC_STAT(const long long tp0 = clock64();)
         float x[DPX], u[DPX], dwv[DPX], sdw[DPX], g[DPX], raw[DPX];
@@ -556,8 +560,9 @@ __device__ __forceinline__ void actor_tc_body(const TcArgs& a, const TcSmem& S, 
     const long long ntiles = (a.B_local + TC_PATHS - 1) / TC_PATHS;
     for (long long tile = blockIdx.x; tile < ntiles; tile = tc_next_tile(S, a)) {
         const long long base = tile * TC_PATHS;
-        const long long gp = base + row;
-        const bool valid = is_path && gp < a.B_local;
+        const long long slot = base + row;
+        const bool valid = is_path && slot < a.B_local;
+        const long long gp = (valid && a.perm) ? (long long)a.perm[slot] : slot;
         TC_STAT(const long long f0 = clock64();)
         const bool wr = valid && primary;               // this thread does the global stores of its path
         float x[DPX], u[DPX], dwv[DPX], raw[DPX];

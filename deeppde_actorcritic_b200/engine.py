@@ -22,7 +22,7 @@ def _get(cfg, key, default=None):
 TORCH_DTYPES = {"float32": torch.float32, "float64": torch.float64}
 
 
-def make_dpb_config(eqn_config, net_config, train_config, dtype="float32", ekn_sigma_fix=False, impl="exact"):
+def make_dpb_config(eqn_config, net_config, train_config, dtype="float32", ekn_sigma_fix=False, impl="exact", lifetime_sort=True):
     c = _cabi.dpb_config()
     name = _get(eqn_config, "eqn_name")
     if name not in _cabi.EQN_IDS:
@@ -44,6 +44,7 @@ def make_dpb_config(eqn_config, net_config, train_config, dtype="float32", ekn_s
     for i, h in enumerate(hc):
         c.hidden_critic[i] = int(h)
     c.impl = {"exact": _cabi.IMPL_EXACT, "tensor": _cabi.IMPL_TENSOR}[impl]
+    c.reserved[0] = 0 if lifetime_sort else 1
     c.R = float(_get(eqn_config, "R"))
     c.discount = float(_get(eqn_config, "discount"))
     for k in ("p", "q", "beta", "a", "epsilon", "a2", "a3"):
@@ -54,7 +55,7 @@ def make_dpb_config(eqn_config, net_config, train_config, dtype="float32", ekn_s
 class Engine:
     """One handle + one device.  All tensors passed in must be CUDA, contiguous, of ``self.dtype``."""
 
-    def __init__(self, eqn_config, net_config, train_config, dtype="float32", device=None, ekn_sigma_fix=False, impl="exact"):
+    def __init__(self, eqn_config, net_config, train_config, dtype="float32", device=None, ekn_sigma_fix=False, impl="exact", lifetime_sort=True):
         self.lib = _cabi.load()
         if not torch.cuda.is_available():
             raise RuntimeError("deeppde_actorcritic_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
@@ -62,7 +63,7 @@ class Engine:
         torch.cuda.set_device(self.device)
         self.dtype_name = dtype
         self.dtype = TORCH_DTYPES[dtype]
-        self.cfg = make_dpb_config(eqn_config, net_config, train_config, dtype, ekn_sigma_fix, impl)
+        self.cfg = make_dpb_config(eqn_config, net_config, train_config, dtype, ekn_sigma_fix, impl, lifetime_sort)
         self.dim, self.control_dim = self.cfg.dim, self.cfg.control_dim
         self.handle = C.c_void_p()
         rc = self.lib.dpb_create(C.byref(self.handle), C.byref(self.cfg))
@@ -104,12 +105,17 @@ class Engine:
     def launch_count(self):
         return int(self.lib.dpb_launch_count(self.handle))
 
-    def _inputs(self, x0, dw, xb, dw_mode, seed, stream_id):
+    def set_timing(self, enable):
+        """CUDA-event timing of the rollout kernels (switched off while an iteration is captured into a CUDA graph)"""
+        self._chk(self.lib.dpb_set_timing(self.handle, 1 if enable else 0))
+
+    def _inputs(self, x0, dw, xb, dw_mode, seed, stream_id, stream_base=None):
         i = _cabi.dpb_inputs()
         i.x0 = x0.data_ptr()
         i.dw = dw.data_ptr() if dw is not None else None
         i.x_bdry = xb.data_ptr() if xb is not None else None
         i.dw_mode, i.seed, i.stream = dw_mode, seed, stream_id
+        i.stream_base = stream_base.data_ptr() if stream_base is not None else None     # device int64 added to stream_id (graph replays)
         return i
 
     def _outs(self, B, N, want):
@@ -129,7 +135,7 @@ class Engine:
     # ------------------------------------------------------------------ steps
     def critic_step(self, theta_actor, theta_V, theta_G, x0, dw, xb, N, T, *, B_global=None, path_offset=0,
                     cheat_control=False, need_grad=False, propagate_only=False, want=(), dw_mode=_cabi.DW_EXTERNAL,
-                    seed=0, stream_id=0):
+                    seed=0, stream_id=0, stream_base=None):
         """CriticModel.call / loss_critic / grad_critic (solver.py:73-78,85-90,159-191).
         Returns dict(loss[2] device tensor, grad_V, grad_G, + requested per-path outputs)."""
         B = x0.shape[0]
@@ -137,7 +143,7 @@ class Engine:
         flags = (1 if cheat_control else 0) | (4 if need_grad else 0) | (8 if propagate_only else 0)
         nb = self.lib.dpb_workspace_bytes(self.handle, B, N)
         ws = self.workspace(nb)
-        inp = self._inputs(x0, dw, xb, dw_mode, seed, stream_id)
+        inp = self._inputs(x0, dw, xb, dw_mode, seed, stream_id, stream_base)
         o, res = self._outs(B, N, want)
         loss = torch.zeros(2, dtype=self.dtype, device=self.device)
         gV = torch.empty(self.n_params["critic"], dtype=self.dtype, device=self.device) if need_grad else None
@@ -150,14 +156,14 @@ class Engine:
         return res
 
     def actor_step(self, theta_actor, theta_V, x0, dw, N, T, *, B_global=None, path_offset=0, cheat_control=False,
-                   cheat_value=False, need_grad=False, want=(), dw_mode=_cabi.DW_EXTERNAL, seed=0, stream_id=0):
+                   cheat_value=False, need_grad=False, want=(), dw_mode=_cabi.DW_EXTERNAL, seed=0, stream_id=0, stream_base=None):
         """ActorModel.call / loss_actor / grad_actor (solver.py:80-83,92-97,207-224)."""
         B = x0.shape[0]
         Bg = B if B_global is None else B_global
         flags = (1 if cheat_control else 0) | (2 if cheat_value else 0) | (4 if need_grad else 0)
         nb = self.lib.dpb_workspace_bytes(self.handle, B, N)
         ws = self.workspace(nb)
-        inp = self._inputs(x0, dw, None, dw_mode, seed, stream_id)
+        inp = self._inputs(x0, dw, None, dw_mode, seed, stream_id, stream_base)
         o, res = self._outs(B, N, want)
         loss = torch.zeros(2, dtype=self.dtype, device=self.device)
         gA = torch.empty(self.n_params["actor"], dtype=self.dtype, device=self.device) if need_grad else None
@@ -255,9 +261,11 @@ class Engine:
         self._chk(self.lib.dpb_err_metrics(self.handle, self._p(t), self._p(a), t.numel(), self._p(out), self._stream()))
         return out
 
-    def adam_step(self, theta, grad, m, v, lr_t, beta1=0.9, beta2=0.999, eps=1e-8):
+    def adam_step(self, theta, grad, m, v, lr_t, beta1=0.9, beta2=0.999, eps=1e-8, lr_dev=None):
+        """lr_dev: optional one-element float64 device tensor that overrides lr_t when the kernel runs (graph replays)"""
         rc = self.lib.dpb_adam_step(self.handle, self._p(theta), self._p(grad), self._p(m), self._p(v), theta.numel(),
-                                    float(lr_t), beta1, beta2, eps, self._stream())
+                                    float(lr_t), C.c_void_p(lr_dev.data_ptr()) if lr_dev is not None else None,
+                                    beta1, beta2, eps, self._stream())
         self._chk(rc)
 
     def philox_dw(self, dw_mode, seed, stream_id, path_offset, B, N):
@@ -266,9 +274,10 @@ class Engine:
         self._chk(rc)
         return dw
 
-    def sample_x(self, seed, stream_id, path_offset, B, want_xb=True):
+    def sample_x(self, seed, stream_id, path_offset, B, want_xb=True, stream_base=None):
         x0 = torch.empty((B, self.dim), dtype=self.dtype, device=self.device)
         xb = torch.empty((B, self.dim), dtype=self.dtype, device=self.device) if want_xb else None
-        rc = self.lib.dpb_sample_x(self.handle, seed, stream_id, path_offset, B, self._p(x0), self._p(xb), self._stream())
+        rc = self.lib.dpb_sample_x(self.handle, seed, stream_id, C.c_void_p(stream_base.data_ptr()) if stream_base is not None else None,
+                                   path_offset, B, self._p(x0), self._p(xb), self._stream())
         self._chk(rc)
         return x0, xb

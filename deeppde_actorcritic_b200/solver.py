@@ -15,6 +15,7 @@ from __future__ import annotations
 
 import logging
 import math
+import os
 import time
 
 import numpy as np
@@ -24,6 +25,15 @@ from . import _cabi
 from .engine import Engine, _get
 
 DELTA_CLIP = 50.0   # solver.py:5 (applied inside the critic kernel)
+
+
+def _rng_to_plain(st):
+    """np.random.get_state() as plain Python / torch objects (loadable with weights_only=True)"""
+    return {"name": st[0], "keys": torch.from_numpy(np.asarray(st[1], dtype=np.int64)), "pos": int(st[2]), "has_gauss": int(st[3]), "gauss": float(st[4])}
+
+
+def _rng_from_plain(d):
+    return (d["name"], np.asarray(d["keys"].numpy(), dtype=np.uint32), d["pos"], d["has_gauss"], d["gauss"])
 
 
 def _dist():
@@ -177,15 +187,21 @@ class KerasAdam(object):
                 return v
         return self.values[-1]
 
-    def apply_gradients(self, grads):
+    def next_lr_t(self):
+        """advance the step counter and return this step's bias-corrected rate"""
         lr = self.learning_rate(self.iterations)
         self.iterations += 1
         t = self.iterations
-        lr_t = lr * math.sqrt(1.0 - self.b2 ** t) / (1.0 - self.b1 ** t)
+        return lr * math.sqrt(1.0 - self.b2 ** t) / (1.0 - self.b1 ** t)
+
+    def apply_gradients(self, grads, lr_dev=None):
+        """lr_dev: one-element float64 device tensor the Adam kernels read the rate from (a captured iteration is replayed
+        with the host writing next_lr_t() there); None: the rate is passed by value"""
+        lr_t = self.next_lr_t() if lr_dev is None else 0.0
         for p, g, m, v in zip(self.params, grads, self.m, self.v):
             if g is None:
                 continue
-            self.engine.adam_step(p, g, m, v, lr_t, self.b1, self.b2, self.eps)
+            self.engine.adam_step(p, g, m, v, lr_t, self.b1, self.b2, self.eps, lr_dev=lr_dev)
 
 
 class ActorCriticSolver(object):
@@ -230,6 +246,10 @@ class ActorCriticSolver(object):
             self.cheat_value_in_actor = True
         self.sampler = _get(self.train_config, "sampler", "device")
         self.seed = int(seed if seed is not None else np.random.randint(1 << 31))
+        if dist and self.world > 1:                                          # one Philox key for all ranks: the device sampler is keyed by
+            sd = torch.tensor([self.seed], dtype=torch.int64, device=self.engine.device)   # (seed, iteration, GLOBAL path index)
+            dist.broadcast(sd, src=0)
+            self.seed = int(sd.item())
         self._dw_mode = _cabi.DW_PHILOX_NORMAL if st == "normal" else _cabi.DW_PHILOX_BOUNDED
         self._iter = 0
         self.N_c = int(_get(self.eqn_config, "num_time_interval_critic"))
@@ -298,33 +318,97 @@ class ActorCriticSolver(object):
         self.optimizer_actor.apply_gradients(grad)
 
     # device-sampled training steps: x0/x_bdry from dpb_sample_x, increments generated in-kernel
-    def _device_batch(self, B, phase):
+    def _device_batch(self, B, phase, graph=None):
         lo, n = self._shard(B)
-        stream_id = (self._iter << 1) | phase
-        x0, xb = self.engine.sample_x(self.seed, stream_id, lo, n, want_xb=(phase == 0))
+        # replayed graph: the iteration lives in device memory (graph["stream"] = iteration << 1), the argument is the phase
+        stream_id = phase if graph else (self._iter << 1) | phase
+        x0, xb = self.engine.sample_x(self.seed, stream_id, lo, n, want_xb=(phase == 0), stream_base=graph["stream"] if graph else None)
         return x0, xb, lo, stream_id
 
-    def train_step_critic_device(self, B):
-        x0, xb, lo, sid = self._device_batch(B, 0)
+    def train_step_critic_device(self, B, graph=None):
+        x0, xb, lo, sid = self._device_batch(B, 0, graph)
         r = self.engine.critic_step(self.model_actor.NN_control.theta, self.model_critic.NN_value.theta,
                                     self.model_critic.NN_value_grad.theta, x0, None, xb, self.N_c, self.T_c, B_global=B,
                                     path_offset=lo, cheat_control=self.cheat_control_in_critic, need_grad=True,
-                                    dw_mode=self._dw_mode, seed=self.seed, stream_id=sid)
+                                    dw_mode=self._dw_mode, seed=self.seed, stream_id=sid, stream_base=graph["stream"] if graph else None)
         gV, gG, loss = self._allreduce([r["grad_V"], r["grad_G"], r["loss"]])
-        self.optimizer_critic.apply_gradients([gV, gG])
+        self.optimizer_critic.apply_gradients([gV, gG], lr_dev=graph["lr"][0:1] if graph else None)
         return loss
 
-    def train_step_actor_device(self, B):
-        x0, _, lo, sid = self._device_batch(B, 1)
+    def train_step_actor_device(self, B, graph=None):
+        x0, _, lo, sid = self._device_batch(B, 1, graph)
         r = self.engine.actor_step(self.model_actor.NN_control.theta, self.model_critic.NN_value.theta, x0, None, self.N_a,
                                    self.T_a, B_global=B, path_offset=lo, cheat_value=self.cheat_value_in_actor, need_grad=True,
-                                   dw_mode=self._dw_mode, seed=self.seed, stream_id=sid)
+                                   dw_mode=self._dw_mode, seed=self.seed, stream_id=sid, stream_base=graph["stream"] if graph else None)
         gA, loss = self._allreduce([r["grad_actor"], r["loss"]])
-        self.optimizer_actor.apply_gradients([gA])
+        self.optimizer_actor.apply_gradients([gA], lr_dev=graph["lr"][1:2] if graph else None)
         return loss
+
+    # ------------------------------------------------------------------ one iteration as ONE CUDA graph
+    def enable_cuda_graph(self):
+        """Capture a whole device-sampled training iteration -- sample_x, weight packing, critic rollout + TD gradient, slab
+        reduction, Adam, the same for the actor -- into one CUDA graph and replay it from then on: one launch per iteration
+        instead of ~40.  What changes from iteration to iteration (the Philox stream id = iteration << 1, the two
+        bias-corrected Adam rates) lives in device memory the kernels read (dpb_inputs.stream_base, dpb_adam_step's lr_t_dev);
+        the host writes it before each replay.  Single process only: with torch.distributed the NCCL all-reduce stays
+        outside a graph and the iteration is launched kernel by kernel as before."""
+        if self.world > 1 or self.sampler != "device":
+            return False
+        dev = self.engine.device
+        g = {"stream": torch.zeros(1, dtype=torch.int64, device=dev), "lr": torch.zeros(2, dtype=torch.float64, device=dev),
+             "graph": None, "launches": 0, "replays": 0}
+        self._graph = g
+        return True
+
+    def _graph_params(self, g):
+        tr = _get(self.train_config, "train")
+        lr = [0.0, 0.0]
+        if tr in ("actor-critic", "critic"):
+            lr[0] = self.optimizer_critic.next_lr_t()
+        if tr in ("actor-critic", "actor"):
+            lr[1] = self.optimizer_actor.next_lr_t()
+        # pageable sources on purpose: the driver stages them before cudaMemcpyAsync returns, so the next iteration's values
+        # can be written while the GPU is still several iterations behind (a pinned buffer would be read when the copy RUNS)
+        g["stream"].copy_(torch.tensor([self._iter << 1], dtype=torch.int64))
+        g["lr"].copy_(torch.tensor(lr, dtype=torch.float64))
+
+    def _graph_body(self, g):
+        tr = _get(self.train_config, "train")
+        B = int(_get(self.net_config, "batch_size"))
+        if tr in ("actor-critic", "critic"):
+            self.train_step_critic_device(B, g)
+        if tr in ("actor-critic", "actor"):
+            self.train_step_actor_device(B, g)
+
+    def _graph_iteration(self):
+        g = self._graph
+        self._graph_params(g)
+        if g["graph"] is None:
+            # the first iteration runs eagerly on a side stream (allocator warm-up, cudaFuncSetAttribute calls), then the
+            # very same call sequence is captured; the captured iteration is NOT executed by the capture itself
+            self.engine.set_timing(False)
+            side = torch.cuda.Stream(device=self.engine.device)
+            side.wait_stream(torch.cuda.current_stream(self.engine.device))
+            with torch.cuda.stream(side):
+                self._graph_body(g)
+            torch.cuda.current_stream(self.engine.device).wait_stream(side)
+            torch.cuda.synchronize(self.engine.device)
+            l0 = self.engine.launch_count()
+            cg = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(cg):
+                self._graph_body(g)
+            g["launches"] = self.engine.launch_count() - l0
+            g["graph"] = cg
+            self._iter += 1
+            return
+        g["graph"].replay()
+        g["replays"] += 1
+        self._iter += 1
 
     def train_iteration(self):
         """One loop body of train() (solver.py:67-70)."""
+        if getattr(self, "_graph", None) is not None:
+            return self._graph_iteration()
         tr = _get(self.train_config, "train")
         B = int(_get(self.net_config, "batch_size"))
         if tr in ("actor-critic", "critic"):
@@ -344,7 +428,11 @@ class ActorCriticSolver(object):
         opt = lambda o: {"m": [t.cpu() for t in o.m], "v": [t.cpu() for t in o.v], "iterations": o.iterations}
         return {"theta_actor": self.model_actor.NN_control.theta.cpu(), "theta_critic": self.model_critic.NN_value.theta.cpu(),
                 "theta_critic_grad": self.model_critic.NN_value_grad.theta.cpu(), "opt_critic": opt(self.optimizer_critic),
-                "opt_actor": opt(self.optimizer_actor), "iter": self._iter, "seed": self.seed, "dtype": self.engine.dtype_name}
+                "opt_actor": opt(self.optimizer_actor), "iter": self._iter, "seed": self.seed, "dtype": self.engine.dtype_name,
+                # the run record so far (main.py writes the whole history), the wall clock already spent, and the host RNG
+                # (the reference's NumPy samplers, used by sampler="host" and by the validation sets)
+                "history": [list(map(float, r)) for r in getattr(self, "_history", [])], "elapsed": float(getattr(self, "_elapsed", 0.0)),
+                "np_rng": _rng_to_plain(np.random.get_state())}
 
     def load_state_dict(self, sd):
         self.model_actor.NN_control.theta.copy_(sd["theta_actor"])
@@ -356,19 +444,26 @@ class ActorCriticSolver(object):
             for dst, src in zip(o.v, sd[k]["v"]):
                 dst.copy_(src)
             o.iterations = int(sd[k]["iterations"])
-        self._iter, self.seed = int(sd["iter"]), int(sd["seed"])      # device sampling is keyed by (seed, iteration): the run continues bit for bit
+        self._iter, self.seed = int(sd["iter"]), int(sd["seed"])      # device sampling is keyed by (seed, iteration): the exact path continues
+        self._history = [list(r) for r in sd.get("history", [])]      # bit for bit (the tensor path up to its FP32 slab-reduction order)
+        self._elapsed = float(sd.get("elapsed", 0.0))
+        if sd.get("np_rng") is not None:
+            np.random.set_state(_rng_from_plain(sd["np_rng"]))
 
     def save_checkpoint(self, path):
         if self.rank == 0:
-            torch.save(self.state_dict(), path)
+            tmp = path + ".tmp"                      # write-then-rename: a kill mid-write never destroys the last good checkpoint
+            torch.save(self.state_dict(), tmp)
+            os.replace(tmp, path)
 
     def load_checkpoint(self, path):
-        self.load_state_dict(torch.load(path, map_location="cpu"))
+        self.load_state_dict(torch.load(path, map_location="cpu", weights_only=True))
 
     # ------------------------------------------------------------------ train loop (solver.py:36-71)
     def train(self):
-        start_time = time.time()
-        training_history = []
+        training_history = [list(r) for r in getattr(self, "_history", [])]      # rows logged before a resume
+        start_time = time.time() - float(getattr(self, "_elapsed", 0.0))         # elapsed time continues across a resume
+        self._history = training_history
         n = self.net_config
         valid_size = int(_get(n, "valid_size"))
         dev = lambda data: tuple(self.engine.tensor(a) for a in data)
@@ -382,6 +477,7 @@ class ActorCriticSolver(object):
         start = self._iter
         for step in range(start, num_iterations + 1):
             if ckpt_path and ckpt_every and step > start and step % ckpt_every == 0:
+                self._elapsed = time.time() - start_time
                 self.save_checkpoint(ckpt_path)
             if step % int(_get(n, "logging_frequency")) == 0:
                 loss_critic = float(self.loss_critic(valid_data_critic, training=False, cheat_control=False))

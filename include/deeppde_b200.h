@@ -62,7 +62,8 @@ typedef struct dpb_config {
     int32_t hidden_actor[DPB_MAX_HIDDEN];
     int32_t hidden_critic[DPB_MAX_HIDDEN];
     int32_t impl;                  /* DPB_IMPL_EXACT: FP32/FP64 CUDA-core FMA; DPB_IMPL_TENSOR: tcgen05 MLP layers */
-    int32_t reserved[3];
+    int32_t reserved[3];           /* reserved[0] bit 0: 1 = do NOT sort the paths by lifetime before tiling them (tensor path, naive
+                                      scheme; the sort is a pure relabelling of the paths -- see dpb_api.cu -- and is on by default) */
     double R, discount;            /* eqn_config.R, discount */
     double p, q, beta;             /* LQR / LQR_var */
     double a, epsilon;             /* VDP (a, epsilon) / LQR_var (epsilon) */
@@ -80,6 +81,8 @@ typedef struct dpb_inputs {
     int32_t reserved;
     uint64_t seed;                 /* Philox key */
     uint64_t stream;               /* Philox stream id: (iteration << 1) | phase */
+    const uint64_t* stream_base;   /* optional DEVICE word added to `stream` when the kernel runs (NULL: none).  Lets a captured
+                                      CUDA graph of one training iteration be replayed: the host writes iteration << 1 there. */
 } dpb_inputs;
 
 /* Optional per-path outputs (any pointer may be NULL). */
@@ -151,7 +154,8 @@ int dpb_err_metrics(dpb_handle* h, const void* truth, const void* approx, int64_
 /* tf.keras Adam step as used at solver.py:16-21,99-107 on a flat vector:
  *   m += (g-m)(1-b1); v += (g*g-v)(1-b2); theta -= lr_t * m / (sqrt(v)+eps),  lr_t given by the host. */
 int dpb_adam_step(dpb_handle* h, void* theta, const void* grad, void* m, void* v, int64_t n,
-                  double lr_t, double beta1, double beta2, double eps, void* stream);
+                  double lr_t, const double* lr_t_dev, double beta1, double beta2, double eps, void* stream);
+/* (lr_t_dev: optional DEVICE double that overrides lr_t when the kernel runs -- CUDA-graph replays, as dpb_inputs.stream_base) */
 
 /* The Brownian increments the PHILOX modes use, materialised as dw[B_local][dim][N] (for parity
  * tests: feed the same tensor to the oracle). */
@@ -161,8 +165,9 @@ int dpb_philox_dw(dpb_handle* h, int32_t dw_mode, uint64_t seed, uint64_t stream
 /* Device-side version of the x0 / x_bdry part of Equation.sample_normal (equation.py:14-22): x0 uniform
  * in the ball |x|<R, x_bdry uniform on the sphere, Philox-keyed by the GLOBAL path index (so that a run
  * sees the same paths however it is sharded).  Either output may be NULL. */
-int dpb_sample_x(dpb_handle* h, uint64_t seed, uint64_t stream_id, int64_t path_offset, int64_t B_local,
+int dpb_sample_x(dpb_handle* h, uint64_t seed, uint64_t stream_id, const uint64_t* stream_base, int64_t path_offset, int64_t B_local,
                  void* x0_out, void* xb_out, void* stream);
+/* (stream_base: optional DEVICE word added to stream_id, see dpb_inputs.stream_base) */
 
 /* Host-buffer convenience used for end-to-end timing: same as dpb_critic_step / dpb_actor_step but
  * x0/dw/x_bdry are HOST pointers (pinned or pageable); they are copied to device staging inside
@@ -180,6 +185,10 @@ int dpb_actor_step_host(dpb_handle* h, const void* theta_actor, const void* thet
 
 /* Number of kernel launches issued by this handle since creation (for bench.py's gpu_launches). */
 int64_t dpb_launch_count(const dpb_handle* h);
+
+/* Switch the CUDA-event timing of the rollout kernels off / on (off while an iteration is being captured into a CUDA graph:
+ * events recorded during capture cannot be queried). */
+int dpb_set_timing(dpb_handle* h, int enable);
 
 /* Device time in ms of the most recent critic/actor rollout kernel of this handle, from CUDA events the
  * library records on the caller's stream around that launch (synchronises on the stop event; < 0 if none). */

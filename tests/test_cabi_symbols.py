@@ -70,7 +70,7 @@ def test_no_cpu_fallback(lib):
     rc = lib.dpb_critic_step(h, C.addressof(buf), C.addressof(buf), C.addressof(buf), C.byref(inp), 1, 0, 1, 10, 0.2, 0,
                              None, None, None, None, C.addressof(ws), 1 << 40, None)
     assert rc == _cabi.DPB_ERR_CUDA and b"no CPU fallback" in lib.dpb_last_error(h)
-    assert lib.dpb_adam_step(h, C.addressof(buf), C.addressof(buf), C.addressof(buf), C.addressof(buf), 8, 1e-3, .9, .999, 1e-8, None) == _cabi.DPB_ERR_CUDA
+    assert lib.dpb_adam_step(h, C.addressof(buf), C.addressof(buf), C.addressof(buf), C.addressof(buf), 8, 1e-3, None, .9, .999, 1e-8, None) == _cabi.DPB_ERR_CUDA
     lib.dpb_destroy(h)
     from deeppde_actorcritic_b200.engine import Engine
     with pytest.raises(RuntimeError):

@@ -317,3 +317,221 @@ def test_solver_modes_run(impl, train, scheme, sample, td):
     assert changed[2] == (train in ("critic", "actor-critic") and td == "TD1")
     valid = tuple(s.engine.tensor(a) for a in s.sample(64, s.N_c))
     assert np.isfinite(float(s.loss_critic(valid, False, False))) and np.isfinite(float(s.loss_actor(valid, False, False, False)))
+
+
+# ------------------------------------------------------------------------------------------------
+# round-2 additions: variants that had no parity test (VERDICT r01 "test debt")
+def _oracle_vs_engines(cfg, B, seed, ekn_sigma_fix=False, impls=(("float64", "exact"), ("float32", "tensor")), cheat=False):
+    """critic residuals / losses / gradients and actor cost / gradient of both implementations against the float64 oracle
+    on the same (x0, dw, x_bdry) and weights; returns the error table"""
+    from oracle import ref_equation as RE
+    from oracle import ref_solver as RS
+    e = cfg["eqn_config"]
+    N, T = int(e["num_time_interval_critic"]), float(e["total_time_critic"])
+    eqn = RE.make_ref_equation(e, ekn_sigma_fix=ekn_sigma_fix)
+    np.random.seed(seed)
+    sampler = eqn.sample_bounded if cfg["train_config"].get("sample_type") == "bounded" else eqn.sample_normal
+    x0, dw, xb = sampler(B, N)
+    x0, dw, xb = (a.astype(np.float32).astype(np.float64) for a in (x0 * 0.9, dw, xb))
+    rng = np.random.RandomState(seed + 1)
+    th = {}
+    for k in ("actor", "critic", "critic_grad"):
+        i, h, o, _ = RS.net_dims(cfg, k)
+        p = RS.init_params(i, h, o, rng)
+        p[-3 * o:-2 * o] = rng.normal(0, 0.1, o)
+        th[k] = p.astype(np.float32).astype(np.float64)
+    tt = {k: torch.tensor(v) for k, v in th.items()}
+    inputs = tuple(torch.tensor(a) for a in (x0, dw, xb))
+    loss_c, gV, gG, delta, delta_b, aux = RS.grad_critic(eqn, cfg, tt, inputs, cheat)
+    loss_a, gA, y, aux_a = RS.grad_actor(eqn, cfg, tt, inputs, False, False)
+    table = {}
+    for dtype, impl in impls:
+        eng = Engine(e, cfg["net_config"], cfg["train_config"], dtype=dtype, impl=impl, ekn_sigma_fix=ekn_sigma_fix)
+        d = [eng.tensor(a) for a in (x0, dw, xb)]
+        thd = {k: eng.tensor(v) for k, v in th.items()}
+        r = eng.critic_step(thd["actor"], thd["critic"], thd["critic_grad"], d[0], d[1], d[2], N, T, need_grad=True, cheat_control=cheat,
+                            want=("delta", "delta_bdry", "coef"))
+        a = eng.actor_step(thd["actor"], thd["critic"], d[0], d[1], N, T, need_grad=True, want=("delta", "coef"))
+        same = (_npy(r["coef"]) == aux["coef"].detach().numpy()).all(1)
+        same_a = (_npy(a["coef"]) == aux_a["coef"].detach().numpy()).all(1)
+        vt = dict(rtol=1e-8, atol=1e-10) if dtype == "float64" else VTOL
+        np.testing.assert_allclose(_npy(r["delta"])[same], delta.numpy()[same], **vt)
+        np.testing.assert_allclose(_npy(r["delta_bdry"]), delta_b.numpy(), **vt)
+        np.testing.assert_allclose(_npy(a["delta"])[same_a], y.numpy()[same_a], **vt)
+        table[impl] = {"same": float(same.mean()), "same_a": float(same_a.mean()),
+                       "gV": _gerr(_npy(r["grad_V"]), gV.numpy()), "gG": _gerr(_npy(r["grad_G"]), gG.numpy()),
+                       "gA": _gerr(_npy(a["grad_actor"]), gA.numpy()), "all_same": bool(same.all() and same_a.all())}
+    return table
+
+
+def test_ekn_sigma_fix_vs_oracle():
+    """the consistent-sigma switch of ekn (sigma = sqrt(2 eps) instead of the reference's literal sqrt(2)) against
+    RefEKN(sigma_fix=True) -- and the literal setting must differ from it (the switch really changes the dynamics)"""
+    z, cfg = _load("ekn_d6_adaptive_normal_td1")
+    cfg = json.loads(json.dumps(cfg))
+    t = _oracle_vs_engines(cfg, 200, 31, ekn_sigma_fix=True)
+    print("ekn sigma_fix:", t)
+    assert t["exact"]["same"] == 1.0 and t["exact"]["same_a"] == 1.0
+    for k in ("gV", "gG", "gA"):
+        assert t["exact"][k] < 1e-7, (k, t["exact"][k])
+        if t["tensor"]["all_same"]:
+            assert t["tensor"][k] < GTOL_TENSOR, (k, t["tensor"][k])
+    assert t["tensor"]["same"] > 0.98
+    # literal sqrt(2): different trajectories
+    e = cfg["eqn_config"]
+    N, T = e["num_time_interval_critic"], e["total_time_critic"]
+    outs = []
+    for fix in (False, True):
+        eng = Engine(e, cfg["net_config"], cfg["train_config"], dtype="float64", ekn_sigma_fix=fix)
+        r = eng.critic_step(None, None, None, eng.tensor(z["x0"]), eng.tensor(z["dw"]), None, N, T, cheat_control=True, propagate_only=True, want=("x_smp",))
+        outs.append(_npy(r["x_smp"]))
+    assert np.abs(outs[0] - outs[1]).max() > 1e-2
+    # the Equation class carries the switch (eqn_config.sigma_fix / constructor argument) into its engine
+    from deeppde_actorcritic_b200 import equation, munchify
+    assert equation.ekn(munchify(dict(e, sigma_fix=True))).sigma_fix and equation.EKN(munchify(e), sigma_fix=True).sigma_fix
+    assert not equation.ekn(munchify(e)).sigma_fix
+
+
+def test_vdp_d20_instantiation_vs_oracle():
+    """configs/vdp_d20.json: d=20, control_dim=10 -- the <24, VDP, 10> instantiation of the tensor kernels (static cyclic
+    neighbour indices), at the config's network sizes, against the oracle"""
+    cfg = json.load(open(os.path.join(ROOT, "configs", "vdp_d20.json")))
+    assert cfg["eqn_config"]["control_dim"] == 10 and cfg["eqn_config"]["dim"] == 20
+    cfg["eqn_config"].update(num_time_interval_critic=20, num_time_interval_actor=20)
+    t = _oracle_vs_engines(cfg, 300, 41)
+    print("vdp_d20:", t)
+    assert t["exact"]["same"] == 1.0 and t["tensor"]["same"] > 0.98
+    for k in ("gV", "gG", "gA"):
+        assert t["exact"][k] < 1e-7, (k, t["exact"][k])
+        if t["tensor"]["all_same"]:
+            assert t["tensor"][k] < GTOL_TENSOR, (k, t["tensor"][k])
+
+
+@pytest.mark.parametrize("L", [5, 6])
+def test_deep_networks_vs_oracle(L):
+    """five and six hidden layers (the maximum the ABI accepts): the chunk schedule of the critic's NN_value phase holds
+    7 (L+1) products (the round-1 schedule overflowed at L >= 5)"""
+    z, cfg = _load("lqr_d5_adaptive_normal_td1")
+    cfg = json.loads(json.dumps(cfg))
+    cfg["net_config"]["num_hiddens_actor"] = [24, 40, 24, 16, 40, 24][:L]
+    cfg["net_config"]["num_hiddens_critic"] = [40, 24, 24, 40, 16, 24][:L]
+    t = _oracle_vs_engines(cfg, 200, 51 + L)
+    print(f"L={L}:", t)
+    assert t["exact"]["same"] == 1.0 and t["tensor"]["same"] > 0.98
+    for k in ("gV", "gG", "gA"):
+        assert t["exact"][k] < 1e-7, (k, t["exact"][k])
+        if t["tensor"]["all_same"]:
+            assert t["tensor"][k] < GTOL_TENSOR, (k, t["tensor"][k])
+
+
+def test_tensor_checkpoint_resume(tmp_path):
+    """train 6 iterations == train 3, checkpoint, reload into a fresh solver, train 3 on the TENSOR path: the device sampler
+    is keyed by (seed, iteration), so the resumed run sees the same paths; the weights agree up to the FP32 summation order
+    of the shared gradient slabs -- stated tolerance 2e-5 of each vector's max-norm.  The checkpoint also
+    carries the history rows, the elapsed time and the NumPy RNG state."""
+    from deeppde_actorcritic_b200 import equation, munchify
+    from deeppde_actorcritic_b200.solver import ActorCriticSolver
+    z, cfg = _load("lqr_d5_adaptive_normal_td1")
+    cfg = json.loads(json.dumps(cfg))
+    cfg["net_config"]["batch_size"] = 300
+
+    def make():
+        config = munchify(cfg)
+        bsde = getattr(equation, config.eqn_config.eqn_name)(config.eqn_config)
+        return ActorCriticSolver(config, bsde, compute_dtype="float32", seed=3, impl="tensor")
+
+    a = make()
+    for _ in range(6):
+        a.train_iteration()
+    b = make()
+    for _ in range(3):
+        b.train_iteration()
+    b._history, b._elapsed = [[0, 1.0, 2.0, 3.0, 4.0, 5.0, 6.0, 7.0, 8.0]], 12.5
+    np.random.seed(77)
+    expect_next = np.random.RandomState(77).standard_normal(3)
+    path = str(tmp_path / "ck.pt")
+    b.save_checkpoint(path)
+    assert not os.path.exists(path + ".tmp")
+    np.random.seed(1)                                     # the resumed process starts from some other RNG state
+    c = make()
+    c.load_checkpoint(path)
+    assert c._iter == 3 and c._history == b._history and c._elapsed == 12.5
+    np.testing.assert_array_equal(np.random.standard_normal(3), expect_next)
+    for _ in range(3):
+        c.train_iteration()
+    for ta, tc in ((a.model_actor.NN_control.theta, c.model_actor.NN_control.theta),
+                   (a.model_critic.NN_value.theta, c.model_critic.NN_value.theta),
+                   (a.model_critic.NN_value_grad.theta, c.model_critic.NN_value_grad.theta)):
+        assert _gerr(_npy(tc), _npy(ta)) < 2e-5
+
+
+@pytest.mark.parametrize("impl", ["exact", "tensor"])
+def test_cuda_graph_iteration_matches_eager(impl):
+    """a whole device-sampled iteration captured as ONE CUDA graph and replayed (the iteration counter and the
+    Adam rates live in device memory) gives the weights of the kernel-by-kernel loop: bit for bit on the exact path, up to
+    the FP32 slab-reduction order on the tensor path"""
+    from deeppde_actorcritic_b200 import equation, munchify
+    from deeppde_actorcritic_b200.solver import ActorCriticSolver
+    z, cfg = _load("lqr_var_d8_adaptive_normal_td1")
+    cfg = json.loads(json.dumps(cfg))
+    cfg["net_config"]["batch_size"] = 300
+    cfg["net_config"]["lr_boundaries_critic"], cfg["net_config"]["lr_values_critic"] = [2], [1e-3, 1e-4]     # the rate changes inside the run
+
+    def make():
+        config = munchify(cfg)
+        bsde = getattr(equation, config.eqn_config.eqn_name)(config.eqn_config)
+        return ActorCriticSolver(config, bsde, compute_dtype="float32", seed=5, impl=impl)
+
+    a, b = make(), make()
+    assert b.enable_cuda_graph()
+    for _ in range(6):
+        a.train_iteration()
+        b.train_iteration()
+    assert b._graph["graph"] is not None and b._graph["replays"] == 5 and b._graph["launches"] >= 10
+    assert a.optimizer_critic.iterations == b.optimizer_critic.iterations == 6
+    for ta, tb in ((a.model_actor.NN_control.theta, b.model_actor.NN_control.theta),
+                   (a.model_critic.NN_value.theta, b.model_critic.NN_value.theta),
+                   (a.model_critic.NN_value_grad.theta, b.model_critic.NN_value_grad.theta)):
+        if impl == "exact":
+            assert torch.equal(ta, tb)
+        else:
+            assert _gerr(_npy(tb), _npy(ta)) < 2e-5
+
+
+def test_naive_lifetime_sort_is_a_relabelling():
+    """naive scheme, tensor path: tiling the paths in order of their lifetime (forward-only pre-pass + counting sort, so that
+    the tiles die as a whole) changes nothing per path -- same x0, same Philox increments, outputs at the path's own index:
+    TD residuals, costs and exit indices are bit-identical to the unsorted run; gradients agree up to FP32 summation order"""
+    cfg = json.load(open(os.path.join(ROOT, "configs", "bench_lqr_d5_naive_normal_td1.json")))
+    e, net, tr = cfg["eqn_config"], cfg["net_config"], cfg["train_config"]
+    assert tr["scheme"] == "naive"
+    from oracle import ref_solver as RS
+    rng = np.random.RandomState(8)
+    B, N, T = 5000, int(e["num_time_interval_critic"]), float(e["total_time_critic"])
+    res = []
+    for sort in (False, True):
+        eng = Engine(e, net, tr, dtype="float32", impl="tensor", lifetime_sort=sort)
+        if not res:
+            th = {}
+            for k in ("actor", "critic", "critic_grad"):
+                i, h, o, _ = RS.net_dims(cfg, k)
+                th[k] = RS.init_params(i, h, o, rng)
+        thd = {k: eng.tensor(v) for k, v in th.items()}
+        x0, xb = eng.sample_x(3, 1, 0, B)
+        kw = dict(dw_mode=1, seed=3, stream_id=7, need_grad=True)
+        r = eng.critic_step(thd["actor"], thd["critic"], thd["critic_grad"], x0, None, xb, N, T, want=("delta", "delta_bdry", "exit_index", "coef"), **kw)
+        a = eng.actor_step(thd["actor"], thd["critic"], x0, None, N, T, want=("delta", "exit_index"), **kw)
+        torch.cuda.synchronize()
+        res.append((r, a, eng.launch_count()))
+    (r0, a0, l0), (r1, a1, l1) = res
+    assert l1 == l0 + 8                                   # two pre-passes: forward-only rollout + histogram + scan + scatter
+    for k in ("delta", "delta_bdry", "exit_index", "coef"):
+        assert torch.equal(r0[k], r1[k]), k
+    for k in ("delta", "exit_index"):
+        assert torch.equal(a0[k], a1[k]), k
+    live = float(r0["coef"].mean())
+    assert live < 0.5                                     # the naive scheme really kills most path-steps here
+    for g in ("grad_V", "grad_G"):
+        assert _gerr(_npy(r1[g]), _npy(r0[g])) < 1e-5
+    assert _gerr(_npy(a1["grad_actor"]), _npy(a0["grad_actor"])) < 1e-5
+    np.testing.assert_allclose(_npy(r1["loss"]), _npy(r0["loss"]), rtol=1e-5)
