@@ -61,13 +61,14 @@ struct TcSmem {
     Sched* sch;
     ProdCtl* pc;
     float* red;
+    uint32_t* dzmax;                 // [2][8]: exchange of the tile's largest |cotangent| among the path warps (path_put_dz)
     TcNet *nA, *nV, *nG;             // shared-memory copies of the network descriptors
     TcSlab *gA, *gV, *gG;
 };
 
 // everything except the ring
 __host__ __device__ inline size_t tc_smem_fixed(int vfA, int vfV, int vfG, int actdz_bytes) {
-    return 2 * (size_t)actdz_bytes + (size_t)(vfA + vfV + vfG) * 4 + (2 * MAX_NSLOT + 3 + MAX_CHUNK) * 8 + 64 + sizeof(Sched) + 64 + 64 + 3 * sizeof(TcNet) + 3 * sizeof(TcSlab) + 64 + 1024;
+    return 2 * (size_t)actdz_bytes + (size_t)(vfA + vfV + vfG) * 4 + (2 * MAX_NSLOT + 3 + MAX_CHUNK) * 8 + 64 + sizeof(Sched) + 64 + 64 + 64 + 3 * sizeof(TcNet) + 3 * sizeof(TcSlab) + 64 + 1024;
 }
 __host__ __device__ inline size_t tc_smem_bytes(int vfA, int vfV, int vfG, int actdz_bytes, int nslot, int slot_bytes) {
     return tc_smem_fixed(vfA, vfV, vfG, actdz_bytes) + (size_t)nslot * slot_bytes;
@@ -93,6 +94,7 @@ __device__ __forceinline__ void tc_carve(TcSmem& s, unsigned char* base, const T
     s.pc = reinterpret_cast<ProdCtl*>(p); p += 64;
     s.red = reinterpret_cast<float*>(((uintptr_t)p + 15) & ~(uintptr_t)15);
     p = reinterpret_cast<unsigned char*>(s.red) + 64;
+    s.dzmax = reinterpret_cast<uint32_t*>(p); p += 64;
     s.nA = reinterpret_cast<TcNet*>(p); p += sizeof(TcNet);
     s.nV = reinterpret_cast<TcNet*>(p); p += sizeof(TcNet);
     s.nG = reinterpret_cast<TcNet*>(p); p += sizeof(TcNet);
@@ -210,7 +212,7 @@ __device__ __forceinline__ void roles_init(Roles& r, const TcSmem& S, const TcAr
     C.act_full = S.act_full; C.act_count = 0; C.nslot = a.nslot; C.slot_bytes = a.slot_bytes; C.act = S.act; C.dz = S.dz;
     r.P.tl = tmem + ((uint32_t)((warp & 3) * 32) << 16);
     r.P.grp = (warp >> 2) % TC_NGRP;
-    r.P.bars = smem_u32(S.acc_full); r.P.sync = 0;
+    r.P.bars = smem_u32(S.acc_full); r.P.sync = 0; r.P.dexp = 0;
     TC_STAT(r.P.t_accw = 0; r.P.t_epi = 0; r.P.t_hid = 0; r.P.t_drain = 0; r.P.t_mark = clock64();)
     TC_STAT(C.t_aready = 0; C.t_issue = 0; C.t_accw = 0; C.t_dw_ready = 0; C.t_act = 0;)
     C.n_ops = 0;
@@ -424,16 +426,16 @@ __device__ __forceinline__ void critic_tc_body(const TcArgs& a, const TcSmem& S,
                 const float delta = v0[0] - y - vN[0] * disc;
                 rhog = valid ? rho_grad(delta, 50.f) * scale : 0.f;
                 cot[0] = -rhog * disc;
-                path_net_backward(P, nV, gV, mk, cot, true, gsV, S.dz, row, dy0);
+                path_net_backward(P, nV, gV, mk, cot, true, gsV, S.dz, row, dy0, S.dzmax);
                 acc_input_sums<DPX>(sxV, s0V, x, dy0, P.grp, d);
                 path_net_forward_keep(P, nV, S.vecV, x0v, v0, mk, copies, S.act, row, false);
                 cot[0] = rhog;
-                path_net_backward(P, nV, gV, mk, cot, true, gsV, S.dz, row, dy0);
+                path_net_backward(P, nV, gV, mk, cot, true, gsV, S.dz, row, dy0, S.dzmax);
                 acc_input_sums<DPX>(sxV, s0V, x0v, dy0, P.grp, d);
                 path_net_forward_keep(P, nV, S.vecV, xbv, vb, mk, copies, S.act, row, false);
                 const float dbb = vb[0] - eq_Z<float, DP, EQN, MV>(E, xbv, 1, 0);
                 cot[0] = valid ? rho_grad(dbb, 50.f) * scale : 0.f;
-                path_net_backward(P, nV, gV, mk, cot, true, gsV, S.dz, row, dy0);
+                path_net_backward(P, nV, gV, mk, cot, true, gsV, S.dz, row, dy0, S.dzmax);
                 acc_input_sums<DPX>(sxV, s0V, xbv, dy0, P.grp, d);
                 reduce_rows_to(gsV + gV.gX, sxV, d, P.grp, true);
                 reduce_rows_to(gsV + gV.g0, s0V, d, P.grp, true);
@@ -473,7 +475,7 @@ __device__ __forceinline__ void critic_tc_body(const TcArgs& a, const TcSmem& S,
                     KLOOP(k, d) { xt[k] = __ldcs(&tr[k * TC_PATHS + row]); cot[k] = __ldcs(&tr[(sr + k) * TC_PATHS + row]) * rhog; }
                     float unused[1];
                     path_net_forward_keep(P, nG, S.vecG, xt, unused, mk, copies, S.act, row, true);
-                    path_net_backward(P, nG, gG, mk, cot, true, gsG, S.dz, row, dy0);
+                    path_net_backward(P, nG, gG, mk, cot, true, gsG, S.dz, row, dy0, S.dzmax);
                     acc_input_sums<DPX>(sxG, s0G, xt, dy0, P.grp, d);
                 }
                 reduce_rows_to(gsG + gG.gX, sxG, d, P.grp, true);
@@ -661,7 +663,7 @@ __device__ __forceinline__ void actor_tc_body(const TcArgs& a, const TcSmem& S, 
                 float cot[1], dy0[DPX];
                 path_net_forward_keep(P, nV, S.vecV, x, vN, mk, nullptr, nullptr, row, false);
                 cot[0] = seed;
-                path_net_backward(P, nV, gV, mk, cot, false, nullptr, nullptr, row, dy0);
+                path_net_backward(P, nV, gV, mk, cot, false, nullptr, nullptr, row, dy0, S.dzmax);
                 const float* g0c = S.vecV + nV.vec_g0;
                 KLOOP(k, d) lam[k] = dy0[k] * g0c[k];
             }
@@ -708,7 +710,7 @@ __device__ __forceinline__ void actor_tc_body(const TcArgs& a, const TcSmem& S, 
                     KLOOP(j, m) cot[j] = ubar[j];
                 }
                 TC_STAT(const long long r2 = clock64(); seg_adj += r2 - r1;)
-                path_net_backward(P, nA, gA, mk, cot, true, gsA, S.dz, row, dy0);
+                path_net_backward(P, nA, gA, mk, cot, true, gsA, S.dz, row, dy0, S.dzmax);
                 TC_STAT(seg_bwd += clock64() - r2;)
                 const float* g0c = S.vecA + nA.vec_g0;
                 acc_input_sums<DPX>(sxA, s0A, xt, dy0, P.grp, d);

@@ -5,6 +5,11 @@
 // 16-column chunk of the epilogues; 1: a single thread with all chunks); the next warp is the control warp (issues
 // every tcgen05.mma), the last one the producer (streams the weights).
 //
+//   * dW products (a_l^T dz_l over the 128 paths of a tile) read both operands from shared memory as FP16 images (11-bit
+//     significands: 8x finer than bf16 at the same size and MMA rate).  FP16's narrow exponent range is handled per backward
+//     evaluation: path_put_dz takes the largest |cotangent| of the tile (one warp reduction + one named barrier), multiplies
+//     every output cotangent by the power of two that brings it to [2^11, 2^12), and -- the whole backward chain being
+//     linear -- the drains of the dW accumulators and the read-out of dy0 divide it out again (exact: powers of two).
 //   * Precision: FP32 emulated with bf16 pairs.  Every operand x is carried as hi = bf16(x) and
 //     lo = bf16(x - hi) and a product a*w is formed as ah*wh + ah*wl + al*wh with FP32 accumulation in
 //     tensor memory (error ~2^-16 relative per term; the dropped al*wl term is ~2^-18).
@@ -191,7 +196,8 @@ struct ProdCtl {
 // warps: everything the next product needs is in place / the accumulator has been drained), a_chunk[16] (count 4: the
 // four warps that converted chunk c of the accumulator published its planes; a_chunk[0] counts every path warp).  Every barrier's parity is tracked on both
 // sides in one word: bit c (< 16) a_chunk[c], bit 16 a_all, bit 17 acc_full, bit 31 the TMEM region of the next A planes.
-constexpr uint32_t SY_ALL = 1u << 16, SY_ACC = 1u << 17, SY_REG = 1u << 31;
+constexpr uint32_t SY_ALL = 1u << 16, SY_ACC = 1u << 17, SY_DZ = 1u << 18, SY_REG = 1u << 31;      // (SY_DZ: buffer parity of the cotangent-maximum exchange)
+__device__ __forceinline__ float pow2f(int e) { return __int_as_float((127 + e) << 23); }            // 2^e, -126 <= e <= 127
 
 struct Ctrl {
     unsigned char* ring;
@@ -360,6 +366,7 @@ struct PathCtx {
     uint32_t bars;                 // shared-memory address of the hand-off barriers: acc_full, a_all, a_chunk[16] (8 bytes each)
     uint32_t sync;                 // parity bits of the hand-off barriers + TMEM region bit (layout: see SY_* above)
     int grp;                       // 0: threads 0..127, 1: threads 128..255 (chunk parity this thread handles)
+    int dexp;                      // the current backward evaluation runs scaled by 2^dexp (see the header: FP16 dW operands)
     TC_STAT(long long t_accw, t_mark;)      // cycles spent waiting for the tensor pipe; time of the last wake-up
     TC_STAT(long long t_epi, t_hid;)        // t_hid: cycles inside hidden-layer epilogues only
     TC_STAT(long long t_drain;)             // cycles inside the dW drains (after the accumulator wait)
@@ -431,14 +438,6 @@ __device__ __forceinline__ void put16(uint32_t tc, const float* v) {
     tmem_st8(tc, h);
     tmem_st8(tc + 8, l);
 }
-// same, also returning the hi words (for the bf16 copies)
-__device__ __forceinline__ void put16h(uint32_t tc, const float* v, uint32_t* h) {
-    uint32_t l[8];
-    split16(v, h, l);
-    tmem_st8(tc, h);
-    tmem_st8(tc + 8, l);
-}
-
 // In-place epilogue of a product with `nco` output chunks: wait for its commit, hand the chunks of this thread's group
 // (c % TC_NGRP == grp) to f(c, r[16], tc) -- r = the 16 accumulator columns, tc = their TMEM address, where f stores the
 // planes of the next product.  mode: EPI_CHUNKS publishes every chunk on its own barrier (the next product starts on it
@@ -491,14 +490,18 @@ __device__ __forceinline__ void affine16(const uint32_t* r, const float* gc, con
     }
 }
 
-// 16 features 16c.. of this thread's row (packed bf16 hi words) -> image (R = 128 rows) at `img` (shared or global)
-__device__ __forceinline__ void copy16h(unsigned char* img, int row, int c, uint32_t* w, int one_at /* feature index set to 1, or -1 */) {
+// 16 features 16c.. of this thread's row -> FP16 operand image of the dW products (R = 128 rows) at `img` (shared or global)
+__device__ __forceinline__ void copy16f(unsigned char* img, int row, int c, const float* v, int one_at /* feature index set to 1, or -1 */) {
+    uint32_t w[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j)                                      // (saturating: a wild value becomes +-65504, not inf)
+        asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(w[j]) : "f"(v[2 * j + 1]), "f"(v[2 * j]));
     const int o = one_at - 16 * c;
-    if (o >= 0 && o < 16) {                                          // bf16(1.0) = 0x3F80
+    if (o >= 0 && o < 16) {                                          // fp16(1.0) = 0x3C00
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            if (o == 2 * j) w[j] = (w[j] & 0xffff0000u) | 0x3F80u;
-            if (o == 2 * j + 1) w[j] = (w[j] & 0x0000ffffu) | 0x3F800000u;
+            if (o == 2 * j) w[j] = (w[j] & 0xffff0000u) | 0x3C00u;
+            if (o == 2 * j + 1) w[j] = (w[j] & 0x0000ffffu) | 0x3C000000u;
         }
     }
     unsigned char* p = img + (size_t)(2 * c) * 2048 + (row >> 3) * 128 + (row & 7) * 16;
@@ -517,14 +520,13 @@ __device__ __forceinline__ void path_put_y0(PathCtx& p, const TcNet& t, const fl
     for (int c = 0; c < 2; ++c) {
         if (c < K0 / 16 && (c % TC_NGRP) == p.grp) {
             float v[16];
-            uint32_t h[8];
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
                 const int k = 16 * c + j;
                 v[j] = (k < NX && k < t.in) ? x[k < NX ? k : 0] * g0c[k] + b0[k] : 0.f;
             }
-            put16h(path_planes(p) + 16 * c, v, h);
-            if (copies) copy16h(copies, row, c, h, t.ly[0].kl);
+            put16(path_planes(p) + 16 * c, v);
+            if (copies) copy16f(copies, row, c, v, t.ly[0].kl);
         }
     }
     if (copies) fence_proxy_async_global();
@@ -673,7 +675,7 @@ __device__ __forceinline__ void ctrl_act_wait(Ctrl& c) {
 // is the region the next dX product will write (the other one holds the dz planes that product reads).
 __device__ __forceinline__ void ctrl_gemm_dw(Ctrl& c, int blk_, int N16_) {
     const int blk = (int)warp_uniform((uint32_t)blk_), N16 = (int)warp_uniform((uint32_t)N16_);
-    const uint32_t idesc = idesc_bf16(128, N16, 1, 1);
+    const uint32_t idesc = idesc_f16(128, N16, 1, 1);                   // FP16 operand images
     uint32_t sync = warp_uniform(c.sync);
     TC_STAT(const long long t0 = clock64();)
     mbar_wait(c.a_all, (sync >> 16) & 1u);                              // operands complete / previous block drained
@@ -737,7 +739,6 @@ static __device__ __noinline__ uint32_t path_hidden_keep_(PathArg p, const TcNet
         const bool planes = !(last_hidden && skip_last);                 // (skip_last: nothing reads a_L as an MMA operand)
         for_acc_chunks(p, N16 / 16, planes ? EPI_CHUNKS : EPI_NONE, dst ? (last_hidden ? 1 : 2) : 0, [&](int c, const uint32_t* r, uint32_t tc) {
             float v[16];
-            uint32_t h[8];
             affine16(r, gc + 16 * c, bb + 16 * c, v);
             uint32_t bits = 0;
 #pragma unroll
@@ -746,9 +747,8 @@ static __device__ __noinline__ uint32_t path_hidden_keep_(PathArg p, const TcNet
             for (int j = 0; j < 8; ++j)
                 up2(add2(pk2(v[2 * j], v[2 * j + 1]), pk2(fmaxf(v[2 * j], 0.f), fmaxf(v[2 * j + 1], 0.f))), v[2 * j], v[2 * j + 1]);
             mk.h[l + 1][c] = bits;
-            if (planes) put16h(tc, v, h);
-            else { uint32_t lo[8]; split16(v, h, lo); }
-            if (dst) copy16h(dst, row, c, h, one_at);                    // (shared ACT image / global copy scratch)
+            if (planes) put16(tc, v);
+            if (dst) copy16f(dst, row, c, v, one_at);                    // (shared ACT image / global copy scratch)
         });
     }
     return p.sync;
@@ -778,6 +778,7 @@ __device__ __forceinline__ void path_drain(PathCtx& p, int blk, int row, int kl,
     // a warp whose 32 rows all lie past the last feature row skips its TMEM loads altogether (the TMEM->register path
     // is the bound of the drain): block 1 of a 200-wide layer has 73 live rows, the input layer's block 21
     const bool warp_live = (128 * blk + (row & ~31)) <= kl;
+    const float inv = pow2f(-p.dexp);                                     // the evaluation ran scaled by 2^dexp
     for (int c = p.grp; warp_live && c < N16 / 16; c += TC_NGRP) {
         uint32_t r[16];
         tmem_ld16(acc + 16 * c, r);
@@ -786,7 +787,8 @@ __device__ __forceinline__ void path_drain(PathCtx& p, int blk, int row, int kl,
 #pragma unroll
         for (int q = 0; q < 4; ++q) {                                     // (columns >= nl of the accumulator are zero)
             const int n = 16 * c + 4 * q;
-            if (n < nl) red_add_v4(dst + (n >> 2) * gstride, __uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]), __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3]));
+            if (n < nl) red_add_v4(dst + (n >> 2) * gstride, __uint_as_float(r[4 * q]) * inv, __uint_as_float(r[4 * q + 1]) * inv,
+                                   __uint_as_float(r[4 * q + 2]) * inv, __uint_as_float(r[4 * q + 3]) * inv);
         }
     }
     tc_fence_before();
@@ -796,22 +798,38 @@ __device__ __forceinline__ void path_drain(PathCtx& p, int blk, int row, int kl,
     TC_STAT(p.t_drain += clock64() - td0;)
 }
 
-// cotangent of the raw output (nl <= 32 values, static indexing) -> planes (+ DZ image), publish
+// cotangent of the raw output (nl <= 32 values, static indexing) -> planes (+ DZ image), publish.  The evaluation runs
+// scaled by 2^dexp, chosen so that the largest |cotangent| of the tile lands in [2^11, 2^12): mxbuf = shared memory, two
+// rows of one word per path warp (alternating, so that one barrier per call is enough).
 template <int NO>
-__device__ __forceinline__ void path_put_dz(PathCtx& p, const TcNet& t, const float (&dout)[NO], unsigned char* dzimg, int row) {
+__device__ __forceinline__ void path_put_dz(PathCtx& p, const TcNet& t, const float (&dout)[NO], unsigned char* dzimg, int row, uint32_t* mxbuf) {
     const int N16 = t.ly[t.L].N16, nl = t.ly[t.L].nl;
+    float m = 0.f;
+#pragma unroll
+    for (int n = 0; n < NO; ++n)
+        if (n < nl) m = fmaxf(m, fabsf(dout[n]));
+    uint32_t mu = __reduce_max_sync(0xffffffffu, __float_as_uint(m));        // (non-negative floats order like their bit patterns)
+    uint32_t* mb = mxbuf + ((p.sync & SY_DZ) ? 8 : 0);
+    p.sync ^= SY_DZ;
+    if ((threadIdx.x & 31) == 0) mb[threadIdx.x >> 5] = mu;
+    asm volatile("bar.sync 2, %0;" ::"r"(TC_PATH_THREADS) : "memory");
+#pragma unroll
+    for (int w = 0; w < TC_PATH_THREADS / 32; ++w) mu = max(mu, mb[w]);
+    const int ex = (int)((mu >> 23) & 0xffu);
+    p.dexp = (ex == 0 || ex == 255) ? 0 : (11 - (ex - 127));                  // zero / denormal / non-finite maximum: no scaling
+    p.dexp = p.dexp < -100 ? -100 : (p.dexp > 100 ? 100 : p.dexp);
+    const float sc = pow2f(p.dexp);
 #pragma unroll
     for (int c = 0; c < 2; ++c) {
         if (c < N16 / 16 && (c % TC_NGRP) == p.grp) {
             float v[16];
-            uint32_t h[8];
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
                 const int n = 16 * c + j;
-                v[j] = (n < NO && n < nl) ? dout[n < NO ? n : 0] : 0.f;
+                v[j] = (n < NO && n < nl) ? dout[n < NO ? n : 0] * sc : 0.f;
             }
-            put16h(path_planes(p) + 16 * c, v, h);
-            if (dzimg) copy16h(dzimg, row, c, h, -1);
+            put16(path_planes(p) + 16 * c, v);
+            if (dzimg) copy16f(dzimg, row, c, v, -1);
         }
     }
     if (dzimg) fence_proxy_async();
@@ -833,14 +851,13 @@ static __device__ __noinline__ uint32_t path_backward_mid_(PathArg p, const TcNe
         for_acc_chunks(p, K16 / 16, need_w ? EPI_ALL : EPI_CHUNKS, need_w ? 1 : 0, [&](int c, const uint32_t* r, uint32_t tc) {
             const uint32_t bits = mk.h[l][c];
             float v[16];
-            uint32_t h[8];
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
                 const float a = __uint_as_float(r[j]);
                 v[j] = ((bits >> j) & 1u) ? 2.f * a : a;                     // d(z + relu z)
             }
-            put16h(tc, v, h);
-            if (need_w) copy16h(dzimg, row, c, h, -1);
+            put16(tc, v);
+            if (need_w) copy16f(dzimg, row, c, v, -1);
         });
     }
     return p.sync;
@@ -854,6 +871,7 @@ template <int NX>
 __device__ __forceinline__ void path_get_dy0(PathCtx& p, const TcNet& t, float (&dy0)[NX]) {
     path_wait_acc(p);
     const uint32_t acc = path_acc(p);
+    const float inv = pow2f(-p.dexp);                                      // the evaluation ran scaled by 2^dexp
     const int K16 = t.ly[0].K16;
 #pragma unroll
     for (int c = 0; c < 2; ++c) {
@@ -864,7 +882,7 @@ __device__ __forceinline__ void path_get_dy0(PathCtx& p, const TcNet& t, float (
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
                 const int k = 16 * c + j;
-                if (k < NX && k < t.in) dy0[k < NX ? k : 0] = __uint_as_float(r[j]);
+                if (k < NX && k < t.in) dy0[k < NX ? k : 0] = __uint_as_float(r[j]) * inv;
             }
         }
     }
@@ -873,8 +891,8 @@ __device__ __forceinline__ void path_get_dy0(PathCtx& p, const TcNet& t, float (
 // gradient slab of the network (need_w); dy0 receives the cotangent of y0.
 template <int NO, int NX>
 __device__ __forceinline__ void path_net_backward(PathCtx& p, const TcNet& t, const TcSlab& g, const Masks& mk, const float (&dout)[NO], bool need_w,
-                                                  float* slab, unsigned char* dzimg, int row, float (&dy0)[NX]) {
-    path_put_dz(p, t, dout, need_w ? dzimg : nullptr, row);
+                                                  float* slab, unsigned char* dzimg, int row, float (&dy0)[NX], uint32_t* mxbuf) {
+    path_put_dz(p, t, dout, need_w ? dzimg : nullptr, row, mxbuf);
     path_backward_mid(p, t, g, mk, need_w, slab, dzimg, row);
     path_get_dy0(p, t, dy0);
 }

@@ -137,8 +137,10 @@ def test_tensor_forward_vs_exact_d20_3x200():
     np.testing.assert_allclose(_npy(yb["delta"])[same], _npy(ya["delta"])[same], **VTOL)
 
 
-GTOL_TENSOR = 1e-2      # stated tolerance of the tensor path: gradients, relative to the gradient's max-norm
-                        # (the dW contraction uses bf16 operands; forward / dX products are bf16x3)
+GTOL_TENSOR = 2e-3      # stated tolerance of the tensor path: gradients, relative to the gradient's max-norm -- the SAME as the
+                        # exact FP32 path's (test_gpu_parity.py).  Forward / dX products are bf16x3 (16 significant bits), the dW
+                        # contraction reads FP16 operand images (11 bits, per-evaluation power-of-two scaling); observed on these
+                        # fixtures (24 paths): <= 4.2e-4, at the BASELINE shapes (1024 paths): <= 2.1e-4
 
 
 def _gerr(got, ref):
