@@ -1,7 +1,7 @@
 // actor_tc_kernel<24, EQ_EKN, 0> (see dpb_tc_inst.cuh)
-// one thread per path (255 registers/thread): measured 7 % faster than two threads per path for the actor kernel
+// helper groups of the actor kernel (dpb_tc_nets.cuh)
 #ifndef DPB_TC_NGRP
-#define DPB_TC_NGRP 1
+#define DPB_TC_NGRP 0
 #endif
 #define DPB_INST_NAME actor_ekn
 #define DPB_INST_KERNEL actor_tc_kernel

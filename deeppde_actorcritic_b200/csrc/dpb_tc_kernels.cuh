@@ -1,9 +1,10 @@
 // dpb_tc_kernels.cuh -- the fused rollout + TD kernels with the MLP layers on tcgen05 (impl = tensor).
 // Same algorithm and per-path arithmetic (dpb_eqn.h) as dpb_kernels.cuh.  CTA = one tile of 128 paths = the 128
-// TMEM lanes; 4 * TC_NGRP path warps (TC_NGRP = 2, critic kernels: threads t and t+128 own path t, state in registers,
-// epilogue chunks split between them; TC_NGRP = 1, actor kernels: one thread per path with 255 registers), then the
+// TMEM lanes.  Warp roles (dpb_tc_nets.cuh): 4 owner warps (thread t owns path t: state in registers, per-path SDE
+// arithmetic, network inputs / outputs), 4 * TC_NGRP stateless helper warps (hidden-layer epilogues, dW drains), the
 // control warp (all lanes run the protocol, the elected lane issues every tcgen05.mma) and the producer warp (lane 0
-// streams the weights).  The group count is a per-translation-unit constant (DPB_TC_NGRP, dpb_tc_nets.cuh).
+// streams the weights).  The body of each kernel is one source compiled once per role, so that all roles walk through the
+// same sequence of products and CTA barriers by construction.
 // Phases per tile -- critic: rollout (actor + NN_value_grad forward) -> NN_value at x_N, x_0, x_bdry (+ backward)
 // -> second sweep re-evaluating NN_value_grad at the stored x_t and back-propagating; actor: rollout -> terminal
 // value (+ input gradient) -> reverse sweep (re-evaluate the actor, adjoint step, back-propagate).
@@ -55,20 +56,20 @@ struct TcSmem {
     unsigned char *act, *dz;
     unsigned char* ring;
     float *vecA, *vecV, *vecG;
-    uint64_t *full, *empty, *acc_full, *a_all, *a_chunk, *act_full;
+    uint64_t *full, *empty, *bars, *act_full;      // bars: the hand-off barriers (BAR_* in dpb_tc_nets.cuh)
     uint32_t* tslot;
     int* tile;                       // the tile a CTA works on next (dynamic tile scheduler)
     Sched* sch;
     ProdCtl* pc;
     float* red;
-    uint32_t* dzmax;                 // [2][8]: exchange of the tile's largest |cotangent| among the path warps (path_put_dz)
+    uint32_t* dzmax;                 // [2][8]: exchange of the tile's largest |cotangent| among the owner warps (own_put_dz); [16]: its exponent
     TcNet *nA, *nV, *nG;             // shared-memory copies of the network descriptors
     TcSlab *gA, *gV, *gG;
 };
 
 // everything except the ring
 __host__ __device__ inline size_t tc_smem_fixed(int vfA, int vfV, int vfG, int actdz_bytes) {
-    return 2 * (size_t)actdz_bytes + (size_t)(vfA + vfV + vfG) * 4 + (2 * MAX_NSLOT + 3 + MAX_CHUNK) * 8 + 64 + sizeof(Sched) + 64 + 64 + 64 + 3 * sizeof(TcNet) + 3 * sizeof(TcSlab) + 64 + 1024;
+    return 2 * (size_t)actdz_bytes + (size_t)(vfA + vfV + vfG) * 4 + (2 * MAX_NSLOT + 1 + NUM_HANDOFF_BARS) * 8 + 64 + sizeof(Sched) + 64 + 64 + 128 + 3 * sizeof(TcNet) + 3 * sizeof(TcSlab) + 64 + 1024;
 }
 __host__ __device__ inline size_t tc_smem_bytes(int vfA, int vfV, int vfG, int actdz_bytes, int nslot, int slot_bytes) {
     return tc_smem_fixed(vfA, vfV, vfG, actdz_bytes) + (size_t)nslot * slot_bytes;
@@ -85,16 +86,14 @@ __device__ __forceinline__ void tc_carve(TcSmem& s, unsigned char* base, const T
     s.vecG = reinterpret_cast<float*>(p); p += (size_t)vfG * 4;
     s.full = reinterpret_cast<uint64_t*>(p); p += MAX_NSLOT * 8;
     s.empty = reinterpret_cast<uint64_t*>(p); p += MAX_NSLOT * 8;
-    s.acc_full = reinterpret_cast<uint64_t*>(p); p += 8;           // acc_full, a_all, a_chunk[16]: contiguous (PathCtx::bars)
-    s.a_all = reinterpret_cast<uint64_t*>(p); p += 8;
-    s.a_chunk = reinterpret_cast<uint64_t*>(p); p += 8 * MAX_CHUNK;
+    s.bars = reinterpret_cast<uint64_t*>(p); p += 8 * NUM_HANDOFF_BARS;
     s.act_full = reinterpret_cast<uint64_t*>(p); p += 8;
     s.tslot = reinterpret_cast<uint32_t*>(p); s.tile = reinterpret_cast<int*>(p) + 4; p += 64;
     s.sch = reinterpret_cast<Sched*>(p); p += sizeof(Sched);
     s.pc = reinterpret_cast<ProdCtl*>(p); p += 64;
     s.red = reinterpret_cast<float*>(((uintptr_t)p + 15) & ~(uintptr_t)15);
     p = reinterpret_cast<unsigned char*>(s.red) + 64;
-    s.dzmax = reinterpret_cast<uint32_t*>(p); p += 64;
+    s.dzmax = reinterpret_cast<uint32_t*>(p); p += 128;            // [2][8] maxima + the exponent word
     s.nA = reinterpret_cast<TcNet*>(p); p += sizeof(TcNet);
     s.nV = reinterpret_cast<TcNet*>(p); p += sizeof(TcNet);
     s.nG = reinterpret_cast<TcNet*>(p); p += sizeof(TcNet);
@@ -113,10 +112,12 @@ __device__ __forceinline__ uint32_t tc_setup(TcSmem& s, const TcArgs& a) {
     if (tid == 0) { *s.nA = a.nA; *s.nV = a.nV; *s.nG = a.nG; *s.gA = a.gA; *s.gV = a.gV; *s.gG = a.gG; }
     if (tid == 0) {
         for (int i = 0; i < MAX_NSLOT; ++i) { mbar_init(&s.full[i], 1); mbar_init(&s.empty[i], 1); }
-        mbar_init(s.acc_full, 1);
-        mbar_init(s.a_all, TC_PATH_THREADS / 32);
-        mbar_init(&s.a_chunk[0], TC_PATH_THREADS / 32);                      // chunk 0: every path warp (see for_acc_chunks)
-        for (int i = 1; i < MAX_CHUNK; ++i) mbar_init(&s.a_chunk[i], 4);     // the four warps of the group that owns the chunk
+        mbar_init(&s.bars[BAR_ACC], 1);
+        mbar_init(&s.bars[BAR_FIN], 1);
+        mbar_init(&s.bars[BAR_HELP], TC_EPI_WARPS);
+        mbar_init(&s.bars[BAR_OWN], TC_OWN_THREADS / 32);
+        mbar_init(&s.bars[BAR_CHUNK], TC_EPI_WARPS);                                    // chunk 0: every helper warp (see for_acc_chunks)
+        for (int i = 1; i < MAX_CHUNK; ++i) mbar_init(&s.bars[BAR_CHUNK + i], 4);       // the four warps of the group that owns the chunk
         mbar_init(s.act_full, 1);
         s.sch->nops = 0;
         s.pc->req = 0; s.pc->gen = 0; s.pc->quit = 0;
@@ -194,64 +195,61 @@ __device__ __forceinline__ void path_dw(const TcArgs& a, long long gpath_local, 
 
 // ------------------------------------------------------------------------------------------------
 // role contexts shared by both kernels
+enum { ROLE_OWN = 0, ROLE_HELP = 1, ROLE_CTRL = 2 };
 struct Roles {
     Ctrl C;
     PathCtx P;
-    bool is_path, is_ctrl, primary;      // primary: the path thread of group 0 (does the global stores of its path)
-    int row;
+    int row;                             // owners / helpers: lane of the tile = path slot this thread works on
 };
 __device__ __forceinline__ void roles_init(Roles& r, const TcSmem& S, const TcArgs& a, uint32_t tmem) {
     const int tid = threadIdx.x, warp = (int)warp_uniform(tid >> 5);
-    r.is_path = warp < TC_CTRL_WARP;
-    r.is_ctrl = (warp == TC_CTRL_WARP);          // the whole warp runs the control protocol (elect_one() issues)
-    r.primary = warp < 4;
     r.row = tid & 127;
     Ctrl& C = r.C;
-    C.ring = S.ring; C.full = S.full; C.empty = S.empty; C.acc_full = S.acc_full; C.a_all = S.a_all; C.a_chunk = S.a_chunk; C.sch = S.sch;
+    C.ring = S.ring; C.full = S.full; C.empty = S.empty; C.bars = S.bars; C.sch = S.sch;
     C.pc = S.pc; C.n_req = 0; C.n_consumed = 0; C.op_count = 0; C.sync = 0; C.tmem = warp_uniform(tmem); C.gen = 0;
     C.act_full = S.act_full; C.act_count = 0; C.nslot = a.nslot; C.slot_bytes = a.slot_bytes; C.act = S.act; C.dz = S.dz;
+    C.dexp = reinterpret_cast<volatile int*>(S.dzmax + 16);
     r.P.tl = tmem + ((uint32_t)((warp & 3) * 32) << 16);
-    r.P.grp = (warp >> 2) % TC_NGRP;
-    r.P.bars = smem_u32(S.acc_full); r.P.sync = 0; r.P.dexp = 0;
+    r.P.grp = warp >= 4 ? ((warp - 4) >> 2) % TC_EGRP : 0;
+    r.P.bars = smem_u32(S.bars); r.P.sync = 0; r.P.dexp = 0;
     TC_STAT(r.P.t_accw = 0; r.P.t_epi = 0; r.P.t_hid = 0; r.P.t_drain = 0; r.P.t_mark = clock64();)
     TC_STAT(C.t_aready = 0; C.t_issue = 0; C.t_accw = 0; C.t_dw_ready = 0; C.t_act = 0;)
     C.n_ops = 0;
     C.mm_slot = 0; C.mm_use = 0;
 }
-// stats row: [0] kernel cycles, ctrl: [1] waiting for the path threads, [2] waiting for weights, [3] ops;
-// path thread 0: [4] waiting for the tensor pipe, [5] epilogue (wake-up -> publish)
+// stats row: [0] kernel cycles, ctrl: [1] waiting for owners / helpers, [2] dW products waiting for their operands, [3] ops,
+// [7] inside issue loops, [8] waiting for the MMAs that read ACT; owner thread 0: [4] waiting for network results, [5] writing
+// inputs; helper thread 128: [6] inside hidden-layer epilogues, [9] waiting for the tensor pipe, [10] in dW drains
 __device__ __forceinline__ void roles_stats(const Roles& r, const TcArgs& a, long long t_start) {
     if (!a.stats) return;
     long long* st = a.stats + (size_t)blockIdx.x * 16;
-    if (r.is_ctrl && (threadIdx.x & 31) == 0) {
+    if ((threadIdx.x >> 5) == TC_CTRL_WARP && (threadIdx.x & 31) == 0) {
         st[0] = clock64() - t_start; st[3] = r.C.n_ops;
         TC_STAT(st[1] = r.C.t_aready; st[2] = r.C.t_dw_ready; st[7] = r.C.t_issue; st[8] = r.C.t_accw;)
     }
-    TC_STAT(if (threadIdx.x == 0) { st[4] = r.P.t_accw; st[5] = r.P.t_epi; st[6] = r.P.t_hid; })
+    TC_STAT(if (threadIdx.x == 0) { st[4] = r.P.t_accw; st[5] = r.P.t_epi; })
+    TC_STAT(if (threadIdx.x == 128) { st[6] = r.P.t_hid; st[9] = r.P.t_accw; st[10] = r.P.t_drain; })
 }
 
-// Input-layer sums SX[k] = sum x_k dy0_k, S0[k] = sum dy0_k.  The two threads of a path split the components: group g
-// (0: threads 0..127, 1: threads 128..255) accumulates k in [g*DH, g*DH + DH), DH = DPX/2, in DH registers each (all
-// indices static -- a run-time index anywhere would put the accumulators in local memory).
+// Input-layer sums SX[k] = sum x_k dy0_k, S0[k] = sum dy0_k, kept by the owner threads in registers (all indices static -- a
+// run-time index anywhere would put the accumulators in local memory).
 template <int DPX>
-__device__ __forceinline__ void acc_input_sums(float (&sx)[DPX / TC_NGRP], float (&s0)[DPX / TC_NGRP], const float (&x)[DPX], const float (&dy0)[DPX], int grp, int d) {
-    constexpr int DH = DPX / TC_NGRP;
+__device__ __forceinline__ void acc_input_sums(float (&sx)[DPX], float (&s0)[DPX], const float (&x)[DPX], const float (&dy0)[DPX], int d) {
 #pragma unroll
-    for (int j = 0; j < DH; ++j) {
-        const float xs = (TC_NGRP > 1 && grp) ? x[(DH + j) % DPX] : x[j], ds = (TC_NGRP > 1 && grp) ? dy0[(DH + j) % DPX] : dy0[j];
-        if (grp * DH + j < d) { sx[j] += xs * ds; s0[j] += ds; }
-    }
+    for (int j = 0; j < DPX; ++j)
+        if (j < d) { sx[j] += x[j] * dy0[j]; s0[j] += dy0[j]; }
 }
-// kernel end: sum over the path threads of each group -> atomicAdd into dst[g*DH + j]
-template <int DH>
-__device__ __forceinline__ void reduce_rows_to(float* dst, const float (&acc)[DH], int d, int grp, bool is_path) {
+// sum over the owner threads -> atomicAdd into dst[k]
+template <int DPX>
+__device__ __forceinline__ void reduce_rows_to(float* dst, const float (&acc)[DPX], int d) {
 #pragma unroll
-    for (int j = 0; j < DH; ++j) {
-        float v = is_path ? acc[j] : 0.f;
+    for (int j = 0; j < DPX; ++j) {
+        if (j < d) {                                                  // (d is uniform: the shuffles stay convergent)
+            float v = acc[j];
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        const int k = grp * DH + j;
-        if (is_path && k < d && (threadIdx.x & 31) == 0) atomicAdd(dst + k, v);
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if ((threadIdx.x & 31) == 0) atomicAdd(dst + j, v);
+        }
     }
 }
 
@@ -259,24 +257,21 @@ __device__ __forceinline__ void reduce_rows_to(float* dst, const float (&acc)[DH
 // DP > 0: instantiation for dim (and control_dim + 1) <= DP with equation EQN fixed at compile time -- the
 // per-path vectors are register arrays and every d-loop is unrolled (MV > 0: VDP with control_dim = MV, which makes its
 // cyclic neighbour indices static); <0,-1,0>: generic run-time version.
-// The body is compiled once per role (IS_PATH: a path warp, otherwise the control warp): the same source, so both roles run
-// the same sequence of CTA barriers by construction, but each role's code is a branch of its own -- its registers are
-// allocated separately, which is what lets `setmaxnreg` give the path warps more than the launch bound.
-template <int DP, int EQN, int MV, bool IS_PATH>
+// The body is compiled once per role (owner / helper / control warp): the same source, so all roles run the same sequence of
+// products and CTA barriers by construction, but each role's code is a branch of its own with its own register allocation.
+template <int DP, int EQN, int MV, int ROLE>
 __device__ __forceinline__ void critic_tc_body(const TcArgs& a, const TcSmem& S, Roles& R) {
     constexpr int DPX = DP > 0 ? DP : 32;
+    constexpr bool is_own = ROLE == ROLE_OWN, is_help = ROLE == ROLE_HELP, is_ctrl = ROLE == ROLE_CTRL;
     Ctrl& C = R.C;
     PathCtx& P = R.P;
     const TcNet& nA = *S.nA;
     const TcNet& nV = *S.nV;
     const TcNet& nG = *S.nG;
-    const TcSlab& gA = *S.gA;
     const TcSlab& gV = *S.gV;
     const TcSlab& gG = *S.gG;
-    (void)gA; (void)gV; (void)gG;
+    (void)gV; (void)gG;
     const int tid = threadIdx.x;
-    constexpr bool is_path = IS_PATH, is_ctrl = !IS_PATH;
-    const bool primary = R.primary;
     const int row = R.row;
     const Eq<float>& E = a.eqf;                                   // kernel-parameter space: fields are constant-bank operands
     const int d = E.d, N = a.N, sr = a.sr;
@@ -289,25 +284,24 @@ __device__ __forceinline__ void critic_tc_body(const TcArgs& a, const TcSmem& S,
     unsigned char* copies = a.copies ? a.copies + (size_t)blockIdx.x * a.copies_per_cta : nullptr;
     float* gsV = a.slabV ? a.slabV + (size_t)(blockIdx.x % a.nslab) * gV.gtotal : nullptr;
     float* gsG = a.slabG ? a.slabG + (size_t)(blockIdx.x % a.nslab) * gG.gtotal : nullptr;
+    uint32_t* mxbuf = S.dzmax;
+    volatile int* dexp = reinterpret_cast<volatile int*>(S.dzmax + 16);
+    (void)traj; (void)copies; (void)gsV; (void)gsG; (void)mxbuf; (void)dexp; (void)scale; (void)fill; (void)sr; (void)row;
 
     float loss0 = 0.f, loss1 = 0.f;
-    TC_STAT(long long ph_roll = 0, ph_val = 0, ph_grad = 0;)          // cycles per phase (diagnostics)
-    TC_STAT(long long seg_dw = 0, seg_A = 0, seg_mv = 0, seg_G = 0;)
     const long long ntiles = (a.B_local + TC_PATHS - 1) / TC_PATHS;
     for (long long tile = blockIdx.x; tile < ntiles; tile = tc_next_tile(S, a)) {
         const long long base = tile * TC_PATHS;
         const long long slot = base + row;                        // position of this thread's path in the tiling
-        const bool valid = is_path && slot < a.B_local;
+        const bool valid = is_own && slot < a.B_local;
         const long long gp = (valid && a.perm) ? (long long)a.perm[slot] : slot;      // local path index of this thread
-        const bool wr = valid && primary;               // this thread does the global stores of its path
-        TC_STAT(const long long tp0 = clock64();)
         float x[DPX], u[DPX], dwv[DPX], sdw[DPX], g[DPX], raw[DPX];
         int flag = 0, nacc = 0;
         float disc = 1.f, y = 0.f;
-        if (is_path) {
+        if (is_own) {
             KLOOP(k, d) x[k] = valid ? a.x0[gp * d + k] : fill;
             flag = fwd_initial_flag<float, DP, EQN, MV>(E, x, 1, 0);
-            if (a.o_x && wr)
+            if (a.o_x && valid)
                 KLOOP(k, d) a.o_x[(gp * d + k) * (long long)(N + 1)] = x[k];
         }
         if (is_ctrl) {                                            // schedule of the rollout
@@ -325,54 +319,46 @@ __device__ __forceinline__ void critic_tc_body(const TcArgs& a, const TcSmem& S,
             if (is_ctrl) {
                 if (!cheat) ctrl_net_forward(C, nA, nA.L);
                 if (td1) ctrl_net_forward(C, nG, nG.L);
-            } else if (is_path) {
-                // per-path arithmetic is placed where the tensor pipe is busy with a first layer
-                if (!cheat) { path_net_begin(P, nA, S.vecA, x); path_hidden_range(P, nA, S.vecA, 0, 1); }
-                TC_STAT(const long long q1 = clock64();)
+            } else if (is_help) {
+                if (!cheat) help_forward(P, nA, S.vecA);
+                if (td1) help_forward(P, nG, S.vecG);
+            } else {
+                // the owners' arithmetic runs while the helpers and the tensor pipe work through the networks
+                if (!cheat) own_put_y0(P, nA, S.vecA, x, nullptr, 0);
                 path_dw(a, gp, valid, t, dwv);
-                TC_STAT(const long long q1b = clock64(); seg_dw += q1b - q1;)
-                if (!cheat) path_hidden_range(P, nA, S.vecA, 1, 2);
                 float dt, sqdt, xn; int dtg;
-                TC_STAT(const long long q2 = clock64();)
                 fwd_dt<float, DP, EQN, MV>(E, x, flag, 1, 0, dt, sqdt, xn, dtg);
-                TC_STAT(seg_A += clock64() - q2;)
                 if (cheat) {
                     eq_u_true<float, DP, EQN, MV>(E, x, u, 1, 0);
                 } else {
-                    path_net_finish(P, nA, S.vecA, raw, 2);
+                    if (TC_COMBINED) help_forward(P, nA, S.vecA);
+                    own_last(P, nA, S.vecA, raw);
                     if (nA.ekn_head) ekn_head_fwd<float, DP, EQN, MV>(raw, u, nA.mctrl, 1, 0);
                     else KLOOP(j, E.m) u[j] = raw[j];
                 }
-                if (td1) path_net_begin(P, nG, S.vecG, x);                        // NN_value_grad at x_t (before the move)
-                TC_STAT(const long long q3 = clock64();)
+                if (td1) own_put_y0(P, nG, S.vecG, x, nullptr, 0);                // NN_value_grad at x_t (before the move)
                 float* tr = traj + (size_t)t * 2 * sr * TC_PATHS;
-                if (need_grad && td1 && primary)
+                if (need_grad && td1)
                     KLOOP(k, d) __stcs(&tr[k * TC_PATHS + row], x[k]);
                 float w = 0.f;
                 if (!prop_only) w = eq_w<float, DP, EQN, MV>(E, x, u, 1, 0);
-                TC_STAT(const long long q3b = clock64(); seg_mv += q3b - q3;)
-                if (td1) path_hidden_range(P, nG, S.vecG, 0, 1);
-                TC_STAT(const long long q3c = clock64();)
                 const int coef = fwd_move<float, DP, EQN, MV>(E, x, u, dwv, dt, sqdt, xn, flag, sdw, 1, 0);
                 const float cf = (float)coef;
-                TC_STAT(const long long q4 = clock64(); seg_mv += q4 - q3c;)
-                if (td1) path_net_finish(P, nG, S.vecG, g, 1);
-                TC_STAT(const long long q5 = clock64();)
+                if (td1) { if (TC_COMBINED) help_forward(P, nG, S.vecG); own_last(P, nG, S.vecG, g); }
                 y = y + w * disc * cf * dt;                                       // solver.py:170-174
                 if (td1) {
                     float dif = 0.f;
                     KLOOP(k, d) dif = dif + sdw[k] * g[k];        // solver.py:177-182
                     dif = dif * disc;
                     y = y - dif * cf * sqdt;                                      // solver.py:184
-                    if (need_grad && primary) {
+                    if (need_grad) {
                         const float q = disc * cf * sqdt;
                         KLOOP(k, d) __stcs(&tr[(sr + k) * TC_PATHS + row], sdw[k] * q);
                     }
                 }
                 disc = disc * expf(-E.gamma * dt * cf);                          // solver.py:187
-                TC_STAT(seg_G += clock64() - q5;)
                 nacc += coef;
-                if (wr) {
+                if (valid) {
                     if (a.o_dt) a.o_dt[gp * N + t] = dt;
                     if (a.o_coef) a.o_coef[gp * N + t] = cf;
                     if (a.o_x)
@@ -380,7 +366,7 @@ __device__ __forceinline__ void critic_tc_body(const TcArgs& a, const TcSmem& S,
                 }
             }
         }
-        if (wr) {
+        if (valid) {
             for (int t = tlive; t < N; ++t) {
                 if (a.o_dt) a.o_dt[gp * N + t] = E.delta_t;
                 if (a.o_coef) a.o_coef[gp * N + t] = 0.f;
@@ -389,7 +375,6 @@ __device__ __forceinline__ void critic_tc_body(const TcArgs& a, const TcSmem& S,
             }
             if (a.o_exit) a.o_exit[gp] = nacc;
         }
-        TC_STAT(const long long tp1 = clock64(); ph_roll += tp1 - tp0;)
         if (prop_only) continue;
         // ------------------------------------------------------------------ NN_value at x_0, x_N, x_bdry
         float rho_v = 0.f, rho_b = 0.f, rhog = 0.f;
@@ -404,45 +389,57 @@ __device__ __forceinline__ void critic_tc_body(const TcArgs& a, const TcSmem& S,
                 for (int i = 0; i < 3; ++i) { sched_add_fwd(C, nV, a.imgV, nV.L); sched_add_bwd(C, nV, a.imgV); }
                 ctrl_sched_ready(C);
                 ctrl_net_forward(C, nV, nV.L);
-                for (int i = 0; i < 3; ++i) { ctrl_net_forward(C, nV, nV.L); ctrl_net_backward(C, nV, true, copies); }
+                for (int i = 0; i < 3; ++i) { ctrl_net_forward(C, nV, nV.L); ctrl_net_backward(C, nV, true, copies, false); }
             }
-        } else if (is_path) {
+        } else if (is_help) {
+            if (!need_grad) {
+                for (int i = 0; i < 3; ++i) help_forward(P, nV, S.vecV);
+            } else {
+                Masks mk;
+                help_forward(P, nV, S.vecV);
+                for (int i = 0; i < 3; ++i) {
+                    help_forward_keep(P, nV, S.vecV, mk, copies, S.act, row, false);
+                    help_backward(P, nV, gV, mk, true, gsV, S.dz, row, dexp);
+                }
+            }
+        } else {
             float vN[1], v0[1], vb[1], x0v[DPX], xbv[DPX], dy0[DPX], cot[1];
             KLOOP(k, d) x0v[k] = valid ? a.x0[gp * d + k] : fill;
             KLOOP(k, d) xbv[k] = valid ? a.xb[gp * d + k] : fill;
             if (!need_grad) {
-                path_net_forward(P, nV, S.vecV, x0v, v0);
-                path_net_forward(P, nV, S.vecV, x, vN);
-                path_net_forward(P, nV, S.vecV, xbv, vb);
+                own_net_forward(P, nV, S.vecV, x0v, v0);
+                own_net_forward(P, nV, S.vecV, x, vN);
+                own_net_forward(P, nV, S.vecV, xbv, vb);
             } else {
-                Masks mk;
                 // (the input-layer sums of NN_value are flushed once per tile: three updates do not justify registers that
                 //  stay live through both sweeps)
-                float sxV[DPX / TC_NGRP], s0V[DPX / TC_NGRP];
+                float sxV[DPX], s0V[DPX];
 #pragma unroll
-                for (int k = 0; k < DPX / TC_NGRP; ++k) { sxV[k] = 0.f; s0V[k] = 0.f; }
-                path_net_forward(P, nV, S.vecV, x0v, v0);
-                path_net_forward_keep(P, nV, S.vecV, x, vN, mk, copies, S.act, row, false);
+                for (int k = 0; k < DPX; ++k) { sxV[k] = 0.f; s0V[k] = 0.f; }
+                Masks mkc;                                                        // (combined mode only)
+                const HelpArgs hv = {&mkc, copies, S.act, &gV, gsV};
+                own_net_forward(P, nV, S.vecV, x0v, v0);
+                own_net_forward_keep(P, nV, S.vecV, x, vN, copies, row, false, hv);
                 const float delta = v0[0] - y - vN[0] * disc;
                 rhog = valid ? rho_grad(delta, 50.f) * scale : 0.f;
                 cot[0] = -rhog * disc;
-                path_net_backward(P, nV, gV, mk, cot, true, gsV, S.dz, row, dy0, S.dzmax);
-                acc_input_sums<DPX>(sxV, s0V, x, dy0, P.grp, d);
-                path_net_forward_keep(P, nV, S.vecV, x0v, v0, mk, copies, S.act, row, false);
+                own_net_backward(P, nV, cot, true, S.dz, row, dy0, mxbuf, dexp, false, hv);
+                acc_input_sums<DPX>(sxV, s0V, x, dy0, d);
+                own_net_forward_keep(P, nV, S.vecV, x0v, v0, copies, row, false, hv);
                 cot[0] = rhog;
-                path_net_backward(P, nV, gV, mk, cot, true, gsV, S.dz, row, dy0, S.dzmax);
-                acc_input_sums<DPX>(sxV, s0V, x0v, dy0, P.grp, d);
-                path_net_forward_keep(P, nV, S.vecV, xbv, vb, mk, copies, S.act, row, false);
+                own_net_backward(P, nV, cot, true, S.dz, row, dy0, mxbuf, dexp, false, hv);
+                acc_input_sums<DPX>(sxV, s0V, x0v, dy0, d);
+                own_net_forward_keep(P, nV, S.vecV, xbv, vb, copies, row, false, hv);
                 const float dbb = vb[0] - eq_Z<float, DP, EQN, MV>(E, xbv, 1, 0);
                 cot[0] = valid ? rho_grad(dbb, 50.f) * scale : 0.f;
-                path_net_backward(P, nV, gV, mk, cot, true, gsV, S.dz, row, dy0, S.dzmax);
-                acc_input_sums<DPX>(sxV, s0V, xbv, dy0, P.grp, d);
-                reduce_rows_to(gsV + gV.gX, sxV, d, P.grp, true);
-                reduce_rows_to(gsV + gV.g0, s0V, d, P.grp, true);
+                own_net_backward(P, nV, cot, true, S.dz, row, dy0, mxbuf, dexp, false, hv);
+                acc_input_sums<DPX>(sxV, s0V, xbv, dy0, d);
+                reduce_rows_to<DPX>(gsV + gV.gX, sxV, d);
+                reduce_rows_to<DPX>(gsV + gV.g0, s0V, d);
             }
             const float delta = v0[0] - y - vN[0] * disc;                         // solver.py:189
             const float db = vb[0] - eq_Z<float, DP, EQN, MV>(E, xbv, 1, 0);                          // solver.py:190
-            if (wr) {
+            if (valid) {
                 rho_v = rho(delta, 50.f);
                 rho_b = rho(db, 50.f);
                 if (a.o_delta) a.o_delta[gp] = delta;
@@ -451,7 +448,6 @@ __device__ __forceinline__ void critic_tc_body(const TcArgs& a, const TcSmem& S,
         }
         loss0 += tc_block_sum(rho_v, S.red);
         loss1 += tc_block_sum(rho_b, S.red);
-        TC_STAT(const long long tp2 = clock64(); ph_val += tp2 - tp1;)
         // ------------------------------------------------------------------ sweep 2: NN_value_grad backward
         if (need_grad && td1) {
             if (is_ctrl) {
@@ -461,30 +457,35 @@ __device__ __forceinline__ void critic_tc_body(const TcArgs& a, const TcSmem& S,
                 ctrl_sched_ready(C);
                 for (int t = 0; t < tlive; ++t) {
                     ctrl_net_forward(C, nG, nG.L - 1);
-                    ctrl_net_backward(C, nG, true, copies);
+                    ctrl_net_backward(C, nG, true, copies, true);
                 }
-            } else if (is_path) {
+            } else if (is_help) {
                 Masks mk;
+                for (int t = 0; t < tlive; ++t) {
+                    help_forward_keep(P, nG, S.vecG, mk, copies, S.act, row, true);
+                    help_backward(P, nG, gG, mk, true, gsG, S.dz, row, dexp);
+                }
+            } else {
                 float xt[DPX], cot[DPX], dy0[DPX];
                 // (input-layer sums of this tile: live in this sweep only, flushed into the slab at its end)
-                float sxG[DPX / TC_NGRP], s0G[DPX / TC_NGRP];
+                float sxG[DPX], s0G[DPX];
 #pragma unroll
-                for (int k = 0; k < DPX / TC_NGRP; ++k) { sxG[k] = 0.f; s0G[k] = 0.f; }
+                for (int k = 0; k < DPX; ++k) { sxG[k] = 0.f; s0G[k] = 0.f; }
+                Masks mkc;                                                        // (combined mode only)
+                const HelpArgs hg = {&mkc, copies, S.act, &gG, gsG};
                 for (int t = 0; t < tlive; ++t) {
                     const float* tr = traj + (size_t)t * 2 * sr * TC_PATHS;
                     KLOOP(k, d) { xt[k] = __ldcs(&tr[k * TC_PATHS + row]); cot[k] = __ldcs(&tr[(sr + k) * TC_PATHS + row]) * rhog; }
-                    float unused[1];
-                    path_net_forward_keep(P, nG, S.vecG, xt, unused, mk, copies, S.act, row, true);
-                    path_net_backward(P, nG, gG, mk, cot, true, gsG, S.dz, row, dy0, S.dzmax);
-                    acc_input_sums<DPX>(sxG, s0G, xt, dy0, P.grp, d);
+                    float none[1];
+                    own_net_forward_keep(P, nG, S.vecG, xt, none, copies, row, true, hg);
+                    own_net_backward(P, nG, cot, true, S.dz, row, dy0, mxbuf, dexp, true, hg);
+                    acc_input_sums<DPX>(sxG, s0G, xt, dy0, d);
                 }
-                reduce_rows_to(gsG + gG.gX, sxG, d, P.grp, true);
-                reduce_rows_to(gsG + gG.g0, s0G, d, P.grp, true);
+                reduce_rows_to<DPX>(gsG + gG.gX, sxG, d);
+                reduce_rows_to<DPX>(gsG + gG.g0, s0G, d);
             }
         }
-        TC_STAT(ph_grad += clock64() - tp2;)
     }
-    TC_STAT(if (a.stats && tid == 0) { long long* st = a.stats + (size_t)blockIdx.x * 16; st[9] = ph_roll; st[10] = ph_val; st[11] = ph_grad; st[12] = seg_dw; st[13] = seg_A; st[14] = seg_mv; st[15] = seg_G; })
     if (is_ctrl) { ctrl_flush(C); C.pc->quit = 1; }
     if (tid == 0 && a.loss_part) {
         a.loss_part[blockIdx.x * 2] = loss0;
@@ -504,16 +505,16 @@ __device__ __forceinline__ void critic_tc_body(const TcArgs& a, const TcSmem& S,
         roles_init(R, S, a, tmem);                                                                                            \
         const long long t_start = clock64();                                                                                  \
         const int warp = threadIdx.x >> 5;                                                                                    \
-        if (warp >= TC_CTRL_WARP) {                      /* control, producer (lane 0 streams the weights), idle warps */     \
-            tc_regs_release();                                                                                                \
+        if (warp >= TC_CTRL_WARP) {                      /* control, producer (lane 0 streams the weights) */                  \
             if (warp == TC_PROD_WARP) {                                                                                       \
                 if ((threadIdx.x & 31) == 0) producer_loop(S.ring, S.full, S.empty, S.sch, S.pc, a.nslot, a.slot_bytes);      \
-            } else if (warp == TC_CTRL_WARP) {                                                                                \
-                NAME##_tc_body<DP, EQN, MV, false>(a, S, R);                                                                  \
+            } else {                                                                                                          \
+                NAME##_tc_body<DP, EQN, MV, ROLE_CTRL>(a, S, R);                                                              \
             }                                                                                                                 \
+        } else if (warp >= 4) {                                                                                               \
+            NAME##_tc_body<DP, EQN, MV, ROLE_HELP>(a, S, R);                                                                  \
         } else {                                                                                                              \
-            tc_regs_take();                                                                                                   \
-            NAME##_tc_body<DP, EQN, MV, true>(a, S, R);                                                                       \
+            NAME##_tc_body<DP, EQN, MV, ROLE_OWN>(a, S, R);                                                                   \
         }                                                                                                                     \
         roles_stats(R, a, t_start);                                                                                           \
         tc_fence_before();                                                                                                    \
@@ -522,24 +523,18 @@ __device__ __forceinline__ void critic_tc_body(const TcArgs& a, const TcSmem& S,
     }
 
 // =================================================================================== actor (tensor)
-// The body is compiled once per role (IS_PATH: a path warp, otherwise the control warp): the same source, so both roles run
-// the same sequence of CTA barriers by construction, but each role's code is a branch of its own -- its registers are
-// allocated separately, which is what lets `setmaxnreg` give the path warps more than the launch bound.
-template <int DP, int EQN, int MV, bool IS_PATH>
+template <int DP, int EQN, int MV, int ROLE>
 __device__ __forceinline__ void actor_tc_body(const TcArgs& a, const TcSmem& S, Roles& R) {
     constexpr int DPX = DP > 0 ? DP : 32;
+    constexpr bool is_own = ROLE == ROLE_OWN, is_help = ROLE == ROLE_HELP, is_ctrl = ROLE == ROLE_CTRL;
     Ctrl& C = R.C;
     PathCtx& P = R.P;
     const TcNet& nA = *S.nA;
     const TcNet& nV = *S.nV;
-    const TcNet& nG = *S.nG;
     const TcSlab& gA = *S.gA;
     const TcSlab& gV = *S.gV;
-    const TcSlab& gG = *S.gG;
-    (void)gA; (void)gV; (void)gG; (void)nG;
+    (void)gA; (void)gV;
     const int tid = threadIdx.x;
-    constexpr bool is_path = IS_PATH, is_ctrl = !IS_PATH;
-    const bool primary = R.primary;
     const int row = R.row;
     const Eq<float>& E = a.eqf;                                   // kernel-parameter space: fields are constant-bank operands
     const int d = E.d, m = E.m, N = a.N, sr = a.sr;
@@ -550,30 +545,29 @@ __device__ __forceinline__ void actor_tc_body(const TcArgs& a, const TcSmem& S, 
     float* traj = a.scratch + (size_t)blockIdx.x * a.scratch_per_cta;               // [N][2*sr + A_NSCAL][128]
     unsigned char* copies = a.copies ? a.copies + (size_t)blockIdx.x * a.copies_per_cta : nullptr;
     float* gsA = a.slabA ? a.slabA + (size_t)(blockIdx.x % a.nslab) * gA.gtotal : nullptr;
+    uint32_t* mxbuf = S.dzmax;
+    volatile int* dexp = reinterpret_cast<volatile int*>(S.dzmax + 16);
+    (void)traj; (void)copies; (void)gsA; (void)mxbuf; (void)dexp; (void)fill; (void)m; (void)row; (void)trs;
 
-    // (kept for the whole kernel: scoping them to the reverse sweep of a tile, as the critic does with its sums, made the
-    //  actor 1.6 % slower)
-    float sxA[DPX / TC_NGRP], s0A[DPX / TC_NGRP];
+    // input-layer sums of the actor network (owners): kept for the whole kernel, flushed once
+    float sxA[DPX], s0A[DPX];
 #pragma unroll
-    for (int k = 0; k < DPX / TC_NGRP; ++k) { sxA[k] = 0.f; s0A[k] = 0.f; }
+    for (int k = 0; k < DPX; ++k) { sxA[k] = 0.f; s0A[k] = 0.f; }
 
     float loss0 = 0.f;
-    TC_STAT(long long seg_fk = 0, seg_adj = 0, seg_bwd = 0, seg_fwd = 0;)   // reverse step: forward_keep / adjoint step / backward; forward rollout
     const long long ntiles = (a.B_local + TC_PATHS - 1) / TC_PATHS;
     for (long long tile = blockIdx.x; tile < ntiles; tile = tc_next_tile(S, a)) {
         const long long base = tile * TC_PATHS;
         const long long slot = base + row;
-        const bool valid = is_path && slot < a.B_local;
+        const bool valid = is_own && slot < a.B_local;
         const long long gp = (valid && a.perm) ? (long long)a.perm[slot] : slot;
-        TC_STAT(const long long f0 = clock64();)
-        const bool wr = valid && primary;               // this thread does the global stores of its path
         float x[DPX], u[DPX], dwv[DPX], raw[DPX];
         int flag = 0, nacc = 0;
         float disc = 1.f, y = 0.f;
-        if (is_path) {
+        if (is_own) {
             KLOOP(k, d) x[k] = valid ? a.x0[gp * d + k] : fill;
             flag = fwd_initial_flag<float, DP, EQN, MV>(E, x, 1, 0);
-            if (a.o_x && wr)
+            if (a.o_x && valid)
                 KLOOP(k, d) a.o_x[(gp * d + k) * (long long)(N + 1)] = x[k];
         }
         if (is_ctrl) {
@@ -589,26 +583,28 @@ __device__ __forceinline__ void actor_tc_body(const TcArgs& a, const TcSmem& S, 
             tlive = t + 1;
             if (is_ctrl) {
                 if (!cheat) ctrl_net_forward(C, nA, nA.L);
-            } else if (is_path) {
-                if (!cheat) { path_net_begin(P, nA, S.vecA, x); path_hidden_range(P, nA, S.vecA, 0, 1); }
+            } else if (is_help) {
+                if (!cheat) help_forward(P, nA, S.vecA);
+            } else {
+                if (!cheat) own_put_y0(P, nA, S.vecA, x, nullptr, 0);
                 path_dw(a, gp, valid, t, dwv);
-                if (!cheat) path_hidden_range(P, nA, S.vecA, 1, 2);
                 float dt, sqdt, xn; int dtg;
                 fwd_dt<float, DP, EQN, MV>(E, x, flag, 1, 0, dt, sqdt, xn, dtg);
+                float* tr = traj + (size_t)t * trs * TC_PATHS;
+                if (need_grad)
+                    KLOOP(k, d) { __stcs(&tr[k * TC_PATHS + row], x[k]); __stcs(&tr[(sr + k) * TC_PATHS + row], dwv[k]); }
                 if (cheat) {
                     eq_u_true<float, DP, EQN, MV>(E, x, u, 1, 0);
                 } else {
-                    path_net_finish(P, nA, S.vecA, raw, 2);
+                    if (TC_COMBINED) help_forward(P, nA, S.vecA);
+                    own_last(P, nA, S.vecA, raw);
                     if (nA.ekn_head) ekn_head_fwd<float, DP, EQN, MV>(raw, u, nA.mctrl, 1, 0);
                     else KLOOP(j, m) u[j] = raw[j];
                 }
-                float* tr = traj + (size_t)t * trs * TC_PATHS;
-                if (need_grad && primary)
-                    KLOOP(k, d) { __stcs(&tr[k * TC_PATHS + row], x[k]); __stcs(&tr[(sr + k) * TC_PATHS + row], dwv[k]); }
                 const float w = eq_w<float, DP, EQN, MV>(E, x, u, 1, 0);
                 const int coef = fwd_move<float, DP, EQN, MV>(E, x, u, dwv, dt, sqdt, xn, flag, (float*)nullptr, 1, 0);
                 const float cf = (float)coef;
-                if (need_grad && primary) {
+                if (need_grad) {
                     float* sc = tr + (size_t)2 * sr * TC_PATHS;
                     sc[A_DT * TC_PATHS + row] = dt; sc[A_SQDT * TC_PATHS + row] = sqdt; sc[A_COEF * TC_PATHS + row] = valid ? cf : 0.f;
                     sc[A_DISC * TC_PATHS + row] = disc; sc[A_XN * TC_PATHS + row] = xn; sc[A_DTG * TC_PATHS + row] = (float)dtg;
@@ -616,7 +612,7 @@ __device__ __forceinline__ void actor_tc_body(const TcArgs& a, const TcSmem& S, 
                 y = y + cf * w * dt * disc;                                       // solver.py:218
                 disc = disc * expf(-E.gamma * dt * cf);                          // solver.py:219
                 nacc += coef;
-                if (wr) {
+                if (valid) {
                     if (a.o_dt) a.o_dt[gp * N + t] = dt;
                     if (a.o_coef) a.o_coef[gp * N + t] = cf;
                     if (a.o_x)
@@ -624,7 +620,7 @@ __device__ __forceinline__ void actor_tc_body(const TcArgs& a, const TcSmem& S, 
                 }
             }
         }
-        if (wr) {
+        if (valid) {
             for (int t = tlive; t < N; ++t) {
                 if (a.o_dt) a.o_dt[gp * N + t] = E.delta_t;
                 if (a.o_coef) a.o_coef[gp * N + t] = 0.f;
@@ -633,7 +629,6 @@ __device__ __forceinline__ void actor_tc_body(const TcArgs& a, const TcSmem& S, 
             }
             if (a.o_exit) a.o_exit[gp] = nacc;
         }
-        TC_STAT(seg_fwd += clock64() - f0;)
         // ------------------------------------------------------------------ terminal value (+ its input gradient)
         float yv = 0.f;
         float lam[DPX];
@@ -645,9 +640,19 @@ __device__ __forceinline__ void actor_tc_body(const TcArgs& a, const TcSmem& S, 
                 if (need_grad) sched_add_bwd(C, nV, a.imgV);
                 ctrl_sched_ready(C);
                 ctrl_net_forward(C, nV, nV.L);
-                if (need_grad) ctrl_net_backward(C, nV, false, nullptr);
+                if (need_grad) ctrl_net_backward(C, nV, false, nullptr, false);
             }
-        } else if (is_path) {
+        } else if (is_help) {
+            if (!cheat_v) {
+                if (!need_grad) {
+                    help_forward(P, nV, S.vecV);
+                } else {
+                    Masks mk;
+                    help_forward_keep(P, nV, S.vecV, mk, nullptr, nullptr, row, false);
+                    help_backward(P, nV, gV, mk, false, nullptr, nullptr, row, dexp);
+                }
+            }
+        } else {
             float vN[1];
             const float seed = valid ? disc * a.invB : 0.f;
             if (cheat_v) {
@@ -657,19 +662,20 @@ __device__ __forceinline__ void actor_tc_body(const TcArgs& a, const TcSmem& S, 
                     KLOOP(k, d) lam[k] = lam[k] * seed;
                 }
             } else if (!need_grad) {
-                path_net_forward(P, nV, S.vecV, x, vN);                         // solver.py:221
+                own_net_forward(P, nV, S.vecV, x, vN);                          // solver.py:221
             } else {
-                Masks mk;
                 float cot[1], dy0[DPX];
-                path_net_forward_keep(P, nV, S.vecV, x, vN, mk, nullptr, nullptr, row, false);
+                Masks mkc;                                                        // (combined mode only)
+                const HelpArgs hv = {&mkc, nullptr, nullptr, &gV, nullptr};
+                own_net_forward_keep(P, nV, S.vecV, x, vN, nullptr, row, false, hv);
                 cot[0] = seed;
-                path_net_backward(P, nV, gV, mk, cot, false, nullptr, nullptr, row, dy0, S.dzmax);
+                own_net_backward(P, nV, cot, false, nullptr, row, dy0, mxbuf, dexp, false, hv);
                 const float* g0c = S.vecV + nV.vec_g0;
                 KLOOP(k, d) lam[k] = dy0[k] * g0c[k];
             }
             Dbar = valid ? vN[0] * a.invB : 0.f;
             y = y + vN[0] * disc;
-            if (wr) {
+            if (valid) {
                 yv = y;
                 if (a.o_delta) a.o_delta[gp] = y;
             }
@@ -690,14 +696,17 @@ __device__ __forceinline__ void actor_tc_body(const TcArgs& a, const TcSmem& S, 
             if (!any) continue;
             if (is_ctrl) {
                 ctrl_net_forward(C, nA, nA.L);
-                ctrl_net_backward(C, nA, true, copies);
-            } else if (is_path) {
+                ctrl_net_backward(C, nA, true, copies, false);
+            } else if (is_help) {
                 Masks mk;
+                help_forward_keep(P, nA, S.vecA, mk, copies, S.act, row, false);
+                help_backward(P, nA, gA, mk, true, gsA, S.dz, row, dexp);
+            } else {
                 float xt[DPX], ubar[DPX], cot[DPX], dy0[DPX];
-                TC_STAT(const long long r0 = clock64();)
                 KLOOP(k, d) { xt[k] = __ldcs(&tr[k * TC_PATHS + row]); dwv[k] = __ldcs(&tr[(sr + k) * TC_PATHS + row]); }
-                path_net_forward_keep(P, nA, S.vecA, xt, raw, mk, copies, S.act, row, false);
-                TC_STAT(const long long r1 = clock64(); seg_fk += r1 - r0;)
+                Masks mkc;                                                        // (combined mode only)
+                const HelpArgs ha = {&mkc, copies, S.act, &gA, gsA};
+                own_net_forward_keep(P, nA, S.vecA, xt, raw, copies, row, false, ha);
                 if (nA.ekn_head) ekn_head_fwd<float, DP, EQN, MV>(raw, u, nA.mctrl, 1, 0);
                 else KLOOP(j, m) u[j] = raw[j];
                 const int coef = (valid && sc[A_COEF * TC_PATHS + row] > 0.f) ? 1 : 0;
@@ -709,27 +718,22 @@ __device__ __forceinline__ void actor_tc_body(const TcArgs& a, const TcSmem& S, 
                 } else {
                     KLOOP(j, m) cot[j] = ubar[j];
                 }
-                TC_STAT(const long long r2 = clock64(); seg_adj += r2 - r1;)
-                path_net_backward(P, nA, gA, mk, cot, true, gsA, S.dz, row, dy0, S.dzmax);
-                TC_STAT(seg_bwd += clock64() - r2;)
+                own_net_backward(P, nA, cot, true, S.dz, row, dy0, mxbuf, dexp, false, ha);
                 const float* g0c = S.vecA + nA.vec_g0;
-                acc_input_sums<DPX>(sxA, s0A, xt, dy0, P.grp, d);
+                acc_input_sums<DPX>(sxA, s0A, xt, dy0, d);
                 KLOOP(k, d) lam[k] = lam[k] + dy0[k] * g0c[k];
             }
         }
     }
     if (is_ctrl) { ctrl_flush(C); C.pc->quit = 1; }
-    if (need_grad) {
-        reduce_rows_to(gsA + gA.gX, sxA, d, P.grp, is_path);
-        reduce_rows_to(gsA + gA.g0, s0A, d, P.grp, is_path);
+    if (need_grad && is_own) {
+        reduce_rows_to<DPX>(gsA + gA.gX, sxA, d);
+        reduce_rows_to<DPX>(gsA + gA.g0, s0A, d);
     }
     if (tid == 0 && a.loss_part) {
         a.loss_part[blockIdx.x * 2] = loss0;
         a.loss_part[blockIdx.x * 2 + 1] = 0.f;
     }
-    TC_STAT(if (a.stats) { long long* st = a.stats + (size_t)blockIdx.x * 16;
-                           if (is_ctrl && (tid & 31) == 0) st[9] = C.t_act;
-                           if (tid == 0) { st[11] = P.t_drain; st[12] = seg_fwd; st[13] = seg_fk; st[14] = seg_adj; st[15] = seg_bwd; } })
 }
 
 DPB_TC_KERNEL(critic)

@@ -1,9 +1,15 @@
 // dpb_tc_nets.cuh -- DeepNN (reference solver.py:227-278) on the 5th-generation tensor cores.
 //
-// One CTA owns a tile of 128 paths; path t = TMEM lane t is owned by TC_NGRP "path threads" (2: t in warps 0-3 and
-// t+128 in warps 4-7, both carrying the identical per-path state in registers and each handling every other
-// 16-column chunk of the epilogues; 1: a single thread with all chunks); the next warp is the control warp (issues
-// every tcgen05.mma), the last one the producer (streams the weights).
+// One CTA owns a tile of 128 paths; path t = TMEM lane t.  Warp roles:
+//   * warps 0-3, the OWNERS: thread t owns path t -- its state lives in that thread's registers -- and does everything that
+//     needs the state: the per-path SDE arithmetic, writing a network's input (y0) or output cotangent as A planes, reading
+//     a network's output (or the input cotangent dy0) back;
+//   * warps 4 .. 4+4*TC_NGRP-1, the HELPERS (TC_NGRP groups of four warps, one warp per TMEM lane quadrant): stateless.
+//     They run every hidden-layer epilogue (accumulator -> planes of the next product, relu masks, FP16 copies for the dW
+//     products) and drain the dW accumulators into the gradient slab; chunk c of an epilogue belongs to group c % TC_NGRP;
+//   * then the control warp (issues every tcgen05.mma) and the producer warp (streams the weights).
+// The owners' arithmetic (Philox increments, step-size rule, Euler-Maruyama move, adjoint step) therefore runs WHILE the
+// helpers and the tensor pipe work through a network; in round 1 the same threads did both, one after the other.
 //
 //   * dW products (a_l^T dz_l over the 128 paths of a tile) read both operands from shared memory as FP16 images (11-bit
 //     significands: 8x finer than bf16 at the same size and MMA rate).  FP16's narrow exponent range is handled per backward
@@ -47,20 +53,48 @@ constexpr int TC_PATHS = 128;
 #ifndef DPB_TC_NGRP
 #define DPB_TC_NGRP 2
 #endif
-constexpr int TC_NGRP = DPB_TC_NGRP;            // groups of 4 path warps.  2: thread t and t+128 own the same path (TMEM lane)
-                                                // and split the 16-column chunks of every epilogue between them (168 registers
-                                                // per thread); 1: one thread per path (255 registers, no duplicated per-path work)
-constexpr int TC_PATH_THREADS = 128 * TC_NGRP;
-constexpr int TC_CTRL_WARP = 4 * TC_NGRP;       // waits for operands, issues every tcgen05.mma
+constexpr int TC_NGRP = DPB_TC_NGRP;            // helper groups of 4 warps (chunk c of an epilogue -> group c % TC_NGRP).  0: no helper
+                                                // warps -- the owners run the helpers' code themselves, one thread per path with up to
+                                                // 255 registers (the actor kernels: their reverse sweep is one serial dependency chain,
+                                                // so separate helpers only add hand-offs and cost the owners registers)
+constexpr bool TC_COMBINED = TC_NGRP == 0;
+constexpr int TC_EGRP = TC_COMBINED ? 1 : TC_NGRP;      // groups the chunks of an epilogue are dealt out to
+constexpr int TC_OWN_THREADS = 128;             // warps 0-3: thread t owns path t
+constexpr int TC_HELP_WARPS = 4 * TC_NGRP;
+constexpr int TC_EPI_WARPS = TC_COMBINED ? 4 : TC_HELP_WARPS;     // warps that arrive on a_help / a_chunk[0]
+constexpr int TC_CTRL_WARP = 4 + TC_HELP_WARPS; // waits for operands, issues every tcgen05.mma
 constexpr int TC_PROD_WARP = TC_CTRL_WARP + 1;  // lane 0: streams the weight chunks (bulk copies) on its own
-constexpr int TC_WORK_THREADS = 32 * (TC_CTRL_WARP + 1);   // path + control warps take part in the in-loop CTA barriers (named barrier 1)
+constexpr int TC_WORK_THREADS = 32 * (TC_CTRL_WARP + 1);   // owner + helper + control warps take part in the in-loop CTA barriers (named barrier 1)
 constexpr int TC_THREADS = TC_WORK_THREADS + 32;
-// (`setmaxnreg`: with 12 warps -- path, path, control + producer + two idle warps -- the third warpgroup could hand its
-//  registers to the path warps, 168 -> 224 per thread.  The kernels are structured for it, one body per role, but ptxas does
-//  not spill inside a region whose budget was raised and the path code does not fit 232 registers without spilling:
-//  "register allocation failed with register count of 224".  Left as hooks until the per-path state shrinks.)
-__device__ __forceinline__ void tc_regs_release() {}
-__device__ __forceinline__ void tc_regs_take() {}
+// Register budgets per role (setmaxnreg, warpgroup-wide): the kernel is compiled for the launch bound (65536 / threads), the
+// helper, control and producer warps hand registers back and the owner warps -- whose per-path state is what spills --
+// take them.  DPB_TC_SETMAXNREG=0 compiles the hooks out.
+#ifndef DPB_TC_SETMAXNREG
+#define DPB_TC_SETMAXNREG 1
+#endif
+#ifndef DPB_TC_REGS_OWNER
+#define DPB_TC_REGS_OWNER 216
+#endif
+#ifndef DPB_TC_REGS_HELPER
+#define DPB_TC_REGS_HELPER 96
+#endif
+#define DPB_STR2(x) #x
+#define DPB_STR(x) DPB_STR2(x)
+__device__ __forceinline__ void tc_regs_owner() {
+#if DPB_TC_SETMAXNREG
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 " DPB_STR(DPB_TC_REGS_OWNER) ";");
+#endif
+}
+__device__ __forceinline__ void tc_regs_helper() {
+#if DPB_TC_SETMAXNREG
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 " DPB_STR(DPB_TC_REGS_HELPER) ";");
+#endif
+}
+__device__ __forceinline__ void tc_regs_small() {
+#if DPB_TC_SETMAXNREG
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
+#endif
+}
 constexpr int MAX_NSLOT = 16;                   // ring slots (runtime count: whatever shared memory is left)
 constexpr uint32_t COL_REG = 256;               // TMEM region r = columns [256 r, 256 r + 256)
 constexpr int MAXOPS = 64;                      // schedule entries of one phase: <= 7 (L+1) products, L <= 6 hidden layers
@@ -192,21 +226,28 @@ struct ProdCtl {
     volatile uint32_t quit;
 };
 
-// Hand-off barriers (shared memory, contiguous):  acc_full (count 1: tcgen05.commit of a product), a_all (count = path
-// warps: everything the next product needs is in place / the accumulator has been drained), a_chunk[16] (count 4: the
-// four warps that converted chunk c of the accumulator published its planes; a_chunk[0] counts every path warp).  Every barrier's parity is tracked on both
-// sides in one word: bit c (< 16) a_chunk[c], bit 16 a_all, bit 17 acc_full, bit 31 the TMEM region of the next A planes.
-constexpr uint32_t SY_ALL = 1u << 16, SY_ACC = 1u << 17, SY_DZ = 1u << 18, SY_REG = 1u << 31;      // (SY_DZ: buffer parity of the cotangent-maximum exchange)
+// Hand-off barriers (shared memory, contiguous, 8 bytes each; index in brackets):
+//   [0]      acc_full   count 1   tcgen05.commit of a product the HELPERS consume (hidden layers, dX of layers >= 1, dW blocks)
+//   [1]      a_help     count = helper warps: an epilogue that publishes at once (EPI_ALL) / a dW accumulator has been drained
+//   [2..17]  a_chunk[c] count 4   the four helper warps that converted chunk c published its planes (a_chunk[0]: every helper warp)
+//   [18]     acc_fin    count 1   tcgen05.commit of a product the OWNERS read (a network's output, the input cotangent dy0;
+//                                 also "the forward products are done" before a skip-last backward)
+//   [19]     a_own      count 4   the owner warps wrote a network input (y0) or an output cotangent
+// Every side tracks the parities of the barriers it waits on in one word, together with the TMEM region of the next A planes.
+constexpr uint32_t SY_HELP = 1u << 16, SY_ACC = 1u << 17, SY_DZ = 1u << 18, SY_OWN = 1u << 19, SY_FIN = 1u << 20, SY_REG = 1u << 31;
+constexpr int BAR_ACC = 0, BAR_HELP = 1, BAR_CHUNK = 2, BAR_FIN = 18, BAR_OWN = 19, NUM_HANDOFF_BARS = 20;
 __device__ __forceinline__ float pow2f(int e) { return __int_as_float((127 + e) << 23); }            // 2^e, -126 <= e <= 127
+enum { IN_OWN = 0, IN_HELP = 1, IN_CHUNKS = 2, IN_BOTH = 3 };            // what a product's inputs were published on
 
 struct Ctrl {
     unsigned char* ring;
-    uint64_t *full, *empty, *acc_full, *a_all, *a_chunk, *act_full;
+    uint64_t *full, *empty, *bars, *act_full;     // bars: the hand-off barriers above
     Sched* sch;
     ProdCtl* pc;
     uint32_t nslot, slot_bytes;
     uint32_t n_req, n_consumed, op_count, act_count, tmem, gen;
-    uint32_t sync;                   // parity bits (see above); op_count = products committed so far
+    uint32_t sync;                   // parity bits (see above); op_count = products committed on acc_full so far
+    volatile int* dexp;              // shared word: the exponent the owners scaled the current backward evaluation by
     uint32_t mm_slot, mm_use;        // ring cursor (slot index, wrap count) of the MMA issuer
     unsigned char *act, *dz;         // shared-memory operand images of the dW products (128 paths x K16 features, bf16)
     long long n_ops;
@@ -288,19 +329,27 @@ __device__ __forceinline__ void sched_add_fwd(Ctrl& c, const TcNet& t, const uns
     for (int l = 0; l <= upto; ++l) sched_add_op(c.sch, img + t.ly[l].img_f, t.ly[l].K16 / 16, t.ly[l].N16, (int)c.slot_bytes);
 }
 
+// wait for the inputs of a product (see IN_*), flipping the tracked parities
+__device__ __forceinline__ void ctrl_wait_inputs(uint32_t bars0, uint32_t& sync, int in_kind) {
+    if (in_kind == IN_OWN || in_kind == IN_BOTH) { mbar_wait_u32(bars0 + 8 * BAR_OWN, (sync >> 19) & 1u); sync ^= SY_OWN; }
+    if (in_kind == IN_HELP || in_kind == IN_BOTH) { mbar_wait_u32(bars0 + 8 * BAR_HELP, (sync >> 16) & 1u); sync ^= SY_HELP; }
+    if (in_kind != IN_CHUNKS) tc_fence_after();
+}
+
 // D[acc region] = A(planes in the other region) x B(streamed image with R rows): nchunks contraction chunks, 3 split
-// products per chunk.  chunked: the A planes come chunk by chunk from an in-place epilogue (a_chunk[s]), otherwise they
-// were published at once (a_all).  toggles: the epilogue converts the accumulator in place into the planes of the next
-// product (the regions then swap roles).
-__device__ __forceinline__ void ctrl_gemm_ts(Ctrl& cref, int nchunks_, int R_, bool chunked_, bool toggles) {
+// products per chunk.  in_kind: where the A planes were published (IN_CHUNKS: chunk by chunk by an in-place epilogue).
+// fin: the owners read the result (commit on acc_fin), otherwise the helpers convert it (acc_full); also_fin: commit on
+// both.  toggles: the epilogue converts the accumulator in place into the planes of the next product (the regions swap).
+__device__ __forceinline__ void ctrl_gemm_ts(Ctrl& cref, int nchunks_, int R_, int in_kind_, bool fin_, bool also_fin_, bool toggles) {
     Ctrl c = cref;                                                       // registers for the issue loop
     // everything an MMA / commit operand is computed from goes through a lane-0 broadcast: the compiler then knows the
     // values are warp-uniform (the state lives in per-thread local memory across the noinline callers)
     const int nchunks = (int)warp_uniform((uint32_t)nchunks_), R = (int)warp_uniform((uint32_t)R_);
-    const bool chunked = warp_uniform(chunked_ ? 1u : 0u) != 0;
+    const int in_kind = (int)warp_uniform((uint32_t)in_kind_);
+    const bool chunked = in_kind == IN_CHUNKS, fin = warp_uniform(fin_ ? 1u : 0u) != 0, also_fin = warp_uniform(also_fin_ ? 1u : 0u) != 0;
     const uint32_t tmem = warp_uniform(c.tmem), nslot = warp_uniform(c.nslot), slot_bytes = warp_uniform(c.slot_bytes);
     const uint32_t ring0 = warp_uniform(smem_u32(c.ring)), full0 = warp_uniform(smem_u32(c.full)), empty0 = warp_uniform(smem_u32(c.empty));
-    const uint32_t accf = warp_uniform(smem_u32(c.acc_full)), aall = warp_uniform(smem_u32(c.a_all)), achk = warp_uniform(smem_u32(c.a_chunk));
+    const uint32_t bars0 = warp_uniform(smem_u32(c.bars));
     uint32_t mm_slot = warp_uniform(c.mm_slot), mm_use = warp_uniform(c.mm_use);
     uint32_t sync = warp_uniform(c.sync);
     const uint32_t reg = sync >> 31;
@@ -311,11 +360,7 @@ __device__ __forceinline__ void ctrl_gemm_ts(Ctrl& cref, int nchunks_, int R_, b
     const uint64_t dlo = ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) | ((uint64_t)(128 >> 4) << 32) | (1ull << 46);
     ctrl_request(c);
     TC_STAT(const long long t0 = clock64();)
-    if (!chunked) {
-        mbar_wait_u32(aall, (sync >> 16) & 1u);
-        sync ^= SY_ALL;
-        tc_fence_after();
-    }
+    ctrl_wait_inputs(bars0, sync, in_kind);
     TC_STAT(const long long ti0 = clock64(); c.t_aready += ti0 - t0;)
     ++c.n_ops;
     for (int s0 = 0; s0 < nchunks; s0 += g) {
@@ -326,7 +371,7 @@ __device__ __forceinline__ void ctrl_gemm_ts(Ctrl& cref, int nchunks_, int R_, b
             const int s = s0 + j;
             if (chunked) {
                 TC_STAT(const long long tw = clock64();)
-                mbar_wait_u32(achk + 8 * s, (sync >> s) & 1u);
+                mbar_wait_u32(bars0 + 8 * (BAR_CHUNK + s), (sync >> s) & 1u);
                 TC_STAT(c.t_aready += clock64() - tw;)
                 sync ^= 1u << s;
                 tc_fence_after();
@@ -345,28 +390,35 @@ __device__ __forceinline__ void ctrl_gemm_ts(Ctrl& cref, int nchunks_, int R_, b
         if (++mm_slot == nslot) { mm_slot = 0; ++mm_use; }
         ctrl_request(c);
     }
-    if (elect_one()) tc_commit_u32(accf);
+    if (elect_one()) {
+        if (!fin) tc_commit_u32(bars0 + 8 * BAR_ACC);
+        if (fin || also_fin) tc_commit_u32(bars0 + 8 * BAR_FIN);
+    }
     TC_STAT(c.t_issue += clock64() - ti0;)
-    ++c.op_count;
+    if (!fin) ++c.op_count;
     if (toggles) sync ^= SY_REG;
     c.sync = sync;
     c.mm_slot = mm_slot; c.mm_use = mm_use;
     cref = c;
 }
 
-// forward products of layers 0..upto: the first reads planes the path threads wrote themselves (y0), the others follow
-// an in-place epilogue
+// forward products of layers 0..upto: the first reads the planes the owners wrote (y0), the others follow an in-place
+// epilogue; the output of layer L goes to the owners.  upto = L-1 (the backward starts from the last hidden layer): its
+// accumulator is not converted into planes (no region swap) and the owners are told when the products are done.
 static __device__ __noinline__ void ctrl_net_forward(Ctrl& c, const TcNet& t, int upto) {
-    for (int l = 0; l <= upto; ++l) ctrl_gemm_ts(c, t.ly[l].K16 / 16, t.ly[l].N16, l > 0, l < t.L);
+    for (int l = 0; l <= upto; ++l) {
+        const bool last_of_skip = (l == upto && upto < t.L);
+        ctrl_gemm_ts(c, t.ly[l].K16 / 16, t.ly[l].N16, l > 0 ? IN_CHUNKS : IN_OWN, l == t.L, last_of_skip, l < t.L && !last_of_skip);
+    }
 }
 
-// ---------------------------------------------------------------------------------- path-thread side
+// ---------------------------------------------------------------------------------- owner / helper side
 struct PathCtx {
     uint32_t tl;                   // TMEM address of this thread's lane (column 0)
-    uint32_t bars;                 // shared-memory address of the hand-off barriers: acc_full, a_all, a_chunk[16] (8 bytes each)
-    uint32_t sync;                 // parity bits of the hand-off barriers + TMEM region bit (layout: see SY_* above)
-    int grp;                       // 0: threads 0..127, 1: threads 128..255 (chunk parity this thread handles)
-    int dexp;                      // the current backward evaluation runs scaled by 2^dexp (see the header: FP16 dW operands)
+    uint32_t bars;                 // shared-memory address of the hand-off barriers (BAR_*)
+    uint32_t sync;                 // parity bits of the barriers this side waits on + TMEM region bit (SY_*)
+    int grp;                       // helpers: group (chunk c belongs to group c % TC_NGRP); owners: 0
+    int dexp;                      // owners: the current backward evaluation runs scaled by 2^dexp (see the header: FP16 dW operands)
     TC_STAT(long long t_accw, t_mark;)      // cycles spent waiting for the tensor pipe; time of the last wake-up
     TC_STAT(long long t_epi, t_hid;)        // t_hid: cycles inside hidden-layer epilogues only
     TC_STAT(long long t_drain;)             // cycles inside the dW drains (after the accumulator wait)
@@ -384,27 +436,27 @@ typedef PathCtx PathArg;
 __device__ __forceinline__ uint32_t path_planes(const PathCtx& p) { return p.tl + COL_REG * (p.sync >> 31); }             // A planes of the next product
 __device__ __forceinline__ uint32_t path_acc(const PathCtx& p) { return p.tl + COL_REG * ((p.sync >> 31) ^ 1u); }         // its accumulator
 
-// Everything the next product needs is in place (planes written by this thread / accumulator drained): one arrival per
-// path warp on a_all.
-__device__ __forceinline__ void path_publish(PathCtx& p) {
+// ---- helpers ------------------------------------------------------------------------------------------------------
+// an epilogue that publishes at once / a drained accumulator: one arrival per helper warp on a_help
+__device__ __forceinline__ void help_publish(PathCtx& p) {
     tmem_st_wait();
     tc_fence_before();
     __syncwarp();
-    if ((threadIdx.x & 31) == 0) mbar_arrive_u32(p.bars + 8);
-    p.sync ^= SY_ALL;
+    if ((threadIdx.x & 31) == 0) mbar_arrive_u32(p.bars + 8 * BAR_HELP);
+    p.sync ^= SY_HELP;
     TC_STAT(p.t_epi += clock64() - p.t_mark;)
 }
 // planes of chunk c of an in-place epilogue are written: one arrival per warp of the group that owns the chunk
-__device__ __forceinline__ void path_publish_chunk(const PathCtx& p, int c) {
+__device__ __forceinline__ void help_publish_chunk(const PathCtx& p, int c) {
     tmem_st_wait();
     tc_fence_before();
     __syncwarp();
-    if ((threadIdx.x & 31) == 0) mbar_arrive_u32(p.bars + 16 + 8 * c);
+    if ((threadIdx.x & 31) == 0) mbar_arrive_u32(p.bars + 8 * (BAR_CHUNK + c));
 }
-// wait for the commit of the current product
-__device__ __forceinline__ void path_wait_acc(PathCtx& p) {
+// wait for the commit of the current helper-consumed product
+__device__ __forceinline__ void help_wait_acc(PathCtx& p) {
     TC_STAT(const long long t0 = clock64();)
-    mbar_wait_u32(p.bars, (p.sync >> 17) & 1u);
+    mbar_wait_u32(p.bars + 8 * BAR_ACC, (p.sync >> 17) & 1u);
     TC_STAT(p.t_mark = clock64(); p.t_accw += p.t_mark - t0;)
     p.sync ^= SY_ACC;
     tc_fence_after();
@@ -438,45 +490,50 @@ __device__ __forceinline__ void put16(uint32_t tc, const float* v) {
     tmem_st8(tc, h);
     tmem_st8(tc + 8, l);
 }
-// In-place epilogue of a product with `nco` output chunks: wait for its commit, hand the chunks of this thread's group
-// (c % TC_NGRP == grp) to f(c, r[16], tc) -- r = the 16 accumulator columns, tc = their TMEM address, where f stores the
-// planes of the next product.  mode: EPI_CHUNKS publishes every chunk on its own barrier (the next product starts on it
-// at once); EPI_ALL publishes once at the end (the next product is a dW product, which needs everything); EPI_NONE leaves
-// the publishing to the caller.  fence: what f wrote besides TMEM and the async proxy reads later (dW operands, bulk
-// copies): 0 nothing, 1 shared memory, 2 global memory; the proxy fence is issued at the end, before the arrival (of this
-// or of a later publish on a_all) that the consumer of those bytes waits for.
-enum { EPI_NONE = 0, EPI_CHUNKS = 1, EPI_ALL = 2 };
+// In-place epilogue of a product with `nco` output chunks (helpers): wait for its commit, hand the chunks of this thread's
+// group (c % TC_NGRP == grp) to f(c, r[16], tc) -- r = the 16 accumulator columns, tc = their TMEM address, where f stores
+// the planes of the next product.  mode: EPI_CHUNKS publishes every chunk on its own barrier (the next product starts on
+// it at once); EPI_ALL publishes once at the end on a_help (the next product is a dW product, which needs everything).
+// fence: what f wrote besides TMEM and the async proxy reads later (dW operands, bulk copies): 0 nothing, 1 shared memory,
+// 2 global memory; the proxy fence precedes the thread's LAST arrival of the epilogue, and whoever consumes those bytes
+// has waited for every chunk (or for a_help).  toggle: the accumulator became the next planes (the regions swap roles).
+enum { EPI_CHUNKS = 1, EPI_ALL = 2 };
 template <class F>
-__device__ __forceinline__ void for_acc_chunks(PathCtx& p, int nco, int mode, int fence, F f) {
+__device__ __forceinline__ void for_acc_chunks(PathCtx& p, int nco, int mode, int fence, bool toggle, F f) {
     // (the TMEM->register path is the bound of every epilogue -- 64 B/clk/SM, see DESIGN.md -- so a plain loop does as
     //  well as a software-pipelined one and needs 16 registers fewer)
-    path_wait_acc(p);
-    // Every path warp takes part in the hand-off of chunk 0 (the owners when its planes are written, the others here, as
+    help_wait_acc(p);
+    // Every helper warp takes part in the hand-off of chunk 0 (its owners when the planes are written, the others here, as
     // soon as they have seen the commit): the next product cannot be committed before all warps have observed this one.
     // Without it a warp that owns no chunk of a narrow output (one chunk: the other group's) could fall two phases behind
     // on acc_full and wait for a parity that has already come round again.
-    if (TC_NGRP > 1 && mode == EPI_CHUNKS && p.grp != 0) {
+    if (TC_EGRP > 1 && mode == EPI_CHUNKS && p.grp != 0) {
         __syncwarp();
-        if ((threadIdx.x & 31) == 0) mbar_arrive_u32(p.bars + 16);
+        if ((threadIdx.x & 31) == 0) mbar_arrive_u32(p.bars + 8 * BAR_CHUNK);
     }
     const uint32_t acc = path_acc(p);
     uint32_t ra[16];
     int pend = -1;                                      // chunk whose stores are in flight (published after the next load)
-    for (int c = p.grp; c < nco; c += TC_NGRP) {
+    for (int c = p.grp; c < nco; c += TC_EGRP) {
         tmem_ld16(acc + 16 * c, ra);
         tmem_ld_wait();
-        if (pend >= 0) path_publish_chunk(p, pend);     // (its stores completed under the latency of the load)
+        if (pend >= 0) help_publish_chunk(p, pend);     // (its stores completed under the latency of the load)
         f(c, ra, acc + 16 * c);
         if (mode == EPI_CHUNKS) {
-            if (c < TC_NGRP) { path_publish_chunk(p, c); pend = -1; }       // first chunk: at once -- the next product starts on it
-            else pend = c;
+            if (c < TC_EGRP) {                                                // first chunk: at once -- the next product starts on it
+                if (fence == 1) fence_proxy_async(); else if (fence == 2) fence_proxy_async_global();     // (it may be this thread's only arrival)
+                help_publish_chunk(p, c);
+                pend = -1;
+            } else {
+                pend = c;
+            }
         }
     }
-    if (pend >= 0) path_publish_chunk(p, pend);
-    if (mode == EPI_CHUNKS) p.sync ^= (1u << nco) - 1u;                    // every a_chunk[c], c < nco, completed a phase
     if (fence == 1) fence_proxy_async(); else if (fence == 2) fence_proxy_async_global();
-    p.sync ^= SY_REG;
-    if (mode == EPI_ALL) path_publish(p);
+    if (pend >= 0) help_publish_chunk(p, pend);
+    if (mode == EPI_CHUNKS) p.sync ^= (1u << nco) - 1u;                    // every a_chunk[c], c < nco, completed a phase
+    if (toggle) p.sync ^= SY_REG;
+    if (mode == EPI_ALL) help_publish(p);
     TC_STAT(else p.t_epi += clock64() - p.t_mark;)
 }
 
@@ -509,16 +566,59 @@ __device__ __forceinline__ void copy16f(unsigned char* img, int row, int c, cons
     *reinterpret_cast<uint4*>(p + 2048) = make_uint4(w[4], w[5], w[6], w[7]);
 }
 
-// y0 = x * g0c + b0 (solver.py:265) -> planes (+ bf16 copy with the constant-1 feature when `copies`), then
+// hidden layer epilogue: a = z + relu(z), z = acc * gc + bb (solver.py:267-269) -> planes
+__device__ __forceinline__ void help_epi_hidden(PathCtx& p, const float* gcbb, int N16) {
+    TC_STAT(const long long th0 = clock64();)
+    const float* gc = gcbb;
+    const float* bb = gcbb + N16;
+    for_acc_chunks(p, N16 / 16, EPI_CHUNKS, 0, true, [&](int c, const uint32_t* r, uint32_t tc) {
+        float v[16];
+        affine16(r, gc + 16 * c, bb + 16 * c, v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            up2(add2(pk2(v[2 * j], v[2 * j + 1]), pk2(fmaxf(v[2 * j], 0.f), fmaxf(v[2 * j + 1], 0.f))), v[2 * j], v[2 * j + 1]);
+        put16(tc, v);
+    });
+    TC_STAT(p.t_hid += clock64() - th0;)
+}
+// the hidden-layer epilogues of one forward-only evaluation (helpers)
+static __device__ __noinline__ uint32_t help_forward_(PathArg p, const TcNet& t, const float* vec) {
+    for (int l = 0; l < t.L; ++l) help_epi_hidden(p, vec + t.ly[l].vec, t.ly[l].N16);
+    return p.sync;
+}
+__device__ __forceinline__ void help_forward(PathCtx& p, const TcNet& t, const float* vec) { p.sync = help_forward_(p, t, vec); }
+
+// ---- owners -------------------------------------------------------------------------------------------------------
+// a network input / output cotangent is in place: one arrival per owner warp on a_own
+__device__ __forceinline__ void own_publish(PathCtx& p) {
+    tmem_st_wait();
+    tc_fence_before();
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) mbar_arrive_u32(p.bars + 8 * BAR_OWN);
+    TC_STAT(p.t_epi += clock64() - p.t_mark;)
+}
+// wait for a product whose result the owners read (or for the end of the forward products of a skip-last evaluation)
+__device__ __forceinline__ void own_wait_fin(PathCtx& p) {
+    TC_STAT(const long long t0 = clock64();)
+    mbar_wait_u32(p.bars + 8 * BAR_FIN, (p.sync >> 20) & 1u);
+    TC_STAT(p.t_mark = clock64(); p.t_accw += p.t_mark - t0;)
+    p.sync ^= SY_FIN;
+    tc_fence_after();
+}
+// the helpers converted `n` accumulators in place since the owners last touched tensor memory: the regions swapped n times
+// (combined mode: the owner ran those conversions itself and its region bit is already up to date)
+__device__ __forceinline__ void own_swaps(PathCtx& p, int n) { if (!TC_COMBINED && (n & 1)) p.sync ^= SY_REG; }
+
+// y0 = x * g0c + b0 (solver.py:265) -> planes (+ FP16 copy with the constant-1 feature when `copies`), then
 // publish.  Everything indexed statically (K16_0 <= 32) so that x can live in registers.
 template <int NX>
-__device__ __forceinline__ void path_put_y0(PathCtx& p, const TcNet& t, const float* vec, const float (&x)[NX], unsigned char* copies, int row) {
+__device__ __forceinline__ void own_put_y0(PathCtx& p, const TcNet& t, const float* vec, const float (&x)[NX], unsigned char* copies, int row) {
     const int K0 = t.ly[0].K16;
     const float* g0c = vec + t.vec_g0;
     const float* b0 = g0c + K0;
 #pragma unroll
     for (int c = 0; c < 2; ++c) {
-        if (c < K0 / 16 && (c % TC_NGRP) == p.grp) {
+        if (c < K0 / 16) {
             float v[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
@@ -530,32 +630,19 @@ __device__ __forceinline__ void path_put_y0(PathCtx& p, const TcNet& t, const fl
         }
     }
     if (copies) fence_proxy_async_global();
-    path_publish(p);
+    own_publish(p);
 }
 
-// hidden layer epilogue: a = z + relu(z), z = acc * gc + bb (solver.py:267-269) -> planes
-__device__ __forceinline__ void path_epi_hidden(PathCtx& p, const float* gcbb, int N16) {
-    TC_STAT(const long long th0 = clock64();)
-    const float* gc = gcbb;
-    const float* bb = gcbb + N16;
-    for_acc_chunks(p, N16 / 16, EPI_CHUNKS, 0, [&](int c, const uint32_t* r, uint32_t tc) {
-        float v[16];
-        affine16(r, gc + 16 * c, bb + 16 * c, v);
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-            up2(add2(pk2(v[2 * j], v[2 * j + 1]), pk2(fmaxf(v[2 * j], 0.f), fmaxf(v[2 * j + 1], 0.f))), v[2 * j], v[2 * j + 1]);
-        put16(tc, v);
-    });
-    TC_STAT(p.t_hid += clock64() - th0;)
-}
-
-// last layer: out[n] = acc * gc + bb (solver.py:270-271), n < nl <= 32; static indexing
+// last layer: out[n] = acc * gc + bb (solver.py:270-271), n < nl <= 32; static indexing.  The helpers converted the L
+// hidden accumulators in the meantime.
 template <int NO>
-__device__ __forceinline__ void path_last(PathCtx& p, const float* gcbb, int N16, int nl, float (&out)[NO]) {
-    path_wait_acc(p);
+__device__ __forceinline__ void own_last(PathCtx& p, const TcNet& t, const float* vec, float (&out)[NO]) {
+    own_wait_fin(p);
+    own_swaps(p, t.L);
     const uint32_t acc = path_acc(p);
-    const float* gc = gcbb;
-    const float* bb = gcbb + N16;
+    const int N16 = t.ly[t.L].N16, nl = t.ly[t.L].nl;
+    const float* gc = vec + t.ly[t.L].vec;
+    const float* bb = gc + N16;
 #pragma unroll
     for (int c = 0; c < 2; ++c) {
         if (c < N16 / 16) {
@@ -570,30 +657,12 @@ __device__ __forceinline__ void path_last(PathCtx& p, const float* gcbb, int N16
         }
     }
 }
-
-// hidden-layer epilogues l0 .. l1-1 of a forward-only evaluation (no per-path arrays involved).  The caller places its
-// own per-path arithmetic between two ranges: it then runs while the tensor pipe works on the layer just published.
-static __device__ __noinline__ uint32_t path_hidden_range_(PathArg p, const TcNet& t, const float* vec, int l0, int l1) {
-    for (int l = l0; l < l1 && l < t.L; ++l) path_epi_hidden(p, vec + t.ly[l].vec, t.ly[l].N16);
-    return p.sync;
-}
-__device__ __forceinline__ void path_hidden_range(PathCtx& p, const TcNet& t, const float* vec, int l0, int l1) { p.sync = path_hidden_range_(p, t, vec, l0, l1); }
-
-// forward-only evaluation:  begin (y0 -> planes)  ...caller's own arithmetic...  finish (-> raw output)
-template <int NX>
-__device__ __forceinline__ void path_net_begin(PathCtx& p, const TcNet& t, const float* vec, const float (&x)[NX]) {
-    path_put_y0(p, t, vec, x, nullptr, 0);
-}
-// layers `from`.. and the raw output
-template <int NO>
-__device__ __forceinline__ void path_net_finish(PathCtx& p, const TcNet& t, const float* vec, float (&out)[NO], int from = 0) {
-    path_hidden_range(p, t, vec, from, t.L);
-    path_last(p, vec + t.ly[t.L].vec, t.ly[t.L].N16, t.ly[t.L].nl, out);
-}
+// one whole forward-only evaluation as the owners see it (combined mode: including the hidden-layer epilogues)
 template <int NX, int NO>
-__device__ __forceinline__ void path_net_forward(PathCtx& p, const TcNet& t, const float* vec, const float (&x)[NX], float (&out)[NO]) {
-    path_net_begin(p, t, vec, x);
-    path_net_finish(p, t, vec, out);
+__device__ __forceinline__ void own_net_forward(PathCtx& p, const TcNet& t, const float* vec, const float (&x)[NX], float (&out)[NO]) {
+    own_put_y0(p, t, vec, x, nullptr, 0);
+    if (TC_COMBINED) help_forward(p, t, vec);
+    own_last(p, t, vec, out);
 }
 
 }  // namespace tc
@@ -673,17 +742,16 @@ __device__ __forceinline__ void ctrl_act_wait(Ctrl& c) {
 
 // D[acc] (rows = features 128*blk .. of ACT, cols = N16 features of DZ) = ACT^T DZ over the 128 paths.  The accumulator
 // is the region the next dX product will write (the other one holds the dz planes that product reads).
-__device__ __forceinline__ void ctrl_gemm_dw(Ctrl& c, int blk_, int N16_) {
-    const int blk = (int)warp_uniform((uint32_t)blk_), N16 = (int)warp_uniform((uint32_t)N16_);
+__device__ __forceinline__ void ctrl_gemm_dw(Ctrl& c, int blk_, int N16_, int in_kind_) {
+    const int blk = (int)warp_uniform((uint32_t)blk_), N16 = (int)warp_uniform((uint32_t)N16_), in_kind = (int)warp_uniform((uint32_t)in_kind_);
     const uint32_t idesc = idesc_f16(128, N16, 1, 1);                   // FP16 operand images
     uint32_t sync = warp_uniform(c.sync);
+    const uint32_t bars0 = warp_uniform(smem_u32(c.bars));
     TC_STAT(const long long t0 = clock64();)
-    mbar_wait(c.a_all, (sync >> 16) & 1u);                              // operands complete / previous block drained
-    sync ^= SY_ALL;
+    ctrl_wait_inputs(bars0, sync, in_kind);                             // operands complete / previous block drained
     TC_STAT(c.t_dw_ready += clock64() - t0;)
-    tc_fence_after();
     const uint32_t a0 = warp_uniform(smem_u32(c.act)) + blk * 16 * 2048, b0 = warp_uniform(smem_u32(c.dz));
-    const uint32_t tmem = warp_uniform(c.tmem), accf = warp_uniform(smem_u32(c.acc_full));
+    const uint32_t tmem = warp_uniform(c.tmem);
     const uint32_t dcol = tmem + COL_REG * ((sync >> 31) ^ 1u);
     if (elect_one()) {
 #pragma unroll
@@ -691,44 +759,47 @@ __device__ __forceinline__ void ctrl_gemm_dw(Ctrl& c, int blk_, int N16_) {
             const uint64_t ad = smem_desc(a0 + s * 256, 128, 2048), bd = smem_desc(b0 + s * 256, 128, 2048);
             mma_ss(dcol, ad, bd, idesc, s > 0);
         }
-        tc_commit_u32(accf);
+        tc_commit_u32(bars0 + 8 * BAR_ACC);
     }
     c.sync = sync;
     ++c.op_count;
 }
 
-// backward of one network evaluation.  need_w: dW products (+ drains on the path side);
-// copies: per-CTA global scratch holding the bf16 copies of a_0..a_{L-1} (a_L is already in ACT).
-static __device__ __noinline__ void ctrl_net_backward(Ctrl& c, const TcNet& t, bool need_w, const unsigned char* copies) {
+// backward of one network evaluation.  need_w: dW products (+ drains on the helper side);
+// copies: per-CTA global scratch holding the FP16 copies of a_0..a_{L-1} (a_L is already in ACT);
+// skip_last: the forward stopped at the last hidden layer, whose epilogue published on a_help (the output cotangent
+// comes from the owners either way).
+static __device__ __noinline__ void ctrl_net_backward(Ctrl& c, const TcNet& t, bool need_w, const unsigned char* copies, bool skip_last) {
     for (int l = t.L; l >= 0; --l) {
         if (need_w) {
             if (l < t.L) ctrl_act_wait(c);
             const int nblk = (t.ly[l].kl + 1 + 127) >> 7;
-            for (int b = 0; b < nblk; ++b) ctrl_gemm_dw(c, b, t.ly[l].N16);
+            for (int b = 0; b < nblk; ++b)
+                ctrl_gemm_dw(c, b, t.ly[l].N16, (l == t.L && b == 0) ? (skip_last ? IN_BOTH : IN_OWN) : IN_HELP);
             if (l > 0) {
                 TC_STAT(const long long t0 = clock64();)
-                mbar_wait(c.acc_full, (c.op_count - 1) & 1);           // the MMAs reading ACT are done
+                mbar_wait(&c.bars[BAR_ACC], (c.op_count - 1) & 1);     // the MMAs reading ACT are done
                 TC_STAT(c.t_accw += clock64() - t0;)
                 ctrl_act_load(c, copies + tc_copy_off(t, l - 1), (uint32_t)(TC_PATHS * t.ly[l - 1].K16 * 2));
             }
         }
-        // dA_l = dz_l x (W_l gamma c)^T; its planes come chunk by chunk only in a chain without dW products
-        ctrl_gemm_ts(c, t.ly[l].N16 / 16, t.ly[l].K16, !need_w && l < t.L, l > 0);
+        // dA_l = dz_l x (W_l gamma c)^T; its planes come chunk by chunk only in a chain without dW products; dy0 (l = 0) goes
+        // to the owners
+        ctrl_gemm_ts(c, t.ly[l].N16 / 16, t.ly[l].K16, need_w ? IN_HELP : (l == t.L ? IN_OWN : IN_CHUNKS), l == 0, false, l > 0);
     }
 }
 
-// ---- path threads ------------------------------------------------------------------------------------
-// relu masks of one evaluation: h[l][c] bit j: a_l[16c + j] > 0  (l = 1..L, K16 <= 256).  Per-thread local memory; every
-// word is written with a plain store by the thread that reads it back (no read-modify-write, no initialisation), and the
-// backward fetches the word of its next chunk one chunk ahead.
+// ---- helpers ------------------------------------------------------------------------------------------------------
+// relu masks of one evaluation: h[l][c] bit j: a_l[16c + j] > 0  (l = 1..L, K16 <= 256).  Per-thread local memory of the
+// helper that converts chunk c of its lane in the forward AND in the backward (the chunk -> group assignment is static).
 struct Masks { uint32_t h[MAXLIN][16]; };
 
-// hidden layers of a forward evaluation that keeps what the backward needs: relu masks (bits), bf16 copies of
+// hidden-layer epilogues of a forward evaluation that keeps what the backward needs: relu masks (bits), FP16 copies of
 // a_1..a_{L-1} (global scratch `copies`, NULL: none) and of a_L (shared ACT image, NULL: none).
-// skip_last: the raw output is not needed -- the last hidden epilogue does not publish (the caller writes
-// dz_L and publishes).
-static __device__ __noinline__ uint32_t path_hidden_keep_(PathArg p, const TcNet& t, const float* vec, Masks& mk, unsigned char* copies,
-                                              unsigned char* act, int row, bool skip_last) {
+// skip_last: the raw output is not needed -- the last hidden accumulator is not converted into planes (no region swap) and
+// the epilogue publishes at once on a_help (the dW product of the last layer waits for it).
+static __device__ __noinline__ uint32_t help_forward_keep_(PathArg p, const TcNet& t, const float* vec, Masks& mk, unsigned char* copies,
+                                                           unsigned char* act, int row, bool skip_last) {
     for (int l = 0; l < t.L; ++l) {
         const int N16 = t.ly[l].N16;
         const float* gc = vec + t.ly[l].vec;
@@ -737,7 +808,7 @@ static __device__ __noinline__ uint32_t path_hidden_keep_(PathArg p, const TcNet
         unsigned char* dst = last_hidden ? act : (copies ? copies + tc_copy_off(t, l + 1) : nullptr);
         const int one_at = t.ly[l + 1].kl;
         const bool planes = !(last_hidden && skip_last);                 // (skip_last: nothing reads a_L as an MMA operand)
-        for_acc_chunks(p, N16 / 16, planes ? EPI_CHUNKS : EPI_NONE, dst ? (last_hidden ? 1 : 2) : 0, [&](int c, const uint32_t* r, uint32_t tc) {
+        for_acc_chunks(p, N16 / 16, planes ? EPI_CHUNKS : EPI_ALL, dst ? (last_hidden ? 1 : 2) : 0, planes, [&](int c, const uint32_t* r, uint32_t tc) {
             float v[16];
             affine16(r, gc + 16 * c, bb + 16 * c, v);
             uint32_t bits = 0;
@@ -753,22 +824,15 @@ static __device__ __noinline__ uint32_t path_hidden_keep_(PathArg p, const TcNet
     }
     return p.sync;
 }
-__device__ __forceinline__ void path_hidden_keep(PathCtx& p, const TcNet& t, const float* vec, Masks& mk, unsigned char* copies,
-                                                 unsigned char* act, int row, bool skip_last) {
-    p.sync = path_hidden_keep_(p, t, vec, mk, copies, act, row, skip_last);
-}
-// x -> (masks, copies) [-> raw output]
-template <int NX, int NO>
-__device__ __forceinline__ void path_net_forward_keep(PathCtx& p, const TcNet& t, const float* vec, const float (&x)[NX], float (&out)[NO],
-                                                      Masks& mk, unsigned char* copies, unsigned char* act, int row, bool skip_last) {
-    path_put_y0(p, t, vec, x, copies, row);
-    path_hidden_keep(p, t, vec, mk, copies, act, row, skip_last);
-    if (!skip_last) path_last(p, vec + t.ly[t.L].vec, t.ly[t.L].N16, t.ly[t.L].nl, out);
+__device__ __forceinline__ void help_forward_keep(PathCtx& p, const TcNet& t, const float* vec, Masks& mk, unsigned char* copies,
+                                                  unsigned char* act, int row, bool skip_last) {
+    p.sync = help_forward_keep_(p, t, vec, mk, copies, act, row, skip_last);
 }
 
-// this thread's row of a dW block -> RED into the slab:  rows f = 128*blk + row (f <= kl), cols n < nl
-__device__ __forceinline__ void path_drain(PathCtx& p, int blk, int row, int kl, int nl, int N16, float* slab) {
-    path_wait_acc(p);
+// this thread's row of a dW block -> RED into the slab:  rows f = 128*blk + row (f <= kl), cols n < nl.  The evaluation ran
+// scaled by 2^dexp (the owners leave the exponent in shared memory before they publish the output cotangent).
+__device__ __forceinline__ void help_drain(PathCtx& p, int blk, int row, int kl, int nl, int N16, float* slab, const volatile int* dexp) {
+    help_wait_acc(p);
     const uint32_t acc = path_acc(p);
     TC_STAT(const long long td0 = clock64();)
     const int f = 128 * blk + row;
@@ -778,8 +842,8 @@ __device__ __forceinline__ void path_drain(PathCtx& p, int blk, int row, int kl,
     // a warp whose 32 rows all lie past the last feature row skips its TMEM loads altogether (the TMEM->register path
     // is the bound of the drain): block 1 of a 200-wide layer has 73 live rows, the input layer's block 21
     const bool warp_live = (128 * blk + (row & ~31)) <= kl;
-    const float inv = pow2f(-p.dexp);                                     // the evaluation ran scaled by 2^dexp
-    for (int c = p.grp; warp_live && c < N16 / 16; c += TC_NGRP) {
+    const float inv = pow2f(-*dexp);
+    for (int c = p.grp; warp_live && c < N16 / 16; c += TC_EGRP) {
         uint32_t r[16];
         tmem_ld16(acc + 16 * c, r);
         tmem_ld_wait();
@@ -793,62 +857,24 @@ __device__ __forceinline__ void path_drain(PathCtx& p, int blk, int row, int kl,
     }
     tc_fence_before();
     __syncwarp();
-    if ((threadIdx.x & 31) == 0) mbar_arrive_u32(p.bars + 8);    // accumulator drained (a_all)
-    p.sync ^= SY_ALL;
+    if ((threadIdx.x & 31) == 0) mbar_arrive_u32(p.bars + 8 * BAR_HELP);    // accumulator drained
+    p.sync ^= SY_HELP;
     TC_STAT(p.t_drain += clock64() - td0;)
 }
 
-// cotangent of the raw output (nl <= 32 values, static indexing) -> planes (+ DZ image), publish.  The evaluation runs
-// scaled by 2^dexp, chosen so that the largest |cotangent| of the tile lands in [2^11, 2^12): mxbuf = shared memory, two
-// rows of one word per path warp (alternating, so that one barrier per call is enough).
-template <int NO>
-__device__ __forceinline__ void path_put_dz(PathCtx& p, const TcNet& t, const float (&dout)[NO], unsigned char* dzimg, int row, uint32_t* mxbuf) {
-    const int N16 = t.ly[t.L].N16, nl = t.ly[t.L].nl;
-    float m = 0.f;
-#pragma unroll
-    for (int n = 0; n < NO; ++n)
-        if (n < nl) m = fmaxf(m, fabsf(dout[n]));
-    uint32_t mu = __reduce_max_sync(0xffffffffu, __float_as_uint(m));        // (non-negative floats order like their bit patterns)
-    uint32_t* mb = mxbuf + ((p.sync & SY_DZ) ? 8 : 0);
-    p.sync ^= SY_DZ;
-    if ((threadIdx.x & 31) == 0) mb[threadIdx.x >> 5] = mu;
-    asm volatile("bar.sync 2, %0;" ::"r"(TC_PATH_THREADS) : "memory");
-#pragma unroll
-    for (int w = 0; w < TC_PATH_THREADS / 32; ++w) mu = max(mu, mb[w]);
-    const int ex = (int)((mu >> 23) & 0xffu);
-    p.dexp = (ex == 0 || ex == 255) ? 0 : (11 - (ex - 127));                  // zero / denormal / non-finite maximum: no scaling
-    p.dexp = p.dexp < -100 ? -100 : (p.dexp > 100 ? 100 : p.dexp);
-    const float sc = pow2f(p.dexp);
-#pragma unroll
-    for (int c = 0; c < 2; ++c) {
-        if (c < N16 / 16 && (c % TC_NGRP) == p.grp) {
-            float v[16];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                const int n = 16 * c + j;
-                v[j] = (n < NO && n < nl) ? dout[n < NO ? n : 0] * sc : 0.f;
-            }
-            put16(path_planes(p) + 16 * c, v);
-            if (dzimg) copy16f(dzimg, row, c, v, -1);
-        }
-    }
-    if (dzimg) fence_proxy_async();
-    path_publish(p);
-}
-
-// middle of the backward: for l = L..0 the dW drains (need_w), and for l >= 1 the dX epilogue
-// dz_{l-1} = dA_l (.) slope(a_l) -> planes (+ DZ).  Ends before the result of the last product (dy0) is read.
-static __device__ __noinline__ uint32_t path_backward_mid_(PathArg p, const TcNet& t, const TcSlab& g, const Masks& mk, bool need_w, float* slab,
-                                               unsigned char* dzimg, int row) {
+// the helpers' part of a backward evaluation: for l = L..0 the dW drains (need_w), and for l >= 1 the dX epilogue
+// dz_{l-1} = dA_l (.) slope(a_l) -> planes (+ DZ image)
+static __device__ __noinline__ uint32_t help_backward_(PathArg p, const TcNet& t, const TcSlab& g, const Masks& mk, bool need_w, float* slab,
+                                                       unsigned char* dzimg, int row, const volatile int* dexp) {
     for (int l = t.L; l >= 0; --l) {
         if (need_w) {
             const int nblk = (t.ly[l].kl + 1 + 127) >> 7;
-            for (int b = 0; b < nblk; ++b) path_drain(p, b, row, t.ly[l].kl, t.ly[l].nl, t.ly[l].N16, slab + g.gW[l]);
+            for (int b = 0; b < nblk; ++b) help_drain(p, b, row, t.ly[l].kl, t.ly[l].nl, t.ly[l].N16, slab + g.gW[l], dexp);
         }
         if (l == 0) break;
         const int K16 = t.ly[l].K16;
         // dA_l in the accumulator (K16_l columns) -> dz_{l-1} planes in place (+ DZ image)
-        for_acc_chunks(p, K16 / 16, need_w ? EPI_ALL : EPI_CHUNKS, need_w ? 1 : 0, [&](int c, const uint32_t* r, uint32_t tc) {
+        for_acc_chunks(p, K16 / 16, need_w ? EPI_ALL : EPI_CHUNKS, need_w ? 1 : 0, true, [&](int c, const uint32_t* r, uint32_t tc) {
             const uint32_t bits = mk.h[l][c];
             float v[16];
 #pragma unroll
@@ -862,14 +888,60 @@ static __device__ __noinline__ uint32_t path_backward_mid_(PathArg p, const TcNe
     }
     return p.sync;
 }
-__device__ __forceinline__ void path_backward_mid(PathCtx& p, const TcNet& t, const TcSlab& g, const Masks& mk, bool need_w, float* slab,
-                                                  unsigned char* dzimg, int row) {
-    p.sync = path_backward_mid_(p, t, g, mk, need_w, slab, dzimg, row);
+__device__ __forceinline__ void help_backward(PathCtx& p, const TcNet& t, const TcSlab& g, const Masks& mk, bool need_w, float* slab,
+                                              unsigned char* dzimg, int row, const volatile int* dexp) {
+    p.sync = help_backward_(p, t, g, mk, need_w, slab, dzimg, row, dexp);
 }
-// cotangent of y0 (in <= 31 values, static indexing)
+
+// ---- owners -------------------------------------------------------------------------------------------------------
+// cotangent of the raw output (nl <= 32 values, static indexing) -> planes (+ DZ image), publish.  The evaluation runs
+// scaled by 2^dexp, chosen so that the largest |cotangent| of the tile lands in [2^11, 2^12): mxbuf = shared memory, two
+// rows of one word per owner warp (alternating, so that one barrier per call is enough); dexp_out = the shared word the
+// helpers read the exponent from when they drain.  skip_last: the forward stopped at the last hidden layer -- wait until
+// its products are done (then the region that held the inputs of that layer is free for the dz planes).
+template <int NO>
+__device__ __forceinline__ void own_put_dz(PathCtx& p, const TcNet& t, const float (&dout)[NO], unsigned char* dzimg, int row, uint32_t* mxbuf,
+                                           volatile int* dexp_out, bool skip_last) {
+    const int N16 = t.ly[t.L].N16, nl = t.ly[t.L].nl;
+    float m = 0.f;
+#pragma unroll
+    for (int n = 0; n < NO; ++n)
+        if (n < nl) m = fmaxf(m, fabsf(dout[n]));
+    uint32_t mu = __reduce_max_sync(0xffffffffu, __float_as_uint(m));        // (non-negative floats order like their bit patterns)
+    uint32_t* mb = mxbuf + ((p.sync & SY_DZ) ? 8 : 0);
+    p.sync ^= SY_DZ;
+    if ((threadIdx.x & 31) == 0) mb[threadIdx.x >> 5] = mu;
+    asm volatile("bar.sync 2, %0;" ::"r"(TC_OWN_THREADS) : "memory");
+#pragma unroll
+    for (int w = 0; w < TC_OWN_THREADS / 32; ++w) mu = max(mu, mb[w]);
+    const int ex = (int)((mu >> 23) & 0xffu);
+    p.dexp = (ex == 0 || ex == 255) ? 0 : (11 - (ex - 127));                  // zero / denormal / non-finite maximum: no scaling
+    p.dexp = p.dexp < -100 ? -100 : (p.dexp > 100 ? 100 : p.dexp);
+    if (threadIdx.x == 0) *dexp_out = p.dexp;
+    const float sc = pow2f(p.dexp);
+    if (skip_last) { own_wait_fin(p); own_swaps(p, t.L - 1); }
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+        if (c < N16 / 16) {
+            float v[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const int n = 16 * c + j;
+                v[j] = (n < NO && n < nl) ? dout[n < NO ? n : 0] * sc : 0.f;
+            }
+            put16(path_planes(p) + 16 * c, v);
+            if (dzimg) copy16f(dzimg, row, c, v, -1);
+        }
+    }
+    if (dzimg) fence_proxy_async();
+    own_publish(p);
+}
+
+// cotangent of y0 (in <= 31 values, static indexing); the helpers converted the L accumulators dA_L..dA_1 in the meantime
 template <int NX>
-__device__ __forceinline__ void path_get_dy0(PathCtx& p, const TcNet& t, float (&dy0)[NX]) {
-    path_wait_acc(p);
+__device__ __forceinline__ void own_get_dy0(PathCtx& p, const TcNet& t, float (&dy0)[NX]) {
+    own_wait_fin(p);
+    own_swaps(p, t.L);
     const uint32_t acc = path_acc(p);
     const float inv = pow2f(-p.dexp);                                      // the evaluation ran scaled by 2^dexp
     const int K16 = t.ly[0].K16;
@@ -887,14 +959,26 @@ __device__ __forceinline__ void path_get_dy0(PathCtx& p, const TcNet& t, float (
         }
     }
 }
-// backward of one network evaluation on the path side.  dout: cotangent of the raw output; slab: this CTA's
-// gradient slab of the network (need_w); dy0 receives the cotangent of y0.
+// What the combined mode (no helper warps) needs besides the owner's own arguments: the helpers' arguments.
+struct HelpArgs {
+    Masks* mk; unsigned char* copies; unsigned char* act; const TcSlab* g; float* slab;
+};
+// forward evaluation that keeps what the backward needs, as the owners see it: y0 (+ its FP16 copy) -> [hidden layers] ->
+// raw output (skip_last: no output, the backward starts from the last hidden layer)
+template <int NX, int NO>
+__device__ __forceinline__ void own_net_forward_keep(PathCtx& p, const TcNet& t, const float* vec, const float (&x)[NX], float (&out)[NO],
+                                                     unsigned char* copies, int row, bool skip_last, const HelpArgs& h) {
+    own_put_y0(p, t, vec, x, copies, row);
+    if (TC_COMBINED) help_forward_keep(p, t, vec, *h.mk, h.copies, h.act, row, skip_last);
+    if (!skip_last) own_last(p, t, vec, out);
+}
+// backward of one network evaluation as the owners see it.  dout: cotangent of the raw output; dy0 receives the cotangent of y0.
 template <int NO, int NX>
-__device__ __forceinline__ void path_net_backward(PathCtx& p, const TcNet& t, const TcSlab& g, const Masks& mk, const float (&dout)[NO], bool need_w,
-                                                  float* slab, unsigned char* dzimg, int row, float (&dy0)[NX], uint32_t* mxbuf) {
-    path_put_dz(p, t, dout, need_w ? dzimg : nullptr, row, mxbuf);
-    path_backward_mid(p, t, g, mk, need_w, slab, dzimg, row);
-    path_get_dy0(p, t, dy0);
+__device__ __forceinline__ void own_net_backward(PathCtx& p, const TcNet& t, const float (&dout)[NO], bool need_w, unsigned char* dzimg, int row,
+                                                 float (&dy0)[NX], uint32_t* mxbuf, volatile int* dexp_out, bool skip_last, const HelpArgs& h) {
+    own_put_dz(p, t, dout, need_w ? dzimg : nullptr, row, mxbuf, dexp_out, skip_last);
+    if (TC_COMBINED) help_backward(p, t, *h.g, *h.mk, need_w, h.slab, dzimg, row, dexp_out);
+    own_get_dy0(p, t, dy0);
 }
 
 }  // namespace tc

@@ -29,11 +29,11 @@ for impl in ("tensor", "exact"):
         sta = eng.tc_stats(B, N) if impl == "tensor" else None
     if impl == "tensor":
         for nm, st in (("critic", stc), ("actor", sta)):
-            print(f"  {nm} CTA0 cycles: total {st[0]:,}  ctrl waits path {st[1]:,} ({st[1]/st[0]:.1%})  ops {st[3]:,} "
-                  f"({st[0]/max(st[3],1):.0f} cyc/op)  path waits tensor {st[4]:,} ({st[4]/st[0]:.1%})  path epilogue {st[5]:,} ({st[5]/st[0]:.1%}) of which hidden-layer epilogues {st[6]:,} ({st[6]/st[0]:.1%}); ctrl issue loops {st[7]:,} ({st[7]/st[0]:.1%}) MMA tail {st[8]:,} ({st[8]/st[0]:.1%})"
-                  + f"; dW: ctrl waits operands {st[2]:,} ({st[2]/st[0]:.1%}) waits MMA {st[8]:,} ({st[8]/st[0]:.1%})"
-                  + (f" waits ACT copy {st[9]:,} ({st[9]/st[0]:.1%}); path in drains {st[11]:,} ({st[11]/st[0]:.1%}); path segments: forward rollout {st[12]/st[0]:.1%}, reverse: forward_keep {st[13]/st[0]:.1%} adjoint {st[14]/st[0]:.1%} backward {st[15]/st[0]:.1%}" if nm == "actor" else "")
-                  + (f"; phases rollout {st[9]/st[0]:.1%} value {st[10]/st[0]:.1%} grad sweep {st[11]/st[0]:.1%}; rollout per-path arithmetic: increments {st[12]:,} step size {st[13]:,} cost+move {st[14]:,} sums {st[15]:,}" if nm == "critic" and st[9] else ""))
+            T = max(int(st[0]), 1)
+            print(f"  {nm} CTA0 cycles: total {st[0]:,} ops {st[3]:,} ({st[0]/max(st[3],1):.0f} cyc/op) | control warp: waits owners/helpers {st[1]/T:.1%}, "
+                  f"dW waits operands {st[2]/T:.1%}, in issue loops {st[7]/T:.1%}, waits MMAs reading ACT {st[8]/T:.1%} | owner thread 0: waits network "
+                  f"results {st[4]/T:.1%}, writes inputs {st[5]/T:.1%} | helper thread 128: waits tensor pipe {st[9]/T:.1%}, hidden epilogues (incl. wait) "
+                  f"{st[6]/T:.1%}, dW drains {st[10]/T:.1%}")
     live = torch.clamp(r["exit_index"].long() + 1, max=N).sum().item()
     print(f"{impl:7s} B={B} grad={need_grad}: critic kernel {kc:9.3f} ms, actor kernel {ka:9.3f} ms, live path-steps {live} "
           f"({live / (B * N):.3f}); critic loss {float(r['loss'].sum()):.6f} actor loss {float(a['loss'][0]):.6f}; "
