@@ -23,6 +23,10 @@
 //     accumulator of layer l from TMEM (tcgen05.ld), applies the BatchNorm affine + y+relu(y), splits
 //     and writes the two bf16 planes back to TMEM (tcgen05.st), from where layer l+1 reads them as the
 //     A operand (tcgen05.mma with A in tensor memory).
+//   * BatchNorm folded into the products: the forward image of layer l holds W[k][n] * gamma_n c (c = 1/sqrt(1+eps)), its row
+//     k = kl (the spare input feature, which every activation carries as a constant 1) holds beta_n (+ bias_n gamma_n c for
+//     the last layer), and its entry (kl, nl) is 0.5, so that the accumulator IS z = a W gamma c + beta and the spare
+//     output feature becomes z + relu(z) = 1 again: the epilogues neither load gamma/beta nor multiply.
 //   * Weights: the pack kernel turns the flat FP32 parameters into bf16 hi/lo operand images (layout in
 //     dpb_tc.cuh), cut into 16-wide contraction chunks of N16*64 bytes.  The control thread streams the
 //     chunks L2 -> shared memory through a ring of slots with 1-D bulk copies (cp.async.bulk,
@@ -182,8 +186,17 @@ static __global__ void tc_pack_kernel(TcNet t, const float* __restrict__ th, uns
             const bool in_rng = (k < y.kl && n < y.nl);
             const float w = in_rng ? th[nd.fW[l] + (long long)k * y.nl + n] : 0.f;
             __nv_bfloat16 hi, lo;
-            // forward image: rows n (N16), contraction k; chunk = k/16
-            split_bf16(w, hi, lo);
+            // forward image: rows n (N16), contraction k; chunk = k/16.  BatchNorm folded in (see the header): W gamma c, row kl =
+            // beta (+ bias gamma c), entry (kl, nl) = 0.5 keeps the constant-1 feature alive through z + relu(z)
+            float wf = 0.f;
+            if (n < y.nl) {
+                const float gcn = th[nd.fg[l] + n] * c;
+                if (k < y.kl) wf = w * gcn;
+                else if (k == y.kl) wf = (l == t.L) ? th[nd.fbias + n] * gcn + th[nd.fb[l] + n] : th[nd.fb[l] + n];
+            } else if (n == y.nl && k == y.kl && l < t.L) {
+                wf = 0.5f;
+            }
+            split_bf16(wf, hi, lo);
             {
                 const long long cb = (long long)y.N16 * 64;
                 unsigned char* base = img + y.img_f + (k >> 4) * cb + (((k & 15) >> 3) * (y.N16 >> 3) + (n >> 3)) * 128 + (n & 7) * 16 + (k & 7) * 2;
@@ -537,11 +550,18 @@ __device__ __forceinline__ void for_acc_chunks(PathCtx& p, int nco, int mode, in
     TC_STAT(else p.t_epi += clock64() - p.t_mark;)
 }
 
-// z = acc * gc + bb for 16 features (gc, bb: 16-byte aligned shared memory)
+// z = acc * gc + bb for 16 features (gc, bb: 16-byte aligned SHARED memory; read with ld.shared -- through generic pointers the
+// compiler emitted eight generic 128-bit loads per chunk)
+__device__ __forceinline__ float4 lds4(uint32_t saddr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
+    return v;
+}
 __device__ __forceinline__ void affine16(const uint32_t* r, const float* gc, const float* bb, float* z) {
+    const uint32_t ga = smem_u32(gc), ba = smem_u32(bb);
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-        const float4 g = reinterpret_cast<const float4*>(gc)[q], b = reinterpret_cast<const float4*>(bb)[q];
+        const float4 g = lds4(ga + 16 * q), b = lds4(ba + 16 * q);
         up2(fma2(pk2(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1])), pk2(g.x, g.y), pk2(b.x, b.y)), z[4 * q], z[4 * q + 1]);
         up2(fma2(pk2(__uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3])), pk2(g.z, g.w), pk2(b.z, b.w)), z[4 * q + 2], z[4 * q + 3]);
     }
@@ -569,11 +589,11 @@ __device__ __forceinline__ void copy16f(unsigned char* img, int row, int c, cons
 // hidden layer epilogue: a = z + relu(z), z = acc * gc + bb (solver.py:267-269) -> planes
 __device__ __forceinline__ void help_epi_hidden(PathCtx& p, const float* gcbb, int N16) {
     TC_STAT(const long long th0 = clock64();)
-    const float* gc = gcbb;
-    const float* bb = gcbb + N16;
+    (void)gcbb;                                                           // (BatchNorm is folded into the product: the accumulator is z)
     for_acc_chunks(p, N16 / 16, EPI_CHUNKS, 0, true, [&](int c, const uint32_t* r, uint32_t tc) {
         float v[16];
-        affine16(r, gc + 16 * c, bb + 16 * c, v);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
 #pragma unroll
         for (int j = 0; j < 8; ++j)
             up2(add2(pk2(v[2 * j], v[2 * j + 1]), pk2(fmaxf(v[2 * j], 0.f), fmaxf(v[2 * j + 1], 0.f))), v[2 * j], v[2 * j + 1]);
@@ -623,7 +643,7 @@ __device__ __forceinline__ void own_put_y0(PathCtx& p, const TcNet& t, const flo
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
                 const int k = 16 * c + j;
-                v[j] = (k < NX && k < t.in) ? x[k < NX ? k : 0] * g0c[k] + b0[k] : 0.f;
+                v[j] = (k < NX && k < t.in) ? x[k < NX ? k : 0] * g0c[k] + b0[k] : (k == t.in ? 1.f : 0.f);      // (k = in: the constant 1)
             }
             put16(path_planes(p) + 16 * c, v);
             if (copies) copy16f(copies, row, c, v, t.ly[0].kl);
@@ -641,8 +661,7 @@ __device__ __forceinline__ void own_last(PathCtx& p, const TcNet& t, const float
     own_swaps(p, t.L);
     const uint32_t acc = path_acc(p);
     const int N16 = t.ly[t.L].N16, nl = t.ly[t.L].nl;
-    const float* gc = vec + t.ly[t.L].vec;
-    const float* bb = gc + N16;
+    (void)vec;
 #pragma unroll
     for (int c = 0; c < 2; ++c) {
         if (c < N16 / 16) {
@@ -652,7 +671,7 @@ __device__ __forceinline__ void own_last(PathCtx& p, const TcNet& t, const float
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
                 const int n = 16 * c + j;
-                if (n < NO && n < nl) out[n < NO ? n : 0] = __uint_as_float(r[j]) * gc[n] + bb[n];
+                if (n < NO && n < nl) out[n < NO ? n : 0] = __uint_as_float(r[j]);        // (affine map and bias folded into the product)
             }
         }
     }
@@ -802,15 +821,15 @@ static __device__ __noinline__ uint32_t help_forward_keep_(PathArg p, const TcNe
                                                            unsigned char* act, int row, bool skip_last) {
     for (int l = 0; l < t.L; ++l) {
         const int N16 = t.ly[l].N16;
-        const float* gc = vec + t.ly[l].vec;
-        const float* bb = gc + N16;
+        (void)vec;
         const bool last_hidden = (l == t.L - 1);
         unsigned char* dst = last_hidden ? act : (copies ? copies + tc_copy_off(t, l + 1) : nullptr);
         const int one_at = t.ly[l + 1].kl;
         const bool planes = !(last_hidden && skip_last);                 // (skip_last: nothing reads a_L as an MMA operand)
         for_acc_chunks(p, N16 / 16, planes ? EPI_CHUNKS : EPI_ALL, dst ? (last_hidden ? 1 : 2) : 0, planes, [&](int c, const uint32_t* r, uint32_t tc) {
             float v[16];
-            affine16(r, gc + 16 * c, bb + 16 * c, v);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);       // (z itself: BatchNorm is folded into the product)
             uint32_t bits = 0;
 #pragma unroll
             for (int j = 0; j < 16; ++j) bits |= (v[j] > 0.f ? 1u : 0u) << j;
