@@ -178,6 +178,9 @@ def main():
     ap.add_argument("--workload", default="lqr_d20_2p20", choices=list(WORKLOADS))
     ap.add_argument("--dtype", default="float32")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cuda-graph", default="auto", choices=["auto", "on", "off"],
+                    help="replay each training iteration as ONE captured CUDA graph (solver.enable_cuda_graph); auto: on for "
+                         "config-size batches (<= 8192 paths per rank, where launch latency shows), single process only")
     args = ap.parse_args()
     # stdout carries exactly one JSON line: keep a private handle to it and point file descriptor 1 at stderr, so that
     # nothing a library prints (NCCL's version banner goes to fd 1) can end up in front of the line
@@ -237,7 +240,10 @@ def main():
         torch.cuda.synchronize()
 
     # ---------------------------------------------------------------- value: inputs resident in HBM
-    for _ in range(args.warmup):
+    use_graph = world == 1 and (args.cuda_graph == "on" or (args.cuda_graph == "auto" and B <= 8192))
+    if use_graph:
+        use_graph = solver.enable_cuda_graph()
+    for _ in range(max(args.warmup, 2 if use_graph else 0)):      # (the first graph iteration runs eagerly, the second captures)
         solver.train_iteration()
     sync_all()
     sampler = ClockSampler(local_rank) if rank == 0 else None
@@ -254,6 +260,10 @@ def main():
     sync_all()
     ms = ev0.elapsed_time(ev1)
     launches = eng.launch_count() - l0
+    if use_graph:                                                # replayed graphs: the library's launch counter does not see them
+        launches += args.steps * solver._graph["launches"]
+        solver._graph = None                                      # the roofline / e2e sections below launch kernel by kernel
+        eng.set_timing(True)
     clocks = sampler.stop() if sampler else None
     tms = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -373,7 +383,7 @@ def main():
                 "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": ("f32 (bf16x3 tensor-core products, FP32 accumulate)" if impl == "tensor" else "f32" if args.dtype == "float32" else "f64"), "data": "synthetic",
                 "config": config_desc, "impl": impl, "iters_per_sec": args.steps / (ms * 1e-3), "clocks": clocks, "e2e": e2e,
-                "gpu_launches": launches, "roofline": roofline, "roofline_kernels": rk, "cpu_baseline": cpu, "last_losses": losses,
+                "gpu_launches": launches, "cuda_graph": bool(use_graph), "roofline": roofline, "roofline_kernels": rk, "cpu_baseline": cpu, "last_losses": losses,
                 "kernel_source_hash": src_hash}
         print(json.dumps(line), file=json_out, flush=True)
     if world > 1:

@@ -68,6 +68,7 @@ struct Layout {
     size_t pkA, pkV, pkG, loss_part, loss_out, scratch, slabs, raw, total;
     size_t imgA, imgV, imgG, vecA, vecV, vecG, copies, stats;      // tensor path: operand images, vector blocks, activation copies, counters
     size_t life_nacc, life_perm, life_hist;                        // tensor path, naive scheme: lifetime sort (exit counts, permutation, bins)
+    size_t s2_rhog, s2_tlive;                                      // tensor path, small batches: hand-over to the second-sweep launch
     long long scratch_per_cta, copies_per_cta;
 };
 
@@ -96,17 +97,20 @@ static Layout make_layout(const dpb_handle* h, long long B_local, int N) {
     L.loss_out = o; o += 256;
     L.scratch_per_cta = (long long)N * (2 * h->sr + A_NSCAL) * P;
     L.scratch = o; o += a256((size_t)L.grid * L.scratch_per_cta * es);
-    L.copies = 0; L.copies_per_cta = 0; L.stats = 0; L.life_nacc = L.life_perm = L.life_hist = 0;
+    L.copies = 0; L.copies_per_cta = 0; L.stats = 0; L.life_nacc = L.life_perm = L.life_hist = 0; L.s2_rhog = L.s2_tlive = 0;
     if (tensor) {
         long long cb = tc::tc_copy_bytes(h->tA);
         if (tc::tc_copy_bytes(h->tV) > cb) cb = tc::tc_copy_bytes(h->tV);
         if (tc::tc_copy_bytes(h->tG) > cb) cb = tc::tc_copy_bytes(h->tG);
         L.copies_per_cta = (long long)a256((size_t)cb);
-        L.copies = o; o += a256((size_t)L.grid * L.copies_per_cta);
-        L.stats = o; o += a256((size_t)L.grid * 16 * 8 + 64);           // + the tile counter of the dynamic tile scheduler
+        // (sized for every SM: the second-sweep launch of a small batch runs more CTAs than the batch has tiles)
+        L.copies = o; o += a256((size_t)h->num_sms * L.copies_per_cta);
+        L.stats = o; o += a256((size_t)h->num_sms * 16 * 8 + 64);       // + the tile counter of the dynamic tile scheduler
         L.life_nacc = o; o += a256((size_t)B_local * 4);
         L.life_perm = o; o += a256((size_t)B_local * 4);
         L.life_hist = o; o += a256((size_t)(N + 2) * 4);
+        L.s2_rhog = o; o += a256((size_t)ntiles * tc::TC_PATHS * 4);
+        L.s2_tlive = o; o += a256((size_t)ntiles * 4);
     }
     const long long gc = tensor ? h->sV.gtotal + h->sG.gtotal : h->nV.gtotal + h->nG.gtotal, ga = tensor ? h->sA.gtotal : h->nA.gtotal;
     const long long gmax = gc > ga ? gc : ga;
@@ -463,7 +467,7 @@ static void tc_fill(dpb_handle* h, tc::TcArgs& a, const Layout& L, char* ws, con
     a.copies = (unsigned char*)(ws + L.copies);
     a.copies_per_cta = L.copies_per_cta;
     a.stats = (long long*)(ws + L.stats);
-    a.tile_counter = (int*)(ws + L.stats + (size_t)L.grid * 16 * 8);
+    a.tile_counter = (int*)(ws + L.stats + (size_t)h->num_sms * 16 * 8);
     a.nslab = L.nslab;
     a.sr = h->sr;
     if (outs) {
@@ -548,12 +552,34 @@ static int critic_step_tc(dpb_handle* h, const void* thA, const void* thV, const
         a.perm = (const int*)(ws + L.life_perm);
     }
     DPB_CUDA(h, cudaMemsetAsync(a.tile_counter, 0, sizeof(int), st));
+    // Small batch (the tiles occupy fewer than half of the SMs): the second sweep -- one independent backward per stored step --
+    // runs as a second launch that spreads (tile, block of steps) items over all SMs (dpb_tc_kernels.cuh, F_S2_ONLY)
+    static const bool no_split = getenv("DPB_NO_SWEEP_SPLIT") != nullptr;
+    const long long ntl = (B_local + tc::TC_PATHS - 1) / tc::TC_PATHS;
+    const bool split = !no_split && need_grad && td1 && ntl * 2 <= h->num_sms;
+    if (split) {
+        a.flags |= tc::F_S2_DEFER;
+        a.s2_rhog = (float*)(ws + L.s2_rhog);
+        a.s2_tlive = (int*)(ws + L.s2_tlive);
+        int nblk = (int)((h->num_sms + ntl - 1) / ntl);
+        if (nblk > N) nblk = N;
+        a.s2_chunk = (N + nblk - 1) / nblk;
+    }
     ev_begin(h, st);
     cudaFuncAttributes fa;                                       // threads per CTA = the launch bound of the instantiation
     DPB_CUDA(h, cudaFuncGetAttributes(&fa, kern));               // (its translation unit chooses the number of path-thread groups)
     kern<<<L.grid, fa.maxThreadsPerBlock, smem, st>>>(a);
-    ev_end(h, st);
     h->launches++;
+    if (split) {
+        tc::TcArgs b = a;
+        b.flags = (a.flags & ~tc::F_S2_DEFER) | tc::F_S2_ONLY;
+        b.loss_part = nullptr;
+        const long long items = ntl * ((N + a.s2_chunk - 1) / a.s2_chunk);
+        const int grid2 = (int)(items < h->num_sms ? items : h->num_sms);
+        kern<<<grid2, fa.maxThreadsPerBlock, smem, st>>>(b);
+        h->launches++;
+    }
+    ev_end(h, st);
     DPB_CUDA(h, cudaGetLastError());
     if (out_loss && !prop_only) {
         const float s = (float)(100.0 / (double)B_global);

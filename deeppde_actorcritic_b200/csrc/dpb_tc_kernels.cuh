@@ -44,7 +44,14 @@ struct TcArgs {
     int* tile_counter;              // zeroed before the launch: CTAs take tile blockIdx.x first, then gridDim.x + counter++
     const int* perm;                // optional: slot i of the tiling works on local path perm[i] (naive scheme: paths sorted by
                                     // lifetime so that the tiles die as a whole; NULL: identity)
+    // Small batches (fewer tiles than half the SMs): the second sweep of the critic -- one independent backward per stored
+    // step -- is cut out of the rollout launch (F_S2_DEFER) and run by a second launch of the same kernel (F_S2_ONLY) that
+    // deals (tile, block of s2_chunk steps) items out to ALL SMs.
+    float* s2_rhog;                 // [tiles][128] rho'(delta) * 100 / B of every path (written by the first launch)
+    int* s2_tlive;                  // [tiles] steps the tile was alive
+    int s2_chunk;
 };
+constexpr unsigned F_S2_DEFER = 0x100u, F_S2_ONLY = 0x200u;       // internal flags (above the DPB_FLAG_* bits)
 
 // the kernels are instantiated in their own translation units (dpb_tc_inst_*.cu)
 typedef void (*TcKernelFn)(const TcArgs);
@@ -290,6 +297,58 @@ __device__ __forceinline__ void critic_tc_body(const TcArgs& a, const TcSmem& S,
 
     float loss0 = 0.f, loss1 = 0.f;
     const long long ntiles = (a.B_local + TC_PATHS - 1) / TC_PATHS;
+    if (a.flags & F_S2_ONLY) {
+        // second launch of a small batch: (tile, block of steps) items of the second sweep, dealt out to all CTAs.  Tile i was
+        // rolled out by CTA i of the first launch (fewer tiles than CTAs), so its trajectory sits in that CTA's scratch.
+        const int nblk = (N + a.s2_chunk - 1) / a.s2_chunk;
+        bool first = true;
+        for (long long it = blockIdx.x; it < ntiles * nblk; it += gridDim.x) {
+            const long long tile = it / nblk;
+            const int t0 = (int)(it % nblk) * a.s2_chunk;
+            const int tl = a.s2_tlive[tile];
+            const int t1 = (t0 + a.s2_chunk < tl) ? t0 + a.s2_chunk : tl;
+            if (t0 >= t1) continue;                                     // (the same decision in every thread of the CTA)
+            const float* trj = a.scratch + (size_t)tile * a.scratch_per_cta;
+            if (is_ctrl) {
+                if (first) {                                            // one cyclic schedule serves every item
+                    ctrl_flush(C);
+                    sched_add_fwd(C, nG, a.imgG, nG.L - 1);
+                    sched_add_bwd(C, nG, a.imgG);
+                    ctrl_sched_ready(C);
+                }
+                for (int t = t0; t < t1; ++t) {
+                    ctrl_net_forward(C, nG, nG.L - 1);
+                    ctrl_net_backward(C, nG, true, copies, true);
+                }
+            } else if (is_help) {
+                Masks mk;
+                for (int t = t0; t < t1; ++t) {
+                    help_forward_keep(P, nG, S.vecG, mk, copies, S.act, row, true);
+                    help_backward(P, nG, gG, mk, true, gsG, S.dz, row, dexp);
+                }
+            } else {
+                float xt[DPX], cot[DPX], dy0[DPX], sxG[DPX], s0G[DPX];
+#pragma unroll
+                for (int k = 0; k < DPX; ++k) { sxG[k] = 0.f; s0G[k] = 0.f; }
+                Masks mkc;                                              // (combined mode only)
+                const HelpArgs hg = {&mkc, copies, S.act, &gG, gsG};
+                const float rg = a.s2_rhog[tile * TC_PATHS + row];
+                for (int t = t0; t < t1; ++t) {
+                    const float* tr = trj + (size_t)t * 2 * sr * TC_PATHS;
+                    KLOOP(k, d) { xt[k] = __ldcs(&tr[k * TC_PATHS + row]); cot[k] = __ldcs(&tr[(sr + k) * TC_PATHS + row]) * rg; }
+                    float none[1];
+                    own_net_forward_keep(P, nG, S.vecG, xt, none, copies, row, true, hg);
+                    own_net_backward(P, nG, cot, true, S.dz, row, dy0, mxbuf, dexp, true, hg);
+                    acc_input_sums<DPX>(sxG, s0G, xt, dy0, d);
+                }
+                reduce_rows_to<DPX>(gsG + gG.gX, sxG, d);
+                reduce_rows_to<DPX>(gsG + gG.g0, s0G, d);
+            }
+            first = false;
+        }
+        if (is_ctrl) { ctrl_flush(C); C.pc->quit = 1; }
+        return;
+    }
     for (long long tile = blockIdx.x; tile < ntiles; tile = tc_next_tile(S, a)) {
         const long long base = tile * TC_PATHS;
         const long long slot = base + row;                        // position of this thread's path in the tiling
@@ -449,7 +508,10 @@ __device__ __forceinline__ void critic_tc_body(const TcArgs& a, const TcSmem& S,
         loss0 += tc_block_sum(rho_v, S.red);
         loss1 += tc_block_sum(rho_b, S.red);
         // ------------------------------------------------------------------ sweep 2: NN_value_grad backward
-        if (need_grad && td1) {
+        if (need_grad && td1 && (a.flags & F_S2_DEFER)) {             // small batch: left to the second launch (see F_S2_ONLY)
+            if (is_own) a.s2_rhog[tile * TC_PATHS + row] = rhog;
+            if (tid == 0) a.s2_tlive[tile] = tlive;
+        } else if (need_grad && td1) {
             if (is_ctrl) {
                 ctrl_flush(C);
                 sched_add_fwd(C, nG, a.imgG, nG.L - 1);
