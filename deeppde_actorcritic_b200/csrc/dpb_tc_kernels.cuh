@@ -238,28 +238,6 @@ __device__ __forceinline__ void roles_stats(const Roles& r, const TcArgs& a, lon
     TC_STAT(if (threadIdx.x == 128) { st[6] = r.P.t_hid; st[9] = r.P.t_accw; st[10] = r.P.t_drain; })
 }
 
-// Input-layer sums SX[k] = sum x_k dy0_k, S0[k] = sum dy0_k, kept by the owner threads in registers (all indices static -- a
-// run-time index anywhere would put the accumulators in local memory).
-template <int DPX>
-__device__ __forceinline__ void acc_input_sums(float (&sx)[DPX], float (&s0)[DPX], const float (&x)[DPX], const float (&dy0)[DPX], int d) {
-#pragma unroll
-    for (int j = 0; j < DPX; ++j)
-        if (j < d) { sx[j] += x[j] * dy0[j]; s0[j] += dy0[j]; }
-}
-// sum over the owner threads -> atomicAdd into dst[k]
-template <int DPX>
-__device__ __forceinline__ void reduce_rows_to(float* dst, const float (&acc)[DPX], int d) {
-#pragma unroll
-    for (int j = 0; j < DPX; ++j) {
-        if (j < d) {                                                  // (d is uniform: the shuffles stay convergent)
-            float v = acc[j];
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-            if ((threadIdx.x & 31) == 0) atomicAdd(dst + j, v);
-        }
-    }
-}
-
 // ================================================================================== critic (tensor)
 // DP > 0: instantiation for dim (and control_dim + 1) <= DP with equation EQN fixed at compile time -- the
 // per-path vectors are register arrays and every d-loop is unrolled (MV > 0: VDP with control_dim = MV, which makes its
@@ -327,9 +305,7 @@ __device__ __forceinline__ void critic_tc_body(const TcArgs& a, const TcSmem& S,
                     help_backward(P, nG, gG, mk, true, gsG, S.dz, row, dexp);
                 }
             } else {
-                float xt[DPX], cot[DPX], dy0[DPX], sxG[DPX], s0G[DPX];
-#pragma unroll
-                for (int k = 0; k < DPX; ++k) { sxG[k] = 0.f; s0G[k] = 0.f; }
+                float xt[DPX], cot[DPX], dy0[DPX];
                 Masks mkc;                                              // (combined mode only)
                 const HelpArgs hg = {&mkc, copies, S.act, &gG, gsG};
                 const float rg = a.s2_rhog[tile * TC_PATHS + row];
@@ -339,10 +315,7 @@ __device__ __forceinline__ void critic_tc_body(const TcArgs& a, const TcSmem& S,
                     float none[1];
                     own_net_forward_keep(P, nG, S.vecG, xt, none, copies, row, true, hg);
                     own_net_backward(P, nG, cot, true, S.dz, row, dy0, mxbuf, dexp, true, hg);
-                    acc_input_sums<DPX>(sxG, s0G, xt, dy0, d);
                 }
-                reduce_rows_to<DPX>(gsG + gG.gX, sxG, d);
-                reduce_rows_to<DPX>(gsG + gG.g0, s0G, d);
             }
             first = false;
         }
@@ -470,11 +443,6 @@ __device__ __forceinline__ void critic_tc_body(const TcArgs& a, const TcSmem& S,
                 own_net_forward(P, nV, S.vecV, x, vN);
                 own_net_forward(P, nV, S.vecV, xbv, vb);
             } else {
-                // (the input-layer sums of NN_value are flushed once per tile: three updates do not justify registers that
-                //  stay live through both sweeps)
-                float sxV[DPX], s0V[DPX];
-#pragma unroll
-                for (int k = 0; k < DPX; ++k) { sxV[k] = 0.f; s0V[k] = 0.f; }
                 Masks mkc;                                                        // (combined mode only)
                 const HelpArgs hv = {&mkc, copies, S.act, &gV, gsV};
                 own_net_forward(P, nV, S.vecV, x0v, v0);
@@ -483,18 +451,13 @@ __device__ __forceinline__ void critic_tc_body(const TcArgs& a, const TcSmem& S,
                 rhog = valid ? rho_grad(delta, 50.f) * scale : 0.f;
                 cot[0] = -rhog * disc;
                 own_net_backward(P, nV, cot, true, S.dz, row, dy0, mxbuf, dexp, false, hv);
-                acc_input_sums<DPX>(sxV, s0V, x, dy0, d);
                 own_net_forward_keep(P, nV, S.vecV, x0v, v0, copies, row, false, hv);
                 cot[0] = rhog;
                 own_net_backward(P, nV, cot, true, S.dz, row, dy0, mxbuf, dexp, false, hv);
-                acc_input_sums<DPX>(sxV, s0V, x0v, dy0, d);
                 own_net_forward_keep(P, nV, S.vecV, xbv, vb, copies, row, false, hv);
                 const float dbb = vb[0] - eq_Z<float, DP, EQN, MV>(E, xbv, 1, 0);
                 cot[0] = valid ? rho_grad(dbb, 50.f) * scale : 0.f;
                 own_net_backward(P, nV, cot, true, S.dz, row, dy0, mxbuf, dexp, false, hv);
-                acc_input_sums<DPX>(sxV, s0V, xbv, dy0, d);
-                reduce_rows_to<DPX>(gsV + gV.gX, sxV, d);
-                reduce_rows_to<DPX>(gsV + gV.g0, s0V, d);
             }
             const float delta = v0[0] - y - vN[0] * disc;                         // solver.py:189
             const float db = vb[0] - eq_Z<float, DP, EQN, MV>(E, xbv, 1, 0);                          // solver.py:190
@@ -529,10 +492,6 @@ __device__ __forceinline__ void critic_tc_body(const TcArgs& a, const TcSmem& S,
                 }
             } else {
                 float xt[DPX], cot[DPX], dy0[DPX];
-                // (input-layer sums of this tile: live in this sweep only, flushed into the slab at its end)
-                float sxG[DPX], s0G[DPX];
-#pragma unroll
-                for (int k = 0; k < DPX; ++k) { sxG[k] = 0.f; s0G[k] = 0.f; }
                 Masks mkc;                                                        // (combined mode only)
                 const HelpArgs hg = {&mkc, copies, S.act, &gG, gsG};
                 for (int t = 0; t < tlive; ++t) {
@@ -541,10 +500,7 @@ __device__ __forceinline__ void critic_tc_body(const TcArgs& a, const TcSmem& S,
                     float none[1];
                     own_net_forward_keep(P, nG, S.vecG, xt, none, copies, row, true, hg);
                     own_net_backward(P, nG, cot, true, S.dz, row, dy0, mxbuf, dexp, true, hg);
-                    acc_input_sums<DPX>(sxG, s0G, xt, dy0, d);
                 }
-                reduce_rows_to<DPX>(gsG + gG.gX, sxG, d);
-                reduce_rows_to<DPX>(gsG + gG.g0, s0G, d);
             }
         }
     }
@@ -610,11 +566,6 @@ __device__ __forceinline__ void actor_tc_body(const TcArgs& a, const TcSmem& S, 
     uint32_t* mxbuf = S.dzmax;
     volatile int* dexp = reinterpret_cast<volatile int*>(S.dzmax + 16);
     (void)traj; (void)copies; (void)gsA; (void)mxbuf; (void)dexp; (void)fill; (void)m; (void)row; (void)trs;
-
-    // input-layer sums of the actor network (owners): kept for the whole kernel, flushed once
-    float sxA[DPX], s0A[DPX];
-#pragma unroll
-    for (int k = 0; k < DPX; ++k) { sxA[k] = 0.f; s0A[k] = 0.f; }
 
     float loss0 = 0.f;
     const long long ntiles = (a.B_local + TC_PATHS - 1) / TC_PATHS;
@@ -782,16 +733,11 @@ __device__ __forceinline__ void actor_tc_body(const TcArgs& a, const TcSmem& S, 
                 }
                 own_net_backward(P, nA, cot, true, S.dz, row, dy0, mxbuf, dexp, false, ha);
                 const float* g0c = S.vecA + nA.vec_g0;
-                acc_input_sums<DPX>(sxA, s0A, xt, dy0, d);
                 KLOOP(k, d) lam[k] = lam[k] + dy0[k] * g0c[k];
             }
         }
     }
     if (is_ctrl) { ctrl_flush(C); C.pc->quit = 1; }
-    if (need_grad && is_own) {
-        reduce_rows_to<DPX>(gsA + gA.gX, sxA, d);
-        reduce_rows_to<DPX>(gsA + gA.g0, s0A, d);
-    }
     if (tid == 0 && a.loss_part) {
         a.loss_part[blockIdx.x * 2] = loss0;
         a.loss_part[blockIdx.x * 2 + 1] = 0.f;

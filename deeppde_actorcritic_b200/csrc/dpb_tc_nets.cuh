@@ -646,7 +646,16 @@ __device__ __forceinline__ void own_put_y0(PathCtx& p, const TcNet& t, const flo
                 v[j] = (k < NX && k < t.in) ? x[k < NX ? k : 0] * g0c[k] + b0[k] : (k == t.in ? 1.f : 0.f);      // (k = in: the constant 1)
             }
             put16(path_planes(p) + 16 * c, v);
-            if (copies) copy16f(copies, row, c, v, t.ly[0].kl);
+            if (copies) {
+                // the dW operand of layer 0 is the RAW input x (+ the constant 1): x^T dz_0 gives the weight gradient AND the
+                // gradients of the input BatchNorm (finalize kernel), so no per-thread input sums are kept
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const int k = 16 * c + j;
+                    v[j] = (k < NX && k < t.in) ? x[k < NX ? k : 0] : 0.f;
+                }
+                copy16f(copies, row, c, v, t.ly[0].kl);
+            }
         }
     }
     if (copies) fence_proxy_async_global();
@@ -694,7 +703,9 @@ namespace tc {
 //   layer l: (kl + 1) rows x nl columns; rows 0..kl-1 = G_l = a_l^T dz_l, row kl = column sums of dz_l (the
 //   activation copies carry a constant 1 in feature kl), stored as [column group of 4][row][4] (tcslab_idx) so that the
 //   32 lanes of a warp -- 32 consecutive rows of the accumulator -- reduce 512 contiguous bytes per instruction;
-//   then SX[in] = sum x*dy0, S0[in] = sum dy0.
+//   layer 0 is stored for the RAW input: rows k < in = GX = x^T dz_0, row `in` = column sums C of dz_0; the finalize kernel forms
+//   y0^T dz_0 = g0c_k GX + b0_k C from it, and the input-BatchNorm gradients SX_k = sum_p x_k dy0_k = sum_n W gc GX[k][n],
+//   S0_k = sum_p dy0_k = sum_n W gc C[n].  (gX / g0 below are no longer used.)
 struct TcSlab { long long gW[MAXLIN], gX, g0, gtotal; };
 __host__ __device__ __forceinline__ long long tcslab_idx(int k, int n, int kl) { return ((long long)(n >> 2) * (kl + 1) + k) * 4 + (n & 3); }
 inline void tcslab_init(TcSlab& g, const TcNet& t) {
@@ -716,19 +727,34 @@ static __global__ void tc_finalize_grad_kernel(TcNet t, TcSlab g, const float* _
     const NetDev& nd = t.flat;
     const long long stride = (long long)gridDim.x * blockDim.x;
     const long long t0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    for (long long i = t0; i < t.in; i += stride) {
-        grad[nd.fg0 + i] = c * raw[g.gX + i];
-        grad[nd.fb0 + i] = raw[g.g0 + i];
+    {   // input BatchNorm (solver.py:265): d gamma0_k = c * sum_p x_k dy0_k, d beta0_k = sum_p dy0_k, dy0 = dz_0 (W_0 gamma_1 c)^T
+        const int kl = t.ly[0].kl, nl = t.ly[0].nl;
+        for (long long k = t0; k < t.in; k += stride) {
+            float sx = 0.f, s0 = 0.f;
+            for (int n = 0; n < nl; ++n) {
+                const float wg = th[nd.fW[0] + k * nl + n] * (th[nd.fg[0] + n] * c);
+                sx = fmaf(wg, raw[g.gW[0] + tcslab_idx((int)k, n, kl)], sx);
+                s0 = fmaf(wg, raw[g.gW[0] + tcslab_idx(kl, n, kl)], s0);
+            }
+            grad[nd.fg0 + k] = c * sx;
+            grad[nd.fb0 + k] = s0;
+        }
     }
     for (int l = 0; l <= t.L; ++l) {
         const int kl = t.ly[l].kl, nl = t.ly[l].nl;
+        // G[k][n] = (a_l^T dz_l)[k][n]; for layer 0 the slab holds x^T dz_0: y0 = x g0c + b0
+        auto G = [&](int k, int n) -> float {
+            const float r = raw[g.gW[l] + tcslab_idx(k, n, kl)];
+            if (l > 0) return r;
+            return fmaf(th[nd.fg0 + k] * c, r, th[nd.fb0 + k] * raw[g.gW[0] + tcslab_idx(kl, n, kl)]);
+        };
         for (long long i = t0; i < (long long)kl * nl; i += stride) {
             int n = (int)(i % nl);
-            grad[nd.fW[l] + i] = raw[g.gW[l] + tcslab_idx((int)(i / nl), n, kl)] * (th[nd.fg[l] + n] * c);
+            grad[nd.fW[l] + i] = G((int)(i / nl), n) * (th[nd.fg[l] + n] * c);
         }
         for (long long n = t0; n < nl; n += stride) {
             float s = 0.f;
-            for (int k = 0; k < kl; ++k) s = fmaf(th[nd.fW[l] + (long long)k * nl + n], raw[g.gW[l] + tcslab_idx(k, n, kl)], s);
+            for (int k = 0; k < kl; ++k) s = fmaf(th[nd.fW[l] + (long long)k * nl + n], G(k, (int)n), s);
             const float C = raw[g.gW[l] + tcslab_idx(kl, n, kl)];
             if (l == t.L) {
                 s = s + th[nd.fbias + n] * C;
