@@ -291,12 +291,12 @@ __device__ __forceinline__ void critic_tc_body(const TcArgs& a, const TcSmem& S,
                 if (first) {                                            // one cyclic schedule serves every item
                     ctrl_flush(C);
                     sched_add_fwd(C, nG, a.imgG, nG.L - 1);
-                    sched_add_bwd(C, nG, a.imgG);
+                    sched_add_bwd(C, nG, a.imgG, false);
                     ctrl_sched_ready(C);
                 }
                 for (int t = t0; t < t1; ++t) {
                     ctrl_net_forward(C, nG, nG.L - 1);
-                    ctrl_net_backward(C, nG, true, copies, true);
+                    ctrl_net_backward(C, nG, true, copies, true, false);
                 }
             } else if (is_help) {
                 Masks mk;
@@ -314,7 +314,7 @@ __device__ __forceinline__ void critic_tc_body(const TcArgs& a, const TcSmem& S,
                     KLOOP(k, d) { xt[k] = __ldcs(&tr[k * TC_PATHS + row]); cot[k] = __ldcs(&tr[(sr + k) * TC_PATHS + row]) * rg; }
                     float none[1];
                     own_net_forward_keep(P, nG, S.vecG, xt, none, copies, row, true, hg);
-                    own_net_backward(P, nG, cot, true, S.dz, row, dy0, mxbuf, dexp, true, hg);
+                    own_net_backward_nody0(P, nG, cot, S.dz, row, mxbuf, dexp, true, hg);
                 }
             }
             first = false;
@@ -418,10 +418,10 @@ __device__ __forceinline__ void critic_tc_body(const TcArgs& a, const TcSmem& S,
                 for (int i = 0; i < 3; ++i) ctrl_net_forward(C, nV, nV.L);
             } else {
                 sched_add_fwd(C, nV, a.imgV, nV.L);                       // V(x_0), forward only
-                for (int i = 0; i < 3; ++i) { sched_add_fwd(C, nV, a.imgV, nV.L); sched_add_bwd(C, nV, a.imgV); }
+                for (int i = 0; i < 3; ++i) { sched_add_fwd(C, nV, a.imgV, nV.L); sched_add_bwd(C, nV, a.imgV, false); }
                 ctrl_sched_ready(C);
                 ctrl_net_forward(C, nV, nV.L);
-                for (int i = 0; i < 3; ++i) { ctrl_net_forward(C, nV, nV.L); ctrl_net_backward(C, nV, true, copies, false); }
+                for (int i = 0; i < 3; ++i) { ctrl_net_forward(C, nV, nV.L); ctrl_net_backward(C, nV, true, copies, false, false); }
             }
         } else if (is_help) {
             if (!need_grad) {
@@ -450,14 +450,14 @@ __device__ __forceinline__ void critic_tc_body(const TcArgs& a, const TcSmem& S,
                 const float delta = v0[0] - y - vN[0] * disc;
                 rhog = valid ? rho_grad(delta, 50.f) * scale : 0.f;
                 cot[0] = -rhog * disc;
-                own_net_backward(P, nV, cot, true, S.dz, row, dy0, mxbuf, dexp, false, hv);
+                own_net_backward_nody0(P, nV, cot, S.dz, row, mxbuf, dexp, false, hv);
                 own_net_forward_keep(P, nV, S.vecV, x0v, v0, copies, row, false, hv);
                 cot[0] = rhog;
-                own_net_backward(P, nV, cot, true, S.dz, row, dy0, mxbuf, dexp, false, hv);
+                own_net_backward_nody0(P, nV, cot, S.dz, row, mxbuf, dexp, false, hv);
                 own_net_forward_keep(P, nV, S.vecV, xbv, vb, copies, row, false, hv);
                 const float dbb = vb[0] - eq_Z<float, DP, EQN, MV>(E, xbv, 1, 0);
                 cot[0] = valid ? rho_grad(dbb, 50.f) * scale : 0.f;
-                own_net_backward(P, nV, cot, true, S.dz, row, dy0, mxbuf, dexp, false, hv);
+                own_net_backward_nody0(P, nV, cot, S.dz, row, mxbuf, dexp, false, hv);
             }
             const float delta = v0[0] - y - vN[0] * disc;                         // solver.py:189
             const float db = vb[0] - eq_Z<float, DP, EQN, MV>(E, xbv, 1, 0);                          // solver.py:190
@@ -478,11 +478,11 @@ __device__ __forceinline__ void critic_tc_body(const TcArgs& a, const TcSmem& S,
             if (is_ctrl) {
                 ctrl_flush(C);
                 sched_add_fwd(C, nG, a.imgG, nG.L - 1);
-                sched_add_bwd(C, nG, a.imgG);
+                sched_add_bwd(C, nG, a.imgG, false);
                 ctrl_sched_ready(C);
                 for (int t = 0; t < tlive; ++t) {
                     ctrl_net_forward(C, nG, nG.L - 1);
-                    ctrl_net_backward(C, nG, true, copies, true);
+                    ctrl_net_backward(C, nG, true, copies, true, false);
                 }
             } else if (is_help) {
                 Masks mk;
@@ -499,7 +499,7 @@ __device__ __forceinline__ void critic_tc_body(const TcArgs& a, const TcSmem& S,
                     KLOOP(k, d) { xt[k] = __ldcs(&tr[k * TC_PATHS + row]); cot[k] = __ldcs(&tr[(sr + k) * TC_PATHS + row]) * rhog; }
                     float none[1];
                     own_net_forward_keep(P, nG, S.vecG, xt, none, copies, row, true, hg);
-                    own_net_backward(P, nG, cot, true, S.dz, row, dy0, mxbuf, dexp, true, hg);
+                    own_net_backward_nody0(P, nG, cot, S.dz, row, mxbuf, dexp, true, hg);
                 }
             }
         }
@@ -653,7 +653,7 @@ __device__ __forceinline__ void actor_tc_body(const TcArgs& a, const TcSmem& S, 
                 if (need_grad) sched_add_bwd(C, nV, a.imgV);
                 ctrl_sched_ready(C);
                 ctrl_net_forward(C, nV, nV.L);
-                if (need_grad) ctrl_net_backward(C, nV, false, nullptr, false);
+                if (need_grad) ctrl_net_backward(C, nV, false, nullptr, false, true);
             }
         } else if (is_help) {
             if (!cheat_v) {
@@ -709,7 +709,7 @@ __device__ __forceinline__ void actor_tc_body(const TcArgs& a, const TcSmem& S, 
             if (!any) continue;
             if (is_ctrl) {
                 ctrl_net_forward(C, nA, nA.L);
-                ctrl_net_backward(C, nA, true, copies, false);
+                ctrl_net_backward(C, nA, true, copies, false, true);
             } else if (is_help) {
                 Masks mk;
                 help_forward_keep(P, nA, S.vecA, mk, copies, S.act, row, false);

@@ -767,8 +767,8 @@ static __global__ void tc_finalize_grad_kernel(TcNet t, TcSlab g, const float* _
 }
 
 // ---- control thread ----------------------------------------------------------------------------------
-__device__ __forceinline__ void sched_add_bwd(Ctrl& c, const TcNet& t, const unsigned char* img) {
-    for (int l = t.L; l >= 0; --l) sched_add_op(c.sch, img + t.ly[l].img_b, t.ly[l].N16 / 16, t.ly[l].K16, (int)c.slot_bytes);
+__device__ __forceinline__ void sched_add_bwd(Ctrl& c, const TcNet& t, const unsigned char* img, bool need_dy0 = true) {
+    for (int l = t.L; l >= (need_dy0 ? 0 : 1); --l) sched_add_op(c.sch, img + t.ly[l].img_b, t.ly[l].N16 / 16, t.ly[l].K16, (int)c.slot_bytes);
 }
 
 // global copy scratch -> ACT (bulk copy; waits until it has landed)
@@ -787,7 +787,8 @@ __device__ __forceinline__ void ctrl_act_wait(Ctrl& c) {
 
 // D[acc] (rows = features 128*blk .. of ACT, cols = N16 features of DZ) = ACT^T DZ over the 128 paths.  The accumulator
 // is the region the next dX product will write (the other one holds the dz planes that product reads).
-__device__ __forceinline__ void ctrl_gemm_dw(Ctrl& c, int blk_, int N16_, int in_kind_) {
+__device__ __forceinline__ void ctrl_gemm_dw(Ctrl& c, int blk_, int N16_, int in_kind_, bool also_fin_ = false) {
+    const bool also_fin = warp_uniform(also_fin_ ? 1u : 0u) != 0;
     const int blk = (int)warp_uniform((uint32_t)blk_), N16 = (int)warp_uniform((uint32_t)N16_), in_kind = (int)warp_uniform((uint32_t)in_kind_);
     const uint32_t idesc = idesc_f16(128, N16, 1, 1);                   // FP16 operand images
     uint32_t sync = warp_uniform(c.sync);
@@ -805,6 +806,7 @@ __device__ __forceinline__ void ctrl_gemm_dw(Ctrl& c, int blk_, int N16_, int in
             mma_ss(dcol, ad, bd, idesc, s > 0);
         }
         tc_commit_u32(bars0 + 8 * BAR_ACC);
+        if (also_fin) tc_commit_u32(bars0 + 8 * BAR_FIN);
     }
     c.sync = sync;
     ++c.op_count;
@@ -814,19 +816,29 @@ __device__ __forceinline__ void ctrl_gemm_dw(Ctrl& c, int blk_, int N16_, int in
 // copies: per-CTA global scratch holding the FP16 copies of a_0..a_{L-1} (a_L is already in ACT);
 // skip_last: the forward stopped at the last hidden layer, whose epilogue published on a_help (the output cotangent
 // comes from the owners either way).
-static __device__ __noinline__ void ctrl_net_backward(Ctrl& c, const TcNet& t, bool need_w, const unsigned char* copies, bool skip_last) {
+// need_dy0 = false (the critic's networks: nothing consumes the cotangent of their input): the product dX of layer 0 is
+// left out; the owners are told when the last dW product is done (from then on the copy of a_0 and the plane region are
+// theirs again) and the control warp itself waits for the last drain.
+static __device__ __noinline__ void ctrl_net_backward(Ctrl& c, const TcNet& t, bool need_w, const unsigned char* copies, bool skip_last, bool need_dy0) {
     for (int l = t.L; l >= 0; --l) {
         if (need_w) {
             if (l < t.L) ctrl_act_wait(c);
             const int nblk = (t.ly[l].kl + 1 + 127) >> 7;
             for (int b = 0; b < nblk; ++b)
-                ctrl_gemm_dw(c, b, t.ly[l].N16, (l == t.L && b == 0) ? (skip_last ? IN_BOTH : IN_OWN) : IN_HELP);
+                ctrl_gemm_dw(c, b, t.ly[l].N16, (l == t.L && b == 0) ? (skip_last ? IN_BOTH : IN_OWN) : IN_HELP,
+                             !need_dy0 && l == 0 && b == nblk - 1);
             if (l > 0) {
                 TC_STAT(const long long t0 = clock64();)
                 mbar_wait(&c.bars[BAR_ACC], (c.op_count - 1) & 1);     // the MMAs reading ACT are done
                 TC_STAT(c.t_accw += clock64() - t0;)
                 ctrl_act_load(c, copies + tc_copy_off(t, l - 1), (uint32_t)(TC_PATHS * t.ly[l - 1].K16 * 2));
             }
+        }
+        if (l == 0 && !need_dy0) {                                       // (need_w holds: a backward without either would be empty)
+            uint32_t sync = warp_uniform(c.sync);
+            ctrl_wait_inputs(warp_uniform(smem_u32(c.bars)), sync, IN_HELP);         // the last drain
+            c.sync = sync;
+            break;
         }
         // dA_l = dz_l x (W_l gamma c)^T; its planes come chunk by chunk only in a chain without dW products; dy0 (l = 0) goes
         // to the owners
@@ -1024,6 +1036,15 @@ __device__ __forceinline__ void own_net_backward(PathCtx& p, const TcNet& t, con
     own_put_dz(p, t, dout, need_w ? dzimg : nullptr, row, mxbuf, dexp_out, skip_last);
     if (TC_COMBINED) help_backward(p, t, *h.g, *h.mk, need_w, h.slab, dzimg, row, dexp_out);
     own_get_dy0(p, t, dy0);
+}
+// the same when nothing consumes dy0 (the critic's networks): wait until the last dW product is done
+template <int NO>
+__device__ __forceinline__ void own_net_backward_nody0(PathCtx& p, const TcNet& t, const float (&dout)[NO], unsigned char* dzimg, int row,
+                                                       uint32_t* mxbuf, volatile int* dexp_out, bool skip_last, const HelpArgs& h) {
+    own_put_dz(p, t, dout, dzimg, row, mxbuf, dexp_out, skip_last);
+    if (TC_COMBINED) help_backward(p, t, *h.g, *h.mk, true, h.slab, dzimg, row, dexp_out);
+    own_wait_fin(p);
+    own_swaps(p, t.L);
 }
 
 }  // namespace tc
