@@ -600,7 +600,9 @@ __device__ __forceinline__ void actor_tc_body(const TcArgs& a, const TcSmem& S, 
                 if (!cheat) help_forward(P, nA, S.vecA);
             } else {
                 if (!cheat) own_put_y0(P, nA, S.vecA, x, nullptr, 0);
+                if (TC_COMBINED && !cheat) help_forward(P, nA, S.vecA, 0, 1);          // (the first layer's product is short)
                 path_dw(a, gp, valid, t, dwv);
+                if (TC_COMBINED && !cheat) help_forward(P, nA, S.vecA, 1, 2);
                 float dt, sqdt, xn; int dtg;
                 fwd_dt<float, DP, EQN, MV>(E, x, flag, 1, 0, dt, sqdt, xn, dtg);
                 float* tr = traj + (size_t)t * trs * TC_PATHS;
@@ -609,7 +611,7 @@ __device__ __forceinline__ void actor_tc_body(const TcArgs& a, const TcSmem& S, 
                 if (cheat) {
                     eq_u_true<float, DP, EQN, MV>(E, x, u, 1, 0);
                 } else {
-                    if (TC_COMBINED) help_forward(P, nA, S.vecA);
+                    if (TC_COMBINED) help_forward(P, nA, S.vecA, 2);
                     own_last(P, nA, S.vecA, raw);
                     if (nA.ekn_head) ekn_head_fwd<float, DP, EQN, MV>(raw, u, nA.mctrl, 1, 0);
                     else KLOOP(j, m) u[j] = raw[j];

@@ -601,12 +601,13 @@ __device__ __forceinline__ void help_epi_hidden(PathCtx& p, const float* gcbb, i
     });
     TC_STAT(p.t_hid += clock64() - th0;)
 }
-// the hidden-layer epilogues of one forward-only evaluation (helpers)
-static __device__ __noinline__ uint32_t help_forward_(PathArg p, const TcNet& t, const float* vec) {
-    for (int l = 0; l < t.L; ++l) help_epi_hidden(p, vec + t.ly[l].vec, t.ly[l].N16);
+// the hidden-layer epilogues l0 .. l1-1 of one forward-only evaluation (helpers; in combined mode the owner places its own
+// per-path arithmetic between two ranges: it then runs while the tensor pipe works on the layer just published)
+static __device__ __noinline__ uint32_t help_forward_(PathArg p, const TcNet& t, const float* vec, int l0, int l1) {
+    for (int l = l0; l < l1 && l < t.L; ++l) help_epi_hidden(p, vec + t.ly[l].vec, t.ly[l].N16);
     return p.sync;
 }
-__device__ __forceinline__ void help_forward(PathCtx& p, const TcNet& t, const float* vec) { p.sync = help_forward_(p, t, vec); }
+__device__ __forceinline__ void help_forward(PathCtx& p, const TcNet& t, const float* vec, int l0 = 0, int l1 = MAXLIN) { p.sync = help_forward_(p, t, vec, l0, l1); }
 
 // ---- owners -------------------------------------------------------------------------------------------------------
 // a network input / output cotangent is in place: one arrival per owner warp on a_own
