@@ -155,6 +155,14 @@ def test_tensor_schedule_bit_exact_under_cheat_control(key):
     b = tn.critic_step(None, None, None, x0, dw, None, N, T, want=want, **kw2)
     for k in want:
         assert torch.equal(a[k], b[k]), f"{key}: propagate {k} differs between impl=tensor and impl=exact under cheat_control"
+    # ... and both equal the INDEPENDENT float32 restatement of the reference's scheme (oracle/ref_schedule_f32.py, NumPy),
+    # bit for bit: states, step sizes, coef, exit index
+    from oracle.ref_schedule_f32 import ScheduleF32
+    o = ScheduleF32(cfg["eqn_config"], cfg["train_config"]["scheme"], T, N)
+    xs_o, dt_o, cf_o, ex_o = o.propagate(x0.cpu().numpy(), dw.cpu().numpy())
+    assert np.array_equal(b["coef"].cpu().numpy(), cf_o) and np.array_equal(b["exit_index"].cpu().numpy(), ex_o)
+    assert np.array_equal(b["dt"].cpu().numpy().view(np.uint32), dt_o.view(np.uint32)), f"{key}: dt bits differ from the float32 oracle"
+    assert np.array_equal(b["x_smp"].cpu().numpy().view(np.uint32), xs_o.view(np.uint32)), f"{key}: state bits differ from the float32 oracle"
     ya = ex.actor_step(None, thd["critic"], x0, None, N, T, want=want + ("delta",), **kw)
     yb = tn.actor_step(None, thd["critic"], x0, None, N, T, want=want + ("delta",), **kw)
     for k in want:

@@ -147,3 +147,39 @@ def test_ekn_head(hh):
         (g,) = torch.autograd.grad(torch.sum(ut * torch.tensor(ubar)), [yt])
         np.testing.assert_allclose(u, ut.detach().numpy(), rtol=1e-13)
         np.testing.assert_allclose(ybar, g.numpy(), rtol=1e-11, atol=1e-14)
+
+
+# ------------------------------------------------------------------------------------------------
+# FLOAT32: the header (g++ build, the very code the CUDA kernels run per path) against the independent NumPy float32
+# restatement of the reference's schemes (oracle/ref_schedule_f32.py) -- bit for bit
+@pytest.mark.parametrize("name", list(EQNS))
+@pytest.mark.parametrize("scheme,T", [("naive", 0.3), ("adaptive", 1.5), ("adaptive", 0.12)])
+def test_f32_schedule_header_vs_numpy_oracle(hh, name, scheme, T):
+    from oracle.ref_schedule_f32 import ScheduleF32
+    N, B = 30, 200
+    d, m = (20, 20) if name in ("LQR", "LQR_var", "ekn") else (20, 10)          # the BASELINE dimension
+    e, c = make_cfg(name, scheme, d, m)
+    c.dtype = 0
+    rng = np.random.RandomState(17)
+    g = rng.standard_normal((B, d))
+    sc = 0.6 if scheme == "naive" else 1.0          # (naive: paths that start near the boundary at d=20 leave at once)
+    x0 = (sc * rng.uniform(0, 1, (B, 1)) ** (1.0 / d) * g / np.sqrt((g ** 2).sum(1, keepdims=True))).astype(np.float32)
+    dw = rng.standard_normal((B, d, N)).astype(np.float32)
+    o = ScheduleF32(e, scheme, T, N)
+    xs_o, dt_o, cf_o, ex_o = o.propagate(x0, dw)
+    A, b = np.zeros((m, d), np.float32), np.zeros(m, np.float32)
+    P = lambda a: a.ctypes.data_as(C.c_void_p)
+    for i in range(B):
+        xs, dts, cfs, y = np.zeros((d, N + 1), np.float32), np.zeros(N, np.float32), np.zeros(N, np.float32), np.zeros(1, np.float32)
+        hh.hh_run_path_f32(C.byref(c), N, C.c_double(T), P(A), P(b), P(np.ascontiguousarray(x0[i])), P(np.ascontiguousarray(dw[i])),
+                           1, C.c_float(1.0), P(xs), P(dts), P(cfs), P(y), None, None)
+        assert np.array_equal(cfs, cf_o[i]), f"path {i}: coef differs"
+        assert np.array_equal(dts.view(np.uint32), dt_o[i].view(np.uint32)), f"path {i}: dt bits differ"
+        assert np.array_equal(xs.view(np.uint32), xs_o[i].view(np.uint32)), f"path {i}: x bits differ"
+    assert 0.003 < cf_o.mean() < 0.9999 and (dt_o != dt_o[0, 0]).any() == (scheme == "adaptive")
+    # and the float32 schedule shadows the float64 oracle's: same exit pattern except within rounding of the boundary
+    eqn = RE.make_ref_equation(e)
+    x64, dw64 = torch.tensor(x0.astype(np.float64)), torch.tensor(dw.astype(np.float64))
+    prop = eqn.propagate_naive if scheme == "naive" else eqn.propagate_adaptive
+    _, _, coef64 = prop(x64, dw64, lambda x: eqn.u_true(x), T, N)
+    assert (coef64.numpy() == cf_o).all(1).mean() > 0.97
