@@ -403,29 +403,51 @@ static int tc_pack(dpb_handle* h, const tc::TcNet& t, const void* theta, char* w
     return DPB_OK;
 }
 
-// the <24, EQN> instantiations keep the per-path vectors in registers: dim and control_dim + 1 must fit in 24 and the
-// equation must index its state statically (VDP's cyclic neighbours do only for a compile-time control_dim: the shipped
-// 2, 5, 10 are instantiated); DPB_TC_GENERIC=1 forces the generic kernels
-static bool tc_specialised(const dpb_handle* h) {
+// The <DP, EQN, MV> instantiations keep the per-path vectors in registers (DP entries each, every loop unrolled, the
+// equation folded in at compile time); the fewer entries, the fewer registers the owner threads spill: DP = 12 serves the
+// d <= 12 configs (d5 / d10, vdp_d4 / vdp_d10), DP = 20 the d = 20 ones (LQR, LQR_var, vdp_d20), DP = 24 ekn (its actor has
+// control_dim + 1 outputs) up to d = 23.  VDP's cyclic neighbours are static only for a compile-time control_dim: the shipped
+// 2, 5, 10 are instantiated.  Everything else runs the generic run-time-loop kernels; DPB_TC_GENERIC=1 forces them.
+enum { TCK_GENERIC = 0, TCK_LQR, TCK_LQR12, TCK_LQRVAR, TCK_LQRVAR12, TCK_EKN, TCK_EKN12, TCK_VDP2, TCK_VDP5, TCK_VDP10 };
+static int tc_pick(const dpb_handle* h) {
     static const bool force_generic = getenv("DPB_TC_GENERIC") != nullptr;
-    return !force_generic && h->cfg.dim <= 23 && h->cfg.control_dim + 1 <= 24;       // VDP: instantiated for control_dim 2, 5, 10
-}
-
-static tc::TcKernelFn tc_pick_critic(const dpb_handle* h) {
-    tc::TcKernelFn kern = tc::tc_get_critic_generic();
-    if (tc_specialised(h)) {
-        switch (h->cfg.eqn) {
-        case DPB_EQN_LQR: kern = tc::tc_get_critic_lqr(); break;
-        case DPB_EQN_EKN: kern = tc::tc_get_critic_ekn(); break;
-        case DPB_EQN_LQR_VAR: kern = tc::tc_get_critic_lqrvar(); break;
-        case DPB_EQN_VDP:
-            if (h->cfg.control_dim == 2) kern = tc::tc_get_critic_vdp2();
-            else if (h->cfg.control_dim == 5) kern = tc::tc_get_critic_vdp5();
-            else if (h->cfg.control_dim == 10) kern = tc::tc_get_critic_vdp10();
-            break;
-        }
+    if (force_generic) return TCK_GENERIC;
+    const int d = h->cfg.dim, m = h->cfg.control_dim;
+    switch (h->cfg.eqn) {
+    case DPB_EQN_LQR: return d <= 12 ? TCK_LQR12 : (d <= 20 ? TCK_LQR : TCK_GENERIC);
+    case DPB_EQN_LQR_VAR: return d <= 12 ? TCK_LQRVAR12 : (d <= 20 ? TCK_LQRVAR : TCK_GENERIC);
+    case DPB_EQN_EKN: return m + 1 <= 12 ? TCK_EKN12 : (m + 1 <= 24 && d <= 23 ? TCK_EKN : TCK_GENERIC);
+    case DPB_EQN_VDP: return (m == 2 && d <= 12) ? TCK_VDP2 : (m == 5 && d <= 12) ? TCK_VDP5 : (m == 10 && d <= 20) ? TCK_VDP10 : TCK_GENERIC;
     }
-    return kern;
+    return TCK_GENERIC;
+}
+static tc::TcKernelFn tc_pick_critic(const dpb_handle* h) {
+    switch (tc_pick(h)) {
+    case TCK_LQR: return tc::tc_get_critic_lqr();
+    case TCK_LQR12: return tc::tc_get_critic_lqr12();
+    case TCK_LQRVAR: return tc::tc_get_critic_lqrvar();
+    case TCK_LQRVAR12: return tc::tc_get_critic_lqrvar12();
+    case TCK_EKN: return tc::tc_get_critic_ekn();
+    case TCK_EKN12: return tc::tc_get_critic_ekn12();
+    case TCK_VDP2: return tc::tc_get_critic_vdp2();
+    case TCK_VDP5: return tc::tc_get_critic_vdp5();
+    case TCK_VDP10: return tc::tc_get_critic_vdp10();
+    }
+    return tc::tc_get_critic_generic();
+}
+static tc::TcKernelFn tc_pick_actor(const dpb_handle* h) {
+    switch (tc_pick(h)) {
+    case TCK_LQR: return tc::tc_get_actor_lqr();
+    case TCK_LQR12: return tc::tc_get_actor_lqr12();
+    case TCK_LQRVAR: return tc::tc_get_actor_lqrvar();
+    case TCK_LQRVAR12: return tc::tc_get_actor_lqrvar12();
+    case TCK_EKN: return tc::tc_get_actor_ekn();
+    case TCK_EKN12: return tc::tc_get_actor_ekn12();
+    case TCK_VDP2: return tc::tc_get_actor_vdp2();
+    case TCK_VDP5: return tc::tc_get_actor_vdp5();
+    case TCK_VDP10: return tc::tc_get_actor_vdp10();
+    }
+    return tc::tc_get_actor_generic();
 }
 
 // ring geometry for a launch: slots of `slot_bytes` (largest chunk of the images used) in what is left of 227 KB
@@ -616,19 +638,7 @@ static int actor_step_tc(dpb_handle* h, const void* thA, const void* thV, const 
         DPB_CUDA(h, cudaMemsetAsync(ws + L.slabs, 0, (size_t)L.nslab * h->sA.gtotal * sizeof(float), st));
     }
     const size_t smem = tc::tc_smem_bytes(h->tA.vec_floats, h->tV.vec_floats, h->tG.vec_floats, a.actdz_bytes, a.nslot, a.slot_bytes);
-    tc::TcKernelFn kern = tc::tc_get_actor_generic();
-    if (tc_specialised(h)) {
-        switch (h->cfg.eqn) {
-        case DPB_EQN_LQR: kern = tc::tc_get_actor_lqr(); break;
-        case DPB_EQN_EKN: kern = tc::tc_get_actor_ekn(); break;
-        case DPB_EQN_LQR_VAR: kern = tc::tc_get_actor_lqrvar(); break;
-        case DPB_EQN_VDP:
-            if (h->cfg.control_dim == 2) kern = tc::tc_get_actor_vdp2();
-            else if (h->cfg.control_dim == 5) kern = tc::tc_get_actor_vdp5();
-            else if (h->cfg.control_dim == 10) kern = tc::tc_get_actor_vdp10();
-            break;
-        }
-    }
+    tc::TcKernelFn kern = tc_pick_actor(h);
     DPB_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     DPB_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, (int)((smem + 1024) * 100 / (228 * 1024) + 1 > 100 ? 100 : (smem + 1024) * 100 / (228 * 1024) + 1)));
     if (tc_lifetime_sort_wanted(h, B_local, flags)) {

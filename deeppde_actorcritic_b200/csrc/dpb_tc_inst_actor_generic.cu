@@ -1,5 +1,5 @@
 // actor_tc_kernel<0, -1, 0> (see dpb_tc_inst.cuh)
-// helper groups of the actor kernel (dpb_tc_nets.cuh)
+// helper groups of the actor kernel: 0 = the owners do the helpers' work themselves (dpb_tc_nets.cuh)
 #ifndef DPB_TC_NGRP
 #define DPB_TC_NGRP 0
 #endif

@@ -1,11 +1,11 @@
-// actor_tc_kernel<20, EQ_LQRVAR, 0> (see dpb_tc_inst.cuh)
+// actor_tc_kernel<12, EQ_LQRVAR, 0> (see dpb_tc_inst.cuh)
 // helper groups of the actor kernel: 0 = the owners do the helpers' work themselves (dpb_tc_nets.cuh)
 #ifndef DPB_TC_NGRP
 #define DPB_TC_NGRP 0
 #endif
-#define DPB_INST_NAME actor_lqrvar
+#define DPB_INST_NAME actor_lqrvar12
 #define DPB_INST_KERNEL actor_tc_kernel
-#define DPB_INST_DP 20
+#define DPB_INST_DP 12
 #define DPB_INST_EQN EQ_LQRVAR
 #define DPB_INST_MV 0
 #include "dpb_tc_inst.cuh"

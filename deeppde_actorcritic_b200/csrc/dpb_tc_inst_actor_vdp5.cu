@@ -1,11 +1,11 @@
-// actor_tc_kernel<24, EQ_VDP, 5> (see dpb_tc_inst.cuh)
-// helper groups of the actor kernel (dpb_tc_nets.cuh)
+// actor_tc_kernel<12, EQ_VDP, 5> (see dpb_tc_inst.cuh)
+// helper groups of the actor kernel: 0 = the owners do the helpers' work themselves (dpb_tc_nets.cuh)
 #ifndef DPB_TC_NGRP
 #define DPB_TC_NGRP 0
 #endif
 #define DPB_INST_NAME actor_vdp5
 #define DPB_INST_KERNEL actor_tc_kernel
-#define DPB_INST_DP 24
+#define DPB_INST_DP 12
 #define DPB_INST_EQN EQ_VDP
 #define DPB_INST_MV 5
 #include "dpb_tc_inst.cuh"

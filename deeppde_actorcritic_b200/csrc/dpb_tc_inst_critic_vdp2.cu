@@ -1,7 +1,7 @@
-// critic_tc_kernel<24, EQ_VDP, 2> (see dpb_tc_inst.cuh)
+// critic_tc_kernel<12, EQ_VDP, 2> (see dpb_tc_inst.cuh)
 #define DPB_INST_NAME critic_vdp2
 #define DPB_INST_KERNEL critic_tc_kernel
-#define DPB_INST_DP 24
+#define DPB_INST_DP 12
 #define DPB_INST_EQN EQ_VDP
 #define DPB_INST_MV 2
 #include "dpb_tc_inst.cuh"

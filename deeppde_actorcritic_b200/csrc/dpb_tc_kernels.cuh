@@ -55,7 +55,7 @@ constexpr unsigned F_S2_DEFER = 0x100u, F_S2_ONLY = 0x200u;       // internal fl
 
 // the kernels are instantiated in their own translation units (dpb_tc_inst_*.cu)
 typedef void (*TcKernelFn)(const TcArgs);
-#define DPB_TC_FOR_INSTANCES(X) X(lqr) X(ekn) X(lqrvar) X(vdp2) X(vdp5) X(vdp10) X(generic)
+#define DPB_TC_FOR_INSTANCES(X) X(lqr) X(ekn) X(lqrvar) X(vdp2) X(vdp5) X(vdp10) X(lqr12) X(ekn12) X(lqrvar12) X(generic)
 #define DPB_TC_DECL_GETTERS(n) TcKernelFn tc_get_critic_##n(); TcKernelFn tc_get_actor_##n();
 DPB_TC_FOR_INSTANCES(DPB_TC_DECL_GETTERS)
 
