@@ -122,7 +122,7 @@ static Layout make_layout(const dpb_handle* h, long long B_local, int N) {
 
 extern "C" {
 
-const char* dpb_version(void) { return "deeppde_b200 0.1 (exact CUDA-core path, sm_100a)"; }
+const char* dpb_version(void) { return "deeppde_b200 0.2 (sm_100a: tcgen05 tensor path + exact CUDA-core path)"; }
 
 const char* dpb_last_error(const dpb_handle* h) { return h ? h->err.c_str() : g_err.c_str(); }
 
