@@ -52,7 +52,8 @@ class dpb_path_outputs(C.Structure):
 
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdeeppde_b200.so")
+# (DPB_LIB_PATH: an experiment build of the same library, e.g. another helper-group layout -- tools/variant_builds.sh)
+LIB_PATH = os.environ.get("DPB_LIB_PATH") or os.path.join(_HERE, "libdeeppde_b200.so")
 
 # name -> (restype, argtypes); every symbol include/deeppde_b200.h declares
 _P, _I64, _I32, _U32, _U64, _D = C.c_void_p, C.c_int64, C.c_int32, C.c_uint32, C.c_uint64, C.c_double
@@ -86,6 +87,7 @@ SYMBOLS = {
     "dpb_tc_handshake_cycles": (C.c_int, [_P, C.c_int]),
     "dpb_tc_epilogue_cycles": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int]),
     "dpb_tc_stats": (C.c_int, [_P, _P, _I64, _I32, _P]),
+    "dpb_tc_trace": (C.c_int, [_P, _P, _I64, _I32, _P]),
     "dpb_tc_mma_cycles": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int]),
 }
 

@@ -22,6 +22,7 @@ struct dpb_handle {
     tc::TcSlab sA, sV, sG;
     int tc_maxw16;                  // widest padded layer extent of the three networks
     int num_sms;
+    int img_rep;                    // copies of every operand image of the tensor path (experiment knob DPB_TC_IMG_REP, default 1)
     int max_smem;
     int sr, hrows, nhb;
     long long launches;
@@ -66,7 +67,7 @@ struct Layout {
     int grid;
     int nslab;              // gradient slabs: one per CTA on the exact path (deterministic), <= 16 shared ones on the tensor path
     size_t pkA, pkV, pkG, loss_part, loss_out, scratch, slabs, raw, total;
-    size_t imgA, imgV, imgG, vecA, vecV, vecG, copies, stats;      // tensor path: operand images, vector blocks, activation copies, counters
+    size_t imgA, imgV, imgG, vecA, vecV, vecG, copies, stats, trace;      // tensor path: operand images, vector blocks, activation copies, counters
     size_t life_nacc, life_perm, life_hist;                        // tensor path, naive scheme: lifetime sort (exit counts, permutation, bins)
     size_t s2_rhog, s2_tlive;                                      // tensor path, small batches: hand-over to the second-sweep launch
     long long scratch_per_cta, copies_per_cta;
@@ -83,9 +84,12 @@ static Layout make_layout(const dpb_handle* h, long long B_local, int N) {
     size_t o = 0;
     L.imgA = L.imgV = L.imgG = L.vecA = L.vecV = L.vecG = 0;
     if (tensor) {
-        L.imgA = o; o += a256(h->tA.img_bytes);
-        L.imgV = o; o += a256(h->tV.img_bytes);
-        L.imgG = o; o += a256(h->tG.img_bytes);
+        // img_rep copies of every operand image (experiment: all CTAs stream the same few hundred KB of weights, roughly in
+        // step -- would one copy keep a handful of L2 slices busy while the others idle?  Measured: 1, 4, 8, 16 copies run
+        // the same 2^17-path step to 0.1 %, so the weight stream is not bound by L2 slices; the default stays 1)
+        L.imgA = o; o += (size_t)h->img_rep * a256(h->tA.img_bytes);
+        L.imgV = o; o += (size_t)h->img_rep * a256(h->tV.img_bytes);
+        L.imgG = o; o += (size_t)h->img_rep * a256(h->tG.img_bytes);
         L.vecA = o; o += a256((size_t)h->tA.vec_floats * 4);
         L.vecV = o; o += a256((size_t)h->tV.vec_floats * 4);
         L.vecG = o; o += a256((size_t)h->tG.vec_floats * 4);
@@ -97,7 +101,7 @@ static Layout make_layout(const dpb_handle* h, long long B_local, int N) {
     L.loss_out = o; o += 256;
     L.scratch_per_cta = (long long)N * (2 * h->sr + A_NSCAL) * P;
     L.scratch = o; o += a256((size_t)L.grid * L.scratch_per_cta * es);
-    L.copies = 0; L.copies_per_cta = 0; L.stats = 0; L.life_nacc = L.life_perm = L.life_hist = 0; L.s2_rhog = L.s2_tlive = 0;
+    L.copies = 0; L.copies_per_cta = 0; L.stats = 0; L.trace = 0; L.life_nacc = L.life_perm = L.life_hist = 0; L.s2_rhog = L.s2_tlive = 0;
     if (tensor) {
         long long cb = tc::tc_copy_bytes(h->tA);
         if (tc::tc_copy_bytes(h->tV) > cb) cb = tc::tc_copy_bytes(h->tV);
@@ -106,6 +110,7 @@ static Layout make_layout(const dpb_handle* h, long long B_local, int N) {
         // (sized for every SM: the second-sweep launch of a small batch runs more CTAs than the batch has tiles)
         L.copies = o; o += a256((size_t)h->num_sms * L.copies_per_cta);
         L.stats = o; o += a256((size_t)h->num_sms * 16 * 8 + 64);       // + the tile counter of the dynamic tile scheduler
+        L.trace = o; o += a256((size_t)3 * tc::TC_TRACE_CAP * 8);        // event trace of CTA 0 (written by stats builds only)
         L.life_nacc = o; o += a256((size_t)B_local * 4);
         L.life_perm = o; o += a256((size_t)B_local * 4);
         L.life_hist = o; o += a256((size_t)(N + 2) * 4);
@@ -189,6 +194,8 @@ int dpb_create(dpb_handle** out, const dpb_config* cfg) {
         cudaGetLastError();
     }
     if (h->num_sms <= 0) h->num_sms = 148;                 // layout only; compute calls fail without a device
+    h->img_rep = 1;
+    if (const char* e = getenv("DPB_TC_IMG_REP")) { const int v = atoi(e); if (v >= 1 && v <= 64) h->img_rep = v; }
     const size_t need = (c.dtype == DPB_F64 ? carve_elems<double>(h->sr, h->hrows, h->nhb) * 8 : carve_elems<float>(h->sr, h->hrows, h->nhb) * 4);
     if (need > 227 * 1024) {
         delete h;
@@ -397,7 +404,8 @@ static int tc_pack(dpb_handle* h, const tc::TcNet& t, const void* theta, char* w
     for (int l = 0; l <= t.L; ++l) work += (long long)t.ly[l].K16 * t.ly[l].N16;
     int blocks = (int)((work + 255) / 256);
     if (blocks > 592) blocks = 592;
-    tc::tc_pack_kernel<<<blocks, 256, 0, st>>>(t, (const float*)theta, (unsigned char*)(ws + img), (float*)(ws + vec), (float)BN_C);
+    tc::tc_pack_kernel<<<blocks, 256, 0, st>>>(t, (const float*)theta, (unsigned char*)(ws + img), (float*)(ws + vec), (float)BN_C, h->img_rep,
+                                               (long long)a256(t.img_bytes));
     h->launches++;
     DPB_CUDA(h, cudaGetLastError());
     return DPB_OK;
@@ -462,7 +470,7 @@ static int tc_ring(dpb_handle* h, tc::TcArgs& a, bool grads) {
     // Five slots already keep the weight stream ahead of the MMAs; if that fits in 196 KB the SM's unified array is carved
     // 196 KB shared / 60 KB L1 instead of 228 / 28, which the path threads' local-memory traffic (register spills, relu
     // masks) feels: critic 68.0 -> 66.5 ms, actor 66.9 -> 65.6 ms at 2^17 paths (3 or 4 slots: slower again).
-    {
+    if (!getenv("DPB_TC_SMEM_MAX")) {                                   // (experiment knob: keep all 227 KB for the ring)
         const size_t cap = (size_t)196 * 1024 - 1024;
         if (fixed + 5 * (size_t)a.slot_bytes <= cap) { const int v = (int)((cap - fixed) / a.slot_bytes); if (v < a.nslot) a.nslot = v; }
     }
@@ -478,6 +486,8 @@ static void tc_fill(dpb_handle* h, tc::TcArgs& a, const Layout& L, char* ws, con
     a.nA = h->tA; a.nV = h->tV; a.nG = h->tG;
     a.gA = h->sA; a.gV = h->sV; a.gG = h->sG;
     a.imgA = (const unsigned char*)(ws + L.imgA); a.imgV = (const unsigned char*)(ws + L.imgV); a.imgG = (const unsigned char*)(ws + L.imgG);
+    a.img_rep = h->img_rep;
+    a.img_strideA = (long long)a256(h->tA.img_bytes); a.img_strideV = (long long)a256(h->tV.img_bytes); a.img_strideG = (long long)a256(h->tG.img_bytes);
     a.x0 = (const float*)in->x0; a.dw = (const float*)in->dw; a.xb = (const float*)in->x_bdry;
     a.dw_mode = in->dw_mode; a.seed = in->seed; a.stream = in->stream; a.stream_base = (const unsigned long long*)in->stream_base;
     a.B_local = B_local; a.path_offset = path_offset;
@@ -490,6 +500,11 @@ static void tc_fill(dpb_handle* h, tc::TcArgs& a, const Layout& L, char* ws, con
     a.copies_per_cta = L.copies_per_cta;
     a.stats = (long long*)(ws + L.stats);
     a.tile_counter = (int*)(ws + L.stats + (size_t)h->num_sms * 16 * 8);
+#ifdef DPB_TC_STATS
+    a.trace = (unsigned long long*)(ws + L.trace);
+#else
+    a.trace = nullptr;
+#endif
     a.nslab = L.nslab;
     a.sr = h->sr;
     if (outs) {
@@ -889,6 +904,17 @@ extern "C" int dpb_tc_stats(dpb_handle* h, const void* workspace, int64_t B_loca
     const Layout L = make_layout(h, B_local, N);
     DPB_CUDA(h, cudaMemcpy(out_host, (const char*)workspace + L.stats, 16 * 8, cudaMemcpyDeviceToHost));
     return DPB_OK;
+}
+
+extern "C" int dpb_tc_trace(dpb_handle* h, const void* workspace, int64_t B_local, int32_t N, uint64_t* out_host) {
+    if (!h || !workspace || !out_host || h->cfg.impl != DPB_IMPL_TENSOR) return fail(h, DPB_ERR_ARG, "dpb_tc_trace: tensor-path handle and workspace required");
+#ifndef DPB_TC_STATS
+    return fail(h, DPB_ERR_ARG, "dpb_tc_trace: the library was built without DPB_TC_STATS");
+#else
+    const Layout L = make_layout(h, B_local, N);
+    DPB_CUDA(h, cudaMemcpy(out_host, (const char*)workspace + L.trace, (size_t)3 * tc::TC_TRACE_CAP * 8, cudaMemcpyDeviceToHost));
+    return DPB_OK;
+#endif
 }
 
 extern "C" int dpb_err_metrics(dpb_handle* h, const void* truth, const void* approx, int64_t n, void* out3, void* stream) {

@@ -61,6 +61,12 @@ __device__ __forceinline__ void mbar_wait_u32(uint32_t addr, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) { mbar_wait_u32(smem_u32(bar), parity); }
 
 // one non-blocking probe of the phase with the given parity
+__device__ __forceinline__ bool mbar_test_u32(uint32_t addr, uint32_t parity) {         // non-blocking
+    uint32_t done;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+    return done != 0;
+}
 __device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity) {
     uint32_t done;
     asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
@@ -157,6 +163,40 @@ __device__ __forceinline__ void mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
                  "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
                  ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+// One contraction chunk of a bf16x3 product (ah*bh, ah*bl, al*bh into D) and the commit that releases its weight slot, then
+// wait until two mbarrier phases are complete (the next weight slot, the next operand chunk).  Both barriers are TESTED before
+// the MMAs are issued and the results are only looked at (by branches, which the assembler cannot move) after the commit: a
+// test has a latency of 80-250 cycles even when the phase is long complete, which the issue of the MMAs then hides.
+// Executed by the whole (converged) warp on warp-uniform operands; the elected lane issues the MMAs and the commit.
+__device__ __forceinline__ void mma_ts3_commit_wait2(uint32_t d_tmem, uint32_t ahi, uint32_t alo, uint64_t bhi, uint64_t blo, uint32_t idesc,
+                                                      uint32_t accumulate, uint32_t release_bar, uint32_t bar1, uint32_t parity1,
+                                                      uint32_t bar2, uint32_t parity2) {
+    asm volatile("{\n\t.reg .pred pe, pa, pt, pu, p1;\n\t"
+                 "mbarrier.test_wait.parity.shared::cta.b64 pt, [%8], %9;\n\t"
+                 "mbarrier.test_wait.parity.shared::cta.b64 pu, [%10], %11;\n\t"
+                 "elect.sync _|pe, 0xffffffff;\n\t"
+                 "setp.ne.b32 pa, %4, 0;\n\t"
+                 "setp.eq.b32 p1, %4, %4;\n\t"
+                 "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %5, %3, pa;\n\t"
+                 "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %6, %3, p1;\n\t"
+                 "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], [%2], %5, %3, p1;\n\t"
+                 "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%7];\n\t"
+                 "W1:\n\t"
+                 "@pt bra D1;\n\t"
+                 "mbarrier.try_wait.parity.shared::cta.b64 pt, [%8], %9;\n\t"
+                 "bra W1;\n\t"
+                 "D1:\n\t"
+                 "@pu bra D2;\n\t"
+                 "mbarrier.try_wait.parity.shared::cta.b64 pu, [%10], %11;\n\t"
+                 "bra D1;\n\t"
+                 "D2:\n\t"
+                 "tcgen05.fence::after_thread_sync;\n\t}"
+                 :
+                 : "r"(d_tmem), "r"(ahi), "r"(alo), "r"(idesc), "r"(accumulate), "l"(bhi), "l"(blo), "r"(release_bar), "r"(bar1), "r"(parity1),
+                   "r"(bar2), "r"(parity2)
+                 : "memory");
 }
 
 // ------------------------------------------------------------------------------ bf16 hi/lo split

@@ -19,6 +19,8 @@ struct TcArgs {
     Eq<float> eqf;                  // equation + scheme constants in the arithmetic type of the tensor path
     TcNet nA, nV, nG;
     const unsigned char *imgA, *imgV, *imgG;
+    int img_rep;                    // copies of each image, img_stride* bytes apart: CTA i streams copy i % img_rep
+    long long img_strideA, img_strideV, img_strideG;
     const float *vecA, *vecV, *vecG;
     const float *x0, *dw, *xb;
     int dw_mode;
@@ -41,6 +43,7 @@ struct TcArgs {
     float *o_x, *o_dt, *o_coef, *o_delta, *o_delta_b;
     int* o_exit;
     long long* stats;               // [grid][16] cycle counters (diagnostics), may be NULL
+    unsigned long long* trace;      // [3][TC_TRACE_CAP] event trace of CTA 0 (stats builds), may be NULL
     int* tile_counter;              // zeroed before the launch: CTAs take tile blockIdx.x first, then gridDim.x + counter++
     const int* perm;                // optional: slot i of the tiling works on local path perm[i] (naive scheme: paths sorted by
                                     // lifetime so that the tiles die as a whole; NULL: identity)
@@ -121,6 +124,7 @@ __device__ __forceinline__ uint32_t tc_setup(TcSmem& s, const TcArgs& a) {
         for (int i = 0; i < MAX_NSLOT; ++i) { mbar_init(&s.full[i], 1); mbar_init(&s.empty[i], 1); }
         mbar_init(&s.bars[BAR_ACC], 1);
         mbar_init(&s.bars[BAR_FIN], 1);
+        mbar_init(&s.bars[BAR_DW], 1);
         mbar_init(&s.bars[BAR_HELP], TC_EPI_WARPS);
         mbar_init(&s.bars[BAR_OWN], TC_OWN_THREADS / 32);
         mbar_init(&s.bars[BAR_CHUNK], TC_EPI_WARPS);                                    // chunk 0: every helper warp (see for_acc_chunks)
@@ -213,14 +217,17 @@ __device__ __forceinline__ void roles_init(Roles& r, const TcSmem& S, const TcAr
     r.row = tid & 127;
     Ctrl& C = r.C;
     C.ring = S.ring; C.full = S.full; C.empty = S.empty; C.bars = S.bars; C.sch = S.sch;
-    C.pc = S.pc; C.n_req = 0; C.n_consumed = 0; C.op_count = 0; C.sync = 0; C.tmem = warp_uniform(tmem); C.gen = 0;
+    C.pc = S.pc; C.n_req = 0; C.n_consumed = 0; C.op_count = 0; C.dw_count = 0; C.sync = 0; C.tmem = warp_uniform(tmem); C.gen = 0;
     C.act_full = S.act_full; C.act_count = 0; C.nslot = a.nslot; C.slot_bytes = a.slot_bytes; C.act = S.act; C.dz = S.dz;
     C.dexp = reinterpret_cast<volatile int*>(S.dzmax + 16);
     r.P.tl = tmem + ((uint32_t)((warp & 3) * 32) << 16);
-    r.P.grp = warp >= 4 ? ((warp - 4) >> 2) % TC_EGRP : 0;
+    r.P.grp = warp >= 4 ? (((warp - 4) >> 2) + (TC_COMBINED ? 1 : 0)) % TC_EGRP : 0;
     r.P.bars = smem_u32(S.bars); r.P.sync = 0; r.P.dexp = 0;
     TC_STAT(r.P.t_accw = 0; r.P.t_epi = 0; r.P.t_hid = 0; r.P.t_drain = 0; r.P.t_mark = clock64();)
     TC_STAT(C.t_aready = 0; C.t_issue = 0; C.t_accw = 0; C.t_dw_ready = 0; C.t_act = 0;)
+    TC_STAT(const bool tr0 = a.trace && blockIdx.x == 0;)
+    TC_STAT(r.P.tn = 0; r.P.tr = (tr0 && tid == 0) ? a.trace : ((tr0 && tid == 128 && TC_HELP_WARPS > 0) ? a.trace + TC_TRACE_CAP : nullptr);)
+    TC_STAT(C.tn = 0; C.tr = (tr0 && warp == TC_CTRL_WARP && (tid & 31) == 0) ? a.trace + 2 * TC_TRACE_CAP : nullptr;)
     C.n_ops = 0;
     C.mm_slot = 0; C.mm_use = 0;
 }
@@ -256,6 +263,11 @@ __device__ __forceinline__ void critic_tc_body(const TcArgs& a, const TcSmem& S,
     const TcSlab& gV = *S.gV;
     const TcSlab& gG = *S.gG;
     (void)gV; (void)gG;
+    const int rep = (int)(blockIdx.x % (unsigned)a.img_rep);
+    const unsigned char* imgA = a.imgA + rep * a.img_strideA;
+    const unsigned char* imgV = a.imgV + rep * a.img_strideV;
+    const unsigned char* imgG = a.imgG + rep * a.img_strideG;
+    (void)imgA; (void)imgV; (void)imgG;
     const int tid = threadIdx.x;
     const int row = R.row;
     const Eq<float>& E = a.eqf;                                   // kernel-parameter space: fields are constant-bank operands
@@ -290,8 +302,8 @@ __device__ __forceinline__ void critic_tc_body(const TcArgs& a, const TcSmem& S,
             if (is_ctrl) {
                 if (first) {                                            // one cyclic schedule serves every item
                     ctrl_flush(C);
-                    sched_add_fwd(C, nG, a.imgG, nG.L - 1);
-                    sched_add_bwd(C, nG, a.imgG, false);
+                    sched_add_fwd(C, nG, imgG, nG.L - 1);
+                    sched_add_bwd(C, nG, imgG, false);
                     ctrl_sched_ready(C);
                 }
                 for (int t = t0; t < t1; ++t) {
@@ -305,15 +317,23 @@ __device__ __forceinline__ void critic_tc_body(const TcArgs& a, const TcSmem& S,
                     help_backward(P, nG, gG, mk, true, gsG, S.dz, row, dexp);
                 }
             } else {
-                float xt[DPX], cot[DPX], dy0[DPX];
+                float xt[DPX], cot[DPX];
                 Masks mkc;                                              // (combined mode only)
                 const HelpArgs hg = {&mkc, copies, S.act, &gG, gsG};
                 const float rg = a.s2_rhog[tile * TC_PATHS + row];
+                float xn[DPX], cn[DPX];
+                {
+                    const float* tr = trj + (size_t)t0 * 2 * sr * TC_PATHS;
+                    KLOOP(k, d) { xn[k] = __ldcs(&tr[k * TC_PATHS + row]); cn[k] = __ldcs(&tr[(sr + k) * TC_PATHS + row]); }
+                }
                 for (int t = t0; t < t1; ++t) {
-                    const float* tr = trj + (size_t)t * 2 * sr * TC_PATHS;
-                    KLOOP(k, d) { xt[k] = __ldcs(&tr[k * TC_PATHS + row]); cot[k] = __ldcs(&tr[(sr + k) * TC_PATHS + row]) * rg; }
+                    KLOOP(k, d) { xt[k] = xn[k]; cot[k] = cn[k] * rg; }
                     float none[1];
                     own_net_forward_keep(P, nG, S.vecG, xt, none, copies, row, true, hg);
+                    if (t + 1 < t1) {
+                        const float* tr = trj + (size_t)(t + 1) * 2 * sr * TC_PATHS;
+                        KLOOP(k, d) { xn[k] = __ldcs(&tr[k * TC_PATHS + row]); cn[k] = __ldcs(&tr[(sr + k) * TC_PATHS + row]); }
+                    }
                     own_net_backward_nody0(P, nG, cot, S.dz, row, mxbuf, dexp, true, hg);
                 }
             }
@@ -338,25 +358,45 @@ __device__ __forceinline__ void critic_tc_body(const TcArgs& a, const TcSmem& S,
         }
         if (is_ctrl) {                                            // schedule of the rollout
             ctrl_flush(C);
-            if (!cheat) sched_add_fwd(C, nA, a.imgA, nA.L);
-            if (td1) sched_add_fwd(C, nG, a.imgG, nG.L);
+            if (!cheat) sched_add_fwd(C, nA, imgA, nA.L);
+            if (td1) sched_add_fwd(C, nG, imgG, nG.L);
             ctrl_sched_ready(C);
         }
         // ------------------------------------------------------------------ sweep 1: rollout
+        // One CTA barrier per step decides whether any path of the tile is still inside.  The control warp and the helpers
+        // run it at the top of the step; the owners run the one of step t+1 INSIDE step t, as soon as they have moved the
+        // state: the networks of a step are one serial chain (the tile is the only one this SM works on), so what the owners
+        // do between the end of one network and the published input of the next is exposed.  They therefore prepare the
+        // next input (BatchNorm, bf16 split) while the current network still runs, and after its last product only read
+        // its output, store the prepared planes and publish; the rest of the step's arithmetic follows under the next network.
         int tlive = 0;
-        for (int t = 0; t < N; ++t) {
-            const int alive = bar_work_or(valid && flag > 0, TC_WORK_THREADS);
-            if (!alive) break;
-            tlive = t + 1;
-            if (is_ctrl) {
-                if (!cheat) ctrl_net_forward(C, nA, nA.L);
-                if (td1) ctrl_net_forward(C, nG, nG.L);
-            } else if (is_help) {
-                if (!cheat) help_forward(P, nA, S.vecA);
-                if (td1) help_forward(P, nG, S.vecG);
-            } else {
-                // the owners' arithmetic runs while the helpers and the tensor pipe work through the networks
-                if (!cheat) own_put_y0(P, nA, S.vecA, x, nullptr, 0);
+        if (!is_own) {
+            for (int t = 0; t < N; ++t) {
+                const int alive = bar_work_or(false, TC_WORK_THREADS);
+                if (!alive) break;
+                tlive = t + 1;
+                if (is_ctrl) {
+                    if (!cheat) ctrl_net_forward(C, nA, nA.L);
+                    if (td1) ctrl_net_forward(C, nG, nG.L);
+                } else if (is_help) {
+                    if (!cheat) help_forward(P, nA, S.vecA);
+                    if (td1) help_forward(P, nG, S.vecG);
+                }
+            }
+        } else {
+            const bool hasA = !cheat, hasG = td1;
+            const TcNet& n1 = hasA ? nA : nG;                             // first network of a step
+            const float* vec1 = hasA ? S.vecA : S.vecG;
+            uint32_t yh[2][8], yl[2][8];
+            int alive = bar_work_or(valid && flag > 0, TC_WORK_THREADS);
+            if (alive && (hasA || hasG)) {
+                own_prep_y0(n1, vec1, x, yh, yl);
+                own_store_y0(P, n1, yh, yl);
+                own_publish(P);
+            }
+            for (int t = 0; t < N && alive; ++t) {
+                tlive = t + 1;
+                if (hasA && hasG) own_prep_y0(nG, S.vecG, x, yh, yl);            // NN_value_grad at x_t (before the move)
                 path_dw(a, gp, valid, t, dwv);
                 float dt, sqdt, xn; int dtg;
                 fwd_dt<float, DP, EQN, MV>(E, x, flag, 1, 0, dt, sqdt, xn, dtg);
@@ -365,10 +405,10 @@ __device__ __forceinline__ void critic_tc_body(const TcArgs& a, const TcSmem& S,
                 } else {
                     if (TC_COMBINED) help_forward(P, nA, S.vecA);
                     own_last(P, nA, S.vecA, raw);
+                    if (hasG) { own_store_y0(P, nG, yh, yl); own_publish(P); }
                     if (nA.ekn_head) ekn_head_fwd<float, DP, EQN, MV>(raw, u, nA.mctrl, 1, 0);
                     else KLOOP(j, E.m) u[j] = raw[j];
                 }
-                if (td1) own_put_y0(P, nG, S.vecG, x, nullptr, 0);                // NN_value_grad at x_t (before the move)
                 float* tr = traj + (size_t)t * 2 * sr * TC_PATHS;
                 if (need_grad && td1)
                     KLOOP(k, d) __stcs(&tr[k * TC_PATHS + row], x[k]);
@@ -376,7 +416,14 @@ __device__ __forceinline__ void critic_tc_body(const TcArgs& a, const TcSmem& S,
                 if (!prop_only) w = eq_w<float, DP, EQN, MV>(E, x, u, 1, 0);
                 const int coef = fwd_move<float, DP, EQN, MV>(E, x, u, dwv, dt, sqdt, xn, flag, sdw, 1, 0);
                 const float cf = (float)coef;
-                if (td1) { if (TC_COMBINED) help_forward(P, nG, S.vecG); own_last(P, nG, S.vecG, g); }
+                if (td1 && TC_COMBINED) help_forward(P, nG, S.vecG);              // (before the barrier: the control warp reaches it
+                                                                                  //  only after it has issued the whole network)
+                int alive_next = 0;
+                if (t + 1 < N) alive_next = bar_work_or(valid && flag > 0, TC_WORK_THREADS);
+                const bool pub = alive_next && (hasA || hasG);
+                if (pub) own_prep_y0(n1, vec1, x, yh, yl);                        // input of the next step's first network
+                if (td1) own_last(P, nG, S.vecG, g);
+                if (pub) { own_store_y0(P, n1, yh, yl); own_publish(P); }
                 y = y + w * disc * cf * dt;                                       // solver.py:170-174
                 if (td1) {
                     float dif = 0.f;
@@ -396,6 +443,7 @@ __device__ __forceinline__ void critic_tc_body(const TcArgs& a, const TcSmem& S,
                     if (a.o_x)
                         KLOOP(k, d) a.o_x[(gp * d + k) * (long long)(N + 1) + t + 1] = x[k];
                 }
+                alive = alive_next;
             }
         }
         if (valid) {
@@ -413,12 +461,12 @@ __device__ __forceinline__ void critic_tc_body(const TcArgs& a, const TcSmem& S,
         if (is_ctrl) {
             ctrl_flush(C);
             if (!need_grad) {
-                sched_add_fwd(C, nV, a.imgV, nV.L);
+                sched_add_fwd(C, nV, imgV, nV.L);
                 ctrl_sched_ready(C);
                 for (int i = 0; i < 3; ++i) ctrl_net_forward(C, nV, nV.L);
             } else {
-                sched_add_fwd(C, nV, a.imgV, nV.L);                       // V(x_0), forward only
-                for (int i = 0; i < 3; ++i) { sched_add_fwd(C, nV, a.imgV, nV.L); sched_add_bwd(C, nV, a.imgV, false); }
+                sched_add_fwd(C, nV, imgV, nV.L);                       // V(x_0), forward only
+                for (int i = 0; i < 3; ++i) { sched_add_fwd(C, nV, imgV, nV.L); sched_add_bwd(C, nV, imgV, false); }
                 ctrl_sched_ready(C);
                 ctrl_net_forward(C, nV, nV.L);
                 for (int i = 0; i < 3; ++i) { ctrl_net_forward(C, nV, nV.L); ctrl_net_backward(C, nV, true, copies, false, false); }
@@ -435,7 +483,7 @@ __device__ __forceinline__ void critic_tc_body(const TcArgs& a, const TcSmem& S,
                 }
             }
         } else {
-            float vN[1], v0[1], vb[1], x0v[DPX], xbv[DPX], dy0[DPX], cot[1];
+            float vN[1], v0[1], vb[1], x0v[DPX], xbv[DPX], cot[1];
             KLOOP(k, d) x0v[k] = valid ? a.x0[gp * d + k] : fill;
             KLOOP(k, d) xbv[k] = valid ? a.xb[gp * d + k] : fill;
             if (!need_grad) {
@@ -477,8 +525,8 @@ __device__ __forceinline__ void critic_tc_body(const TcArgs& a, const TcSmem& S,
         } else if (need_grad && td1) {
             if (is_ctrl) {
                 ctrl_flush(C);
-                sched_add_fwd(C, nG, a.imgG, nG.L - 1);
-                sched_add_bwd(C, nG, a.imgG, false);
+                sched_add_fwd(C, nG, imgG, nG.L - 1);
+                sched_add_bwd(C, nG, imgG, false);
                 ctrl_sched_ready(C);
                 for (int t = 0; t < tlive; ++t) {
                     ctrl_net_forward(C, nG, nG.L - 1);
@@ -491,14 +539,20 @@ __device__ __forceinline__ void critic_tc_body(const TcArgs& a, const TcSmem& S,
                     help_backward(P, nG, gG, mk, true, gsG, S.dz, row, dexp);
                 }
             } else {
-                float xt[DPX], cot[DPX], dy0[DPX];
+                float xt[DPX], cot[DPX];
                 Masks mkc;                                                        // (combined mode only)
                 const HelpArgs hg = {&mkc, copies, S.act, &gG, gsG};
+                // (the trajectory of step t+1 is fetched while the backward pass of step t runs)
+                float xn[DPX], cn[DPX];
+                if (tlive > 0) KLOOP(k, d) { xn[k] = __ldcs(&traj[k * TC_PATHS + row]); cn[k] = __ldcs(&traj[(sr + k) * TC_PATHS + row]); }
                 for (int t = 0; t < tlive; ++t) {
-                    const float* tr = traj + (size_t)t * 2 * sr * TC_PATHS;
-                    KLOOP(k, d) { xt[k] = __ldcs(&tr[k * TC_PATHS + row]); cot[k] = __ldcs(&tr[(sr + k) * TC_PATHS + row]) * rhog; }
+                    KLOOP(k, d) { xt[k] = xn[k]; cot[k] = cn[k] * rhog; }
                     float none[1];
                     own_net_forward_keep(P, nG, S.vecG, xt, none, copies, row, true, hg);
+                    if (t + 1 < tlive) {
+                        const float* tr = traj + (size_t)(t + 1) * 2 * sr * TC_PATHS;
+                        KLOOP(k, d) { xn[k] = __ldcs(&tr[k * TC_PATHS + row]); cn[k] = __ldcs(&tr[(sr + k) * TC_PATHS + row]); }
+                    }
                     own_net_backward_nody0(P, nG, cot, S.dz, row, mxbuf, dexp, true, hg);
                 }
             }
@@ -552,6 +606,10 @@ __device__ __forceinline__ void actor_tc_body(const TcArgs& a, const TcSmem& S, 
     const TcSlab& gA = *S.gA;
     const TcSlab& gV = *S.gV;
     (void)gA; (void)gV;
+    const int rep = (int)(blockIdx.x % (unsigned)a.img_rep);
+    const unsigned char* imgA = a.imgA + rep * a.img_strideA;
+    const unsigned char* imgV = a.imgV + rep * a.img_strideV;
+    (void)imgA; (void)imgV;
     const int tid = threadIdx.x;
     const int row = R.row;
     const Eq<float>& E = a.eqf;                                   // kernel-parameter space: fields are constant-bank operands
@@ -585,7 +643,7 @@ __device__ __forceinline__ void actor_tc_body(const TcArgs& a, const TcSmem& S, 
         }
         if (is_ctrl) {
             ctrl_flush(C);
-            if (!cheat) sched_add_fwd(C, nA, a.imgA, nA.L);
+            if (!cheat) sched_add_fwd(C, nA, imgA, nA.L);
             ctrl_sched_ready(C);
         }
         // ------------------------------------------------------------------ forward rollout
@@ -651,8 +709,8 @@ __device__ __forceinline__ void actor_tc_body(const TcArgs& a, const TcSmem& S, 
         if (is_ctrl) {
             ctrl_flush(C);
             if (!cheat_v) {
-                sched_add_fwd(C, nV, a.imgV, nV.L);
-                if (need_grad) sched_add_bwd(C, nV, a.imgV);
+                sched_add_fwd(C, nV, imgV, nV.L);
+                if (need_grad) sched_add_bwd(C, nV, imgV);
                 ctrl_sched_ready(C);
                 ctrl_net_forward(C, nV, nV.L);
                 if (need_grad) ctrl_net_backward(C, nV, false, nullptr, false, true);
@@ -700,13 +758,17 @@ __device__ __forceinline__ void actor_tc_body(const TcArgs& a, const TcSmem& S, 
         // ------------------------------------------------------------------ reverse sweep
         if (is_ctrl) {
             ctrl_flush(C);
-            sched_add_fwd(C, nA, a.imgA, nA.L);
-            sched_add_bwd(C, nA, a.imgA);
+            sched_add_fwd(C, nA, imgA, nA.L);
+            sched_add_bwd(C, nA, imgA);
             ctrl_sched_ready(C);
         }
         for (int t = tlive - 1; t >= 0; --t) {
             const float* tr = traj + (size_t)t * trs * TC_PATHS;
             const float* sc = tr + (size_t)2 * sr * TC_PATHS;
+            if (is_own && t > 0) {                                       // the record of the step before: on its way to L2 by the time it is read
+                const char* nb = reinterpret_cast<const char*>(tr - (size_t)trs * TC_PATHS);
+                for (int i = row; i < trs * 4; i += TC_OWN_THREADS) asm volatile("prefetch.global.L2 [%0];" ::"l"(nb + (size_t)i * 128));
+            }
             const int any = bar_work_or(valid && sc[A_COEF * TC_PATHS + row] > 0.f, TC_WORK_THREADS);
             if (!any) continue;
             if (is_ctrl) {

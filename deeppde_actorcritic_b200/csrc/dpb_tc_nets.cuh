@@ -54,6 +54,7 @@ namespace dpb {
 namespace tc {
 
 constexpr int TC_PATHS = 128;
+constexpr int TC_TRACE_CAP = 4096;             // events per role of the diagnostic trace (stats builds)
 #ifndef DPB_TC_NGRP
 #define DPB_TC_NGRP 2
 #endif
@@ -61,11 +62,16 @@ constexpr int TC_NGRP = DPB_TC_NGRP;            // helper groups of 4 warps (chu
                                                 // warps -- the owners run the helpers' code themselves, one thread per path with up to
                                                 // 255 registers (the actor kernels: their reverse sweep is one serial dependency chain,
                                                 // so separate helpers only add hand-offs and cost the owners registers)
-constexpr bool TC_COMBINED = TC_NGRP == 0;
-constexpr int TC_EGRP = TC_COMBINED ? 1 : TC_NGRP;      // groups the chunks of an epilogue are dealt out to
+#ifndef DPB_TC_OWNHELP
+#define DPB_TC_OWNHELP 0
+#endif
+// the owners take part in the epilogues and drains as group 0 (always when there are no helper warps; DPB_TC_OWNHELP=1: next
+// to TC_NGRP helper groups, which are then groups 1..TC_NGRP)
+constexpr bool TC_COMBINED = TC_NGRP == 0 || DPB_TC_OWNHELP != 0;
+constexpr int TC_EGRP = TC_NGRP + (TC_COMBINED ? 1 : 0);      // groups the chunks of an epilogue are dealt out to
 constexpr int TC_OWN_THREADS = 128;             // warps 0-3: thread t owns path t
 constexpr int TC_HELP_WARPS = 4 * TC_NGRP;
-constexpr int TC_EPI_WARPS = TC_COMBINED ? 4 : TC_HELP_WARPS;     // warps that arrive on a_help / a_chunk[0]
+constexpr int TC_EPI_WARPS = 4 * TC_EGRP;       // warps that arrive on a_help / a_chunk[0]
 constexpr int TC_CTRL_WARP = 4 + TC_HELP_WARPS; // waits for operands, issues every tcgen05.mma
 constexpr int TC_PROD_WARP = TC_CTRL_WARP + 1;  // lane 0: streams the weight chunks (bulk copies) on its own
 constexpr int TC_WORK_THREADS = 32 * (TC_CTRL_WARP + 1);   // owner + helper + control warps take part in the in-loop CTA barriers (named barrier 1)
@@ -162,14 +168,16 @@ inline bool tcnet_supported(const TcNet& t) {
 
 // ------------------------------------------------------------------------------------------- pack
 // flat FP32 parameters -> bf16 hi/lo operand images + the FP32 vector block (gamma*c, beta, ...)
-static __global__ void tc_pack_kernel(TcNet t, const float* __restrict__ th, unsigned char* __restrict__ img, float* __restrict__ vec, float c) {
+// (nrep copies of the image, rep_stride bytes apart: CTA i streams copy i % nrep -- see TcArgs::img_rep)
+static __global__ void tc_pack_kernel(TcNet t, const float* __restrict__ th, unsigned char* __restrict__ img, float* __restrict__ vec, float c,
+                                      int nrep, long long rep_stride) {
     const NetDev& nd = t.flat;
     const long long stride = (long long)gridDim.x * blockDim.x;
     const long long t0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const int K0 = t.ly[0].K16;
     for (long long i = t0; i < K0; i += stride) {
         vec[t.vec_g0 + i] = i < t.in ? th[nd.fg0 + i] * c : 0.f;
-        vec[t.vec_g0 + K0 + i] = i < t.in ? th[nd.fb0 + i] : 0.f;
+        vec[t.vec_g0 + K0 + i] = i < t.in ? th[nd.fb0 + i] : (i == t.in ? 1.f : 0.f);      // (i = in: the constant-1 feature)
     }
     for (int l = 0; l <= t.L; ++l) {
         const TcLayer y = t.ly[l];
@@ -200,8 +208,10 @@ static __global__ void tc_pack_kernel(TcNet t, const float* __restrict__ th, uns
             {
                 const long long cb = (long long)y.N16 * 64;
                 unsigned char* base = img + y.img_f + (k >> 4) * cb + (((k & 15) >> 3) * (y.N16 >> 3) + (n >> 3)) * 128 + (n & 7) * 16 + (k & 7) * 2;
-                *reinterpret_cast<__nv_bfloat16*>(base) = hi;
-                *reinterpret_cast<__nv_bfloat16*>(base + y.N16 * 32) = lo;
+                for (int r = 0; r < nrep; ++r) {
+                    *reinterpret_cast<__nv_bfloat16*>(base + r * rep_stride) = hi;
+                    *reinterpret_cast<__nv_bfloat16*>(base + r * rep_stride + y.N16 * 32) = lo;
+                }
             }
             // backward image: rows k (K16), contraction n, value W[k][n] * gamma[n]*c; chunk = n/16
             const float wg = in_rng ? w * (th[nd.fg[l] + n] * c) : 0.f;
@@ -209,8 +219,10 @@ static __global__ void tc_pack_kernel(TcNet t, const float* __restrict__ th, uns
             {
                 const long long cb = (long long)y.K16 * 64;
                 unsigned char* base = img + y.img_b + (n >> 4) * cb + (((n & 15) >> 3) * (y.K16 >> 3) + (k >> 3)) * 128 + (k & 7) * 16 + (n & 7) * 2;
-                *reinterpret_cast<__nv_bfloat16*>(base) = hi;
-                *reinterpret_cast<__nv_bfloat16*>(base + y.K16 * 32) = lo;
+                for (int r = 0; r < nrep; ++r) {
+                    *reinterpret_cast<__nv_bfloat16*>(base + r * rep_stride) = hi;
+                    *reinterpret_cast<__nv_bfloat16*>(base + r * rep_stride + y.K16 * 32) = lo;
+                }
             }
         }
     }
@@ -220,8 +232,21 @@ static __global__ void tc_pack_kernel(TcNet t, const float* __restrict__ th, uns
 // per-thread local memory across the noinline helpers and cost ~6 % of the kernel when enabled
 #ifdef DPB_TC_STATS
 #define TC_STAT(...) __VA_ARGS__
+// event trace of CTA 0 (owner thread 0, helper thread 128, control lane 0): (clock64 << 8) | event id, TC_TRACE_CAP events per
+// role (dpb_tc_trace, tools/trace_timeline.py).  ids: control 1 operands of a TS product ready, 2 product issued and committed,
+// 3 / 4 the same for a dW block, 5 product entered (before the operand wait); helpers 10 epilogue entered, 11 accumulator
+// committed, 12 epilogue done, 13 / 14 / 15 the same for a drain; owners 20 published, 21 waits for a result, 22 has it
+// (DPB_TC_TRACE_FINE: also 6 weight slot landed, 7 operand chunk published, 8 slot's MMAs issued and slot release committed)
+#ifdef DPB_TC_TRACE_FINE
+#define TC_TRACE2(ctx, id) TC_TRACE(ctx, id)
+#else
+#define TC_TRACE2(ctx, id)
+#endif
+#define TC_TRACE(ctx, id) do { if ((ctx).tr && (ctx).tn < TC_TRACE_CAP) (ctx).tr[(ctx).tn++] = ((unsigned long long)clock64() << 8) | (unsigned)(id); } while (0)
 #else
 #define TC_STAT(...)
+#define TC_TRACE(ctx, id)
+#define TC_TRACE2(ctx, id)
 #endif
 
 // ------------------------------------------------------------------------------ control-thread side
@@ -246,11 +271,14 @@ struct ProdCtl {
 //   [18]     acc_fin    count 1   tcgen05.commit of a product the OWNERS read (a network's output, the input cotangent dy0;
 //                                 also "the forward products are done" before a skip-last backward)
 //   [19]     a_own      count 4   the owner warps wrote a network input (y0) or an output cotangent
+//   [20]     acc_dw     count 1   tcgen05.commit of a dW block (drained by the helpers; its own barrier because a dW block is
+//                                 committed right behind the dX product of its layer -- two commits the helpers have not yet looked
+//                                 at would wrap the parity of a shared barrier)
 // Every side tracks the parities of the barriers it waits on in one word, together with the TMEM region of the next A planes.
-constexpr uint32_t SY_HELP = 1u << 16, SY_ACC = 1u << 17, SY_DZ = 1u << 18, SY_OWN = 1u << 19, SY_FIN = 1u << 20, SY_REG = 1u << 31;
-constexpr int BAR_ACC = 0, BAR_HELP = 1, BAR_CHUNK = 2, BAR_FIN = 18, BAR_OWN = 19, NUM_HANDOFF_BARS = 20;
+constexpr uint32_t SY_HELP = 1u << 16, SY_ACC = 1u << 17, SY_DZ = 1u << 18, SY_OWN = 1u << 19, SY_FIN = 1u << 20, SY_DW = 1u << 21, SY_REG = 1u << 31;
+constexpr int BAR_ACC = 0, BAR_HELP = 1, BAR_CHUNK = 2, BAR_FIN = 18, BAR_OWN = 19, BAR_DW = 20, NUM_HANDOFF_BARS = 21;
 __device__ __forceinline__ float pow2f(int e) { return __int_as_float((127 + e) << 23); }            // 2^e, -126 <= e <= 127
-enum { IN_OWN = 0, IN_HELP = 1, IN_CHUNKS = 2, IN_BOTH = 3 };            // what a product's inputs were published on
+enum { IN_OWN = 0, IN_HELP = 1, IN_CHUNKS = 2, IN_BOTH = 3, IN_NONE = 4 };     // what a product's inputs were published on (IN_NONE: already seen)
 
 struct Ctrl {
     unsigned char* ring;
@@ -258,7 +286,7 @@ struct Ctrl {
     Sched* sch;
     ProdCtl* pc;
     uint32_t nslot, slot_bytes;
-    uint32_t n_req, n_consumed, op_count, act_count, tmem, gen;
+    uint32_t n_req, n_consumed, op_count, dw_count, act_count, tmem, gen;      // dw_count: dW blocks committed on acc_dw so far
     uint32_t sync;                   // parity bits (see above); op_count = products committed on acc_full so far
     volatile int* dexp;              // shared word: the exponent the owners scaled the current backward evaluation by
     uint32_t mm_slot, mm_use;        // ring cursor (slot index, wrap count) of the MMA issuer
@@ -266,6 +294,7 @@ struct Ctrl {
     long long n_ops;
     TC_STAT(long long t_aready, t_issue, t_accw;)   // cycle counters (diagnostics)
     TC_STAT(long long t_dw_ready, t_act;)           // dW products: waiting for their operands / for the ACT bulk copy
+    TC_STAT(unsigned long long* tr; int tn;)        // event trace (lane 0 of CTA 0 only)
 };
 
 // let the producer run up to nslot loads ahead of the MMAs (one shared-memory store, never waits)
@@ -346,7 +375,7 @@ __device__ __forceinline__ void sched_add_fwd(Ctrl& c, const TcNet& t, const uns
 __device__ __forceinline__ void ctrl_wait_inputs(uint32_t bars0, uint32_t& sync, int in_kind) {
     if (in_kind == IN_OWN || in_kind == IN_BOTH) { mbar_wait_u32(bars0 + 8 * BAR_OWN, (sync >> 19) & 1u); sync ^= SY_OWN; }
     if (in_kind == IN_HELP || in_kind == IN_BOTH) { mbar_wait_u32(bars0 + 8 * BAR_HELP, (sync >> 16) & 1u); sync ^= SY_HELP; }
-    if (in_kind != IN_CHUNKS) tc_fence_after();
+    if (in_kind != IN_CHUNKS && in_kind != IN_NONE) tc_fence_after();
 }
 
 // D[acc region] = A(planes in the other region) x B(streamed image with R rows): nchunks contraction chunks, 3 split
@@ -373,11 +402,21 @@ __device__ __forceinline__ void ctrl_gemm_ts(Ctrl& cref, int nchunks_, int R_, i
     const uint64_t dlo = ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) | ((uint64_t)(128 >> 4) << 32) | (1ull << 46);
     ctrl_request(c);
     TC_STAT(const long long t0 = clock64();)
+    TC_TRACE(c, 5);
     ctrl_wait_inputs(bars0, sync, in_kind);
     TC_STAT(const long long ti0 = clock64(); c.t_aready += ti0 - t0;)
+    TC_TRACE(c, 1);
     ++c.n_ops;
+    // Issue loop (the whole warp runs it on warp-uniform values; the elected lane issues).  Per slot: wait for its weights (ring
+    // slot landed), per chunk for its operand planes, three MMAs, the commit that releases the slot.  Round 2 tried three other
+    // shapes of this loop, all measured slower or equal at 2^17 paths (profiles/r02_issue_loop_variants.txt):
+    // polling all barriers at once from the 32 lanes (an mbarrier test costs ~80 cycles PER DISTINCT ADDRESS of the warp
+    // instruction), byte counters in shared memory instead of the chunk barriers, and testing the next slot's / chunk's barrier
+    // under the MMAs of the current one (mma_ts3_commit_wait2 in dpb_tc.cuh: no change -- with the latencies hidden the MMAs
+    // themselves still need ~520 cycles per slot next to a running epilogue).
     for (int s0 = 0; s0 < nchunks; s0 += g) {
         mbar_wait_u32(full0 + mm_slot * 8, mm_use & 1);
+        TC_TRACE2(c, 6);
         const uint32_t sb0 = ring0 + mm_slot * slot_bytes;
         const int n = (nchunks - s0) < g ? (nchunks - s0) : g;
         for (int j = 0; j < n; ++j) {
@@ -388,6 +427,7 @@ __device__ __forceinline__ void ctrl_gemm_ts(Ctrl& cref, int nchunks_, int R_, i
                 TC_STAT(c.t_aready += clock64() - tw;)
                 sync ^= 1u << s;
                 tc_fence_after();
+                TC_TRACE2(c, 7);
             }
             const uint32_t sb = sb0 + j * R * 64;
             const uint64_t bhi = dlo | (uint64_t)((sb >> 4) & 0x3FFF), blo = dlo | (uint64_t)(((sb + R * 32) >> 4) & 0x3FFF);
@@ -399,6 +439,7 @@ __device__ __forceinline__ void ctrl_gemm_ts(Ctrl& cref, int nchunks_, int R_, i
             }
         }
         if (elect_one()) tc_commit_u32(empty0 + mm_slot * 8);
+        TC_TRACE2(c, 8);
         ++c.n_consumed;
         if (++mm_slot == nslot) { mm_slot = 0; ++mm_use; }
         ctrl_request(c);
@@ -408,6 +449,7 @@ __device__ __forceinline__ void ctrl_gemm_ts(Ctrl& cref, int nchunks_, int R_, i
         if (fin || also_fin) tc_commit_u32(bars0 + 8 * BAR_FIN);
     }
     TC_STAT(c.t_issue += clock64() - ti0;)
+    TC_TRACE(c, 2);
     if (!fin) ++c.op_count;
     if (toggles) sync ^= SY_REG;
     c.sync = sync;
@@ -435,6 +477,7 @@ struct PathCtx {
     TC_STAT(long long t_accw, t_mark;)      // cycles spent waiting for the tensor pipe; time of the last wake-up
     TC_STAT(long long t_epi, t_hid;)        // t_hid: cycles inside hidden-layer epilogues only
     TC_STAT(long long t_drain;)             // cycles inside the dW drains (after the accumulator wait)
+    TC_STAT(unsigned long long* tr; int tn;)  // event trace (owner thread 0 / helper thread 128 of CTA 0 only)
 };
 
 // The out-of-line helpers take the context BY VALUE (registers) and return the one field they change: passed by reference it
@@ -515,7 +558,9 @@ template <class F>
 __device__ __forceinline__ void for_acc_chunks(PathCtx& p, int nco, int mode, int fence, bool toggle, F f) {
     // (the TMEM->register path is the bound of every epilogue -- 64 B/clk/SM, see DESIGN.md -- so a plain loop does as
     //  well as a software-pipelined one and needs 16 registers fewer)
+    TC_TRACE(p, 10);
     help_wait_acc(p);
+    TC_TRACE(p, 11);
     // Every helper warp takes part in the hand-off of chunk 0 (its owners when the planes are written, the others here, as
     // soon as they have seen the commit): the next product cannot be committed before all warps have observed this one.
     // Without it a warp that owns no chunk of a narrow output (one chunk: the other group's) could fall two phases behind
@@ -548,6 +593,7 @@ __device__ __forceinline__ void for_acc_chunks(PathCtx& p, int nco, int mode, in
     if (toggle) p.sync ^= SY_REG;
     if (mode == EPI_ALL) help_publish(p);
     TC_STAT(else p.t_epi += clock64() - p.t_mark;)
+    TC_TRACE(p, 12);
 }
 
 // z = acc * gc + bb for 16 features (gc, bb: 16-byte aligned SHARED memory; read with ld.shared -- through generic pointers the
@@ -617,12 +663,15 @@ __device__ __forceinline__ void own_publish(PathCtx& p) {
     __syncwarp();
     if ((threadIdx.x & 31) == 0) mbar_arrive_u32(p.bars + 8 * BAR_OWN);
     TC_STAT(p.t_epi += clock64() - p.t_mark;)
+    TC_TRACE(p, 20);
 }
 // wait for a product whose result the owners read (or for the end of the forward products of a skip-last evaluation)
 __device__ __forceinline__ void own_wait_fin(PathCtx& p) {
     TC_STAT(const long long t0 = clock64();)
+    TC_TRACE(p, 21);
     mbar_wait_u32(p.bars + 8 * BAR_FIN, (p.sync >> 20) & 1u);
     TC_STAT(p.t_mark = clock64(); p.t_accw += p.t_mark - t0;)
+    TC_TRACE(p, 22);
     p.sync ^= SY_FIN;
     tc_fence_after();
 }
@@ -632,24 +681,62 @@ __device__ __forceinline__ void own_swaps(PathCtx& p, int n) { if (!TC_COMBINED 
 
 // y0 = x * g0c + b0 (solver.py:265) -> planes (+ FP16 copy with the constant-1 feature when `copies`), then
 // publish.  Everything indexed statically (K16_0 <= 32) so that x can live in registers.
+// y0 = x * g0c + b0 (input BatchNorm; feature `in` is the constant 1: g0c = 0, b0 = 1 there) as hi / lo plane words.  Split
+// from the stores so that the owners can prepare the next input while the networks still run and only have to store and
+// publish it once the plane region is free (critic rollout).
+template <int NX>
+__device__ __forceinline__ void own_prep_y0_chunk(const TcNet& t, const float* vec, const float (&x)[NX], int c, uint32_t (&h)[8], uint32_t (&l)[8]) {
+    const int K0 = t.ly[0].K16;
+    const uint32_t ga = smem_u32(vec + t.vec_g0), ba = ga + 4u * (uint32_t)K0;
+    float v[16];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const float4 g = lds4(ga + 64 * c + 16 * q), b = lds4(ba + 64 * c + 16 * q);
+        const float gg[4] = {g.x, g.y, g.z, g.w}, bb[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int k = 16 * c + 4 * q + i;
+            const float xv = (k < NX && k < t.in) ? x[k < NX ? k : 0] : 0.f;       // (entries past d are not initialised)
+            v[4 * q + i] = xv * gg[i] + bb[i];
+        }
+    }
+    split16(v, h, l);
+}
+template <int NX>
+__device__ __forceinline__ void own_prep_y0(const TcNet& t, const float* vec, const float (&x)[NX], uint32_t (&yh)[2][8], uint32_t (&yl)[2][8]) {
+#pragma unroll
+    for (int c = 0; c < 2; ++c)
+        if (c < t.ly[0].K16 / 16) own_prep_y0_chunk(t, vec, x, c, yh[c], yl[c]);
+}
+__device__ __forceinline__ void own_store_y0(PathCtx& p, const TcNet& t, const uint32_t (&yh)[2][8], const uint32_t (&yl)[2][8]) {
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+        if (c < t.ly[0].K16 / 16) {
+            tmem_st8(path_planes(p) + 16 * c, yh[c]);
+            tmem_st8(path_planes(p) + 16 * c + 8, yl[c]);
+        }
+    }
+}
+// y0 -> planes (+ the FP16 copy of the RAW input for the dW product of layer 0), publish
 template <int NX>
 __device__ __forceinline__ void own_put_y0(PathCtx& p, const TcNet& t, const float* vec, const float (&x)[NX], unsigned char* copies, int row) {
     const int K0 = t.ly[0].K16;
-    const float* g0c = vec + t.vec_g0;
-    const float* b0 = g0c + K0;
 #pragma unroll
     for (int c = 0; c < 2; ++c) {
         if (c < K0 / 16) {
-            float v[16];
+            uint32_t h[8], l[8];
+            own_prep_y0_chunk(t, vec, x, c, h, l);
+            tmem_st8(path_planes(p) + 16 * c, h);
+            tmem_st8(path_planes(p) + 16 * c + 8, l);
+        }
+    }
+    if (copies) {
+        // the dW operand of layer 0 is the RAW input x (+ the constant 1): x^T dz_0 gives the weight gradient AND the
+        // gradients of the input BatchNorm (finalize kernel), so no per-thread input sums are kept
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                const int k = 16 * c + j;
-                v[j] = (k < NX && k < t.in) ? x[k < NX ? k : 0] * g0c[k] + b0[k] : (k == t.in ? 1.f : 0.f);      // (k = in: the constant 1)
-            }
-            put16(path_planes(p) + 16 * c, v);
-            if (copies) {
-                // the dW operand of layer 0 is the RAW input x (+ the constant 1): x^T dz_0 gives the weight gradient AND the
-                // gradients of the input BatchNorm (finalize kernel), so no per-thread input sums are kept
+        for (int c = 0; c < 2; ++c) {
+            if (c < K0 / 16) {
+                float v[16];
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
                     const int k = 16 * c + j;
@@ -658,8 +745,8 @@ __device__ __forceinline__ void own_put_y0(PathCtx& p, const TcNet& t, const flo
                 copy16f(copies, row, c, v, t.ly[0].kl);
             }
         }
+        fence_proxy_async_global();
     }
-    if (copies) fence_proxy_async_global();
     own_publish(p);
 }
 
@@ -786,8 +873,9 @@ __device__ __forceinline__ void ctrl_act_wait(Ctrl& c) {
     ++c.act_count;
 }
 
-// D[acc] (rows = features 128*blk .. of ACT, cols = N16 features of DZ) = ACT^T DZ over the 128 paths.  The accumulator
-// is the region the next dX product will write (the other one holds the dz planes that product reads).
+// D[acc] (rows = features 128*blk .. of ACT, cols = N16 features of DZ) = ACT^T DZ over the 128 paths.  The accumulator is
+// the region the NEXT TS product will write: issued behind the dX product of its layer (layers >= 1) that is the region
+// whose dz planes that product has just consumed; issued before it (layer 0) the region the dX product will write.
 __device__ __forceinline__ void ctrl_gemm_dw(Ctrl& c, int blk_, int N16_, int in_kind_, bool also_fin_ = false) {
     const bool also_fin = warp_uniform(also_fin_ ? 1u : 0u) != 0;
     const int blk = (int)warp_uniform((uint32_t)blk_), N16 = (int)warp_uniform((uint32_t)N16_), in_kind = (int)warp_uniform((uint32_t)in_kind_);
@@ -795,8 +883,10 @@ __device__ __forceinline__ void ctrl_gemm_dw(Ctrl& c, int blk_, int N16_, int in
     uint32_t sync = warp_uniform(c.sync);
     const uint32_t bars0 = warp_uniform(smem_u32(c.bars));
     TC_STAT(const long long t0 = clock64();)
+    TC_TRACE(c, 5);
     ctrl_wait_inputs(bars0, sync, in_kind);                             // operands complete / previous block drained
     TC_STAT(c.t_dw_ready += clock64() - t0;)
+    TC_TRACE(c, 3);
     const uint32_t a0 = warp_uniform(smem_u32(c.act)) + blk * 16 * 2048, b0 = warp_uniform(smem_u32(c.dz));
     const uint32_t tmem = warp_uniform(c.tmem);
     const uint32_t dcol = tmem + COL_REG * ((sync >> 31) ^ 1u);
@@ -806,11 +896,12 @@ __device__ __forceinline__ void ctrl_gemm_dw(Ctrl& c, int blk_, int N16_, int in
             const uint64_t ad = smem_desc(a0 + s * 256, 128, 2048), bd = smem_desc(b0 + s * 256, 128, 2048);
             mma_ss(dcol, ad, bd, idesc, s > 0);
         }
-        tc_commit_u32(bars0 + 8 * BAR_ACC);
+        tc_commit_u32(bars0 + 8 * BAR_DW);
         if (also_fin) tc_commit_u32(bars0 + 8 * BAR_FIN);
     }
+    TC_TRACE(c, 4);
     c.sync = sync;
-    ++c.op_count;
+    ++c.dw_count;
 }
 
 // backward of one network evaluation.  need_w: dW products (+ drains on the helper side);
@@ -820,31 +911,42 @@ __device__ __forceinline__ void ctrl_gemm_dw(Ctrl& c, int blk_, int N16_, int in
 // need_dy0 = false (the critic's networks: nothing consumes the cotangent of their input): the product dX of layer 0 is
 // left out; the owners are told when the last dW product is done (from then on the copy of a_0 and the plane region are
 // theirs again) and the control warp itself waits for the last drain.
+// Order within a layer l >= 1 (round 2): dX FIRST -- it needs only the dz planes, which the epilogue of layer l+1 hands over
+// chunk by chunk, so the tensor pipe works on dA_l while the helpers still convert dA_{l+1} -- then the dW blocks of the
+// layer, accumulated in the region whose planes dX has just consumed (DZ still holds dz_l: the helpers write dz_{l-1} into
+// it only after they have drained those blocks).  Layer 0 keeps dW before dX: its dX result goes to the owners, who reuse
+// the plane region at once.
 static __device__ __noinline__ void ctrl_net_backward(Ctrl& c, const TcNet& t, bool need_w, const unsigned char* copies, bool skip_last, bool need_dy0) {
-    for (int l = t.L; l >= 0; --l) {
+    for (int l = t.L; l >= 1; --l) {
+        // dA_l = dz_l x (W_l gamma c)^T.  (skip_last: its accumulator is the one the helpers read a_L from -- wait for them too)
+        ctrl_gemm_ts(c, t.ly[l].N16 / 16, t.ly[l].K16, l == t.L ? (skip_last ? IN_BOTH : IN_OWN) : IN_CHUNKS, false, false, true);
         if (need_w) {
             if (l < t.L) ctrl_act_wait(c);
             const int nblk = (t.ly[l].kl + 1 + 127) >> 7;
             for (int b = 0; b < nblk; ++b)
-                ctrl_gemm_dw(c, b, t.ly[l].N16, (l == t.L && b == 0) ? (skip_last ? IN_BOTH : IN_OWN) : IN_HELP,
-                             !need_dy0 && l == 0 && b == nblk - 1);
-            if (l > 0) {
-                TC_STAT(const long long t0 = clock64();)
-                mbar_wait(&c.bars[BAR_ACC], (c.op_count - 1) & 1);     // the MMAs reading ACT are done
-                TC_STAT(c.t_accw += clock64() - t0;)
-                ctrl_act_load(c, copies + tc_copy_off(t, l - 1), (uint32_t)(TC_PATHS * t.ly[l - 1].K16 * 2));
-            }
+                ctrl_gemm_dw(c, b, t.ly[l].N16, b > 0 ? IN_HELP : IN_NONE);
+            TC_STAT(const long long t0 = clock64();)
+            mbar_wait(&c.bars[BAR_DW], (c.dw_count - 1) & 1);            // the MMAs reading ACT are done
+            TC_STAT(c.t_accw += clock64() - t0;)
+            ctrl_act_load(c, copies + tc_copy_off(t, l - 1), (uint32_t)(TC_PATHS * t.ly[l - 1].K16 * 2));
+            uint32_t sync = warp_uniform(c.sync);
+            ctrl_wait_inputs(warp_uniform(smem_u32(c.bars)), sync, IN_HELP);         // the last drain of the layer: its region is the next accumulator
+            c.sync = sync;
         }
-        if (l == 0 && !need_dy0) {                                       // (need_w holds: a backward without either would be empty)
+    }
+    if (need_w) {                                                        // layer 0
+        ctrl_act_wait(c);
+        const int nblk = (t.ly[0].kl + 1 + 127) >> 7;
+        for (int b = 0; b < nblk; ++b) ctrl_gemm_dw(c, b, t.ly[0].N16, IN_HELP, !need_dy0 && b == nblk - 1);
+        if (!need_dy0) {
             uint32_t sync = warp_uniform(c.sync);
             ctrl_wait_inputs(warp_uniform(smem_u32(c.bars)), sync, IN_HELP);         // the last drain
             c.sync = sync;
-            break;
+            return;
         }
-        // dA_l = dz_l x (W_l gamma c)^T; its planes come chunk by chunk only in a chain without dW products; dy0 (l = 0) goes
-        // to the owners
-        ctrl_gemm_ts(c, t.ly[l].N16 / 16, t.ly[l].K16, need_w ? IN_HELP : (l == t.L ? IN_OWN : IN_CHUNKS), l == 0, false, l > 0);
     }
+    // dy0 goes to the owners; after dW blocks its inputs were published at once, in a chain without them chunk by chunk
+    ctrl_gemm_ts(c, t.ly[0].N16 / 16, t.ly[0].K16, need_w ? IN_HELP : IN_CHUNKS, true, false, false);
 }
 
 // ---- helpers ------------------------------------------------------------------------------------------------------
@@ -889,9 +991,17 @@ __device__ __forceinline__ void help_forward_keep(PathCtx& p, const TcNet& t, co
 
 // this thread's row of a dW block -> RED into the slab:  rows f = 128*blk + row (f <= kl), cols n < nl.  The evaluation ran
 // scaled by 2^dexp (the owners leave the exponent in shared memory before they publish the output cotangent).
-__device__ __forceinline__ void help_drain(PathCtx& p, int blk, int row, int kl, int nl, int N16, float* slab, const volatile int* dexp) {
-    help_wait_acc(p);
-    const uint32_t acc = path_acc(p);
+__device__ __forceinline__ void help_drain(PathCtx& p, int blk, int row, int kl, int nl, int N16, float* slab, const volatile int* dexp, bool in_planes_region) {
+    {
+        TC_STAT(const long long t0 = clock64();)
+        TC_TRACE(p, 13);
+        mbar_wait_u32(p.bars + 8 * BAR_DW, (p.sync >> 21) & 1u);
+        TC_STAT(p.t_mark = clock64(); p.t_accw += p.t_mark - t0;)
+        TC_TRACE(p, 14);
+        p.sync ^= SY_DW;
+        tc_fence_after();
+    }
+    const uint32_t acc = in_planes_region ? path_planes(p) : path_acc(p);
     TC_STAT(const long long td0 = clock64();)
     const int f = 128 * blk + row;
     float* dst = slab + (long long)f * 4;
@@ -918,21 +1028,23 @@ __device__ __forceinline__ void help_drain(PathCtx& p, int blk, int row, int kl,
     if ((threadIdx.x & 31) == 0) mbar_arrive_u32(p.bars + 8 * BAR_HELP);    // accumulator drained
     p.sync ^= SY_HELP;
     TC_STAT(p.t_drain += clock64() - td0;)
+    TC_TRACE(p, 15);
 }
 
-// the helpers' part of a backward evaluation: for l = L..0 the dW drains (need_w), and for l >= 1 the dX epilogue
-// dz_{l-1} = dA_l (.) slope(a_l) -> planes (+ DZ image)
+// the helpers' part of a backward evaluation (same order as ctrl_net_backward): for l = L..1 the drains of the layer's dW
+// blocks (need_w; they sit in the region whose planes dX_l consumed), then the epilogue dz_{l-1} = dA_l (.) slope(a_l) ->
+// planes (+ DZ image), handed over chunk by chunk -- except for l = 1 with dW products: layer 0's dW block comes before its
+// dX and needs the whole image; finally the drains of layer 0
 static __device__ __noinline__ uint32_t help_backward_(PathArg p, const TcNet& t, const TcSlab& g, const Masks& mk, bool need_w, float* slab,
                                                        unsigned char* dzimg, int row, const volatile int* dexp) {
-    for (int l = t.L; l >= 0; --l) {
+    for (int l = t.L; l >= 1; --l) {
         if (need_w) {
             const int nblk = (t.ly[l].kl + 1 + 127) >> 7;
-            for (int b = 0; b < nblk; ++b) help_drain(p, b, row, t.ly[l].kl, t.ly[l].nl, t.ly[l].N16, slab + g.gW[l], dexp);
+            for (int b = 0; b < nblk; ++b) help_drain(p, b, row, t.ly[l].kl, t.ly[l].nl, t.ly[l].N16, slab + g.gW[l], dexp, true);
         }
-        if (l == 0) break;
         const int K16 = t.ly[l].K16;
         // dA_l in the accumulator (K16_l columns) -> dz_{l-1} planes in place (+ DZ image)
-        for_acc_chunks(p, K16 / 16, need_w ? EPI_ALL : EPI_CHUNKS, need_w ? 1 : 0, true, [&](int c, const uint32_t* r, uint32_t tc) {
+        for_acc_chunks(p, K16 / 16, (need_w && l == 1) ? EPI_ALL : EPI_CHUNKS, need_w ? 1 : 0, true, [&](int c, const uint32_t* r, uint32_t tc) {
             const uint32_t bits = mk.h[l][c];
             float v[16];
 #pragma unroll
@@ -943,6 +1055,10 @@ static __device__ __noinline__ uint32_t help_backward_(PathArg p, const TcNet& t
             put16(tc, v);
             if (need_w) copy16f(dzimg, row, c, v, -1);
         });
+    }
+    if (need_w) {
+        const int nblk = (t.ly[0].kl + 1 + 127) >> 7;
+        for (int b = 0; b < nblk; ++b) help_drain(p, b, row, t.ly[0].kl, t.ly[0].nl, t.ly[0].N16, slab + g.gW[0], dexp, false);
     }
     return p.sync;
 }

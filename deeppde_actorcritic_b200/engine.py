@@ -222,6 +222,13 @@ class Engine:
         self._chk(self.lib.dpb_tc_stats(self.handle, C.c_void_p(self._ws.data_ptr()), B, N, out.ctypes.data_as(C.c_void_p)))
         return out
 
+    def tc_trace(self, B, N):
+        """event trace of CTA 0 of the last tensor-path launch: uint64[3][4096] (stats builds only; diagnostics)"""
+        import numpy as np
+        out = np.zeros((3, 4096), dtype=np.uint64)
+        self._chk(self.lib.dpb_tc_trace(self.handle, C.c_void_p(self._ws.data_ptr()), B, N, out.ctypes.data_as(C.c_void_p)))
+        return out
+
     def last_kernel_ms(self):
         """device time of the most recent critic/actor kernel launch (CUDA events recorded by the library)"""
         return float(self.lib.dpb_last_kernel_ms(self.handle))

@@ -220,6 +220,11 @@ int dpb_tc_mma_cycles(int64_t* out_host, int n, int rounds, int ts, int per_comm
  * [7] control thread inside MMA issue loops. */
 int dpb_tc_stats(dpb_handle* h, const void* workspace, int64_t B_local, int32_t N, int64_t* out_host);
 
+/* Diagnostic (tensor path, library built with DPB_TC_STATS; otherwise an error): event trace of CTA 0 of the last
+ * critic/actor launch -- out_host[3][4096] words (clock64 << 8) | event id for owner thread 0, helper thread 128 and the
+ * control warp; unused entries keep what an earlier launch left.  Event ids: deeppde_actorcritic_b200/csrc/dpb_tc_nets.cuh. */
+int dpb_tc_trace(dpb_handle* h, const void* workspace, int64_t B_local, int32_t N, uint64_t* out_host);
+
 #ifdef __cplusplus
 }
 #endif
