@@ -537,3 +537,32 @@ def test_naive_lifetime_sort_is_a_relabelling():
         assert _gerr(_npy(r1[g]), _npy(r0[g])) < 1e-5
     assert _gerr(_npy(a1["grad_actor"]), _npy(a0["grad_actor"])) < 1e-5
     np.testing.assert_allclose(_npy(r1["loss"]), _npy(r0["loss"]), rtol=1e-5)
+
+
+def test_event_trace_fails_loudly_without_the_stats_build():
+    """dpb_tc_trace: a library built without DPB_TC_STATS holds no trace and says so instead of returning stale zeros; a
+    stats build returns a monotone event log for every traced role (diagnostic entry point, include/deeppde_b200.h)"""
+    from deeppde_actorcritic_b200._cabi import DpbError
+    cfg = json.load(open(os.path.join(ROOT, "configs", "lqr_d5.json")))
+    e, net, tr = cfg["eqn_config"], cfg["net_config"], cfg["train_config"]
+    from oracle import ref_solver as RS
+    eng = Engine(e, net, tr, dtype="float32", impl="tensor")
+    rng = np.random.RandomState(2)
+    th = {}
+    for k in ("actor", "critic", "critic_grad"):
+        i, h, o, _ = RS.net_dims(cfg, k)
+        th[k] = eng.tensor(RS.init_params(i, h, o, rng))
+    B, N, T = 256, int(e["num_time_interval_critic"]), float(e["total_time_critic"])
+    x0, xb = eng.sample_x(3, 1, 0, B)
+    eng.critic_step(th["actor"], th["critic"], th["critic_grad"], x0, None, xb, N, T, dw_mode=1, seed=3, stream_id=7, need_grad=True)
+    torch.cuda.synchronize()
+    try:
+        trace = eng.tc_trace(B, N)
+    except DpbError as err:
+        assert "DPB_TC_STATS" in str(err)
+        return
+    for r in (0, 2):                                       # owner thread 0 and the control warp always log
+        w = trace[r][trace[r] != 0]
+        assert len(w) > 10
+        t = (w >> np.uint64(8)).astype(np.int64)
+        assert (np.diff(t[: min(len(t), 200)]) >= 0).all()
