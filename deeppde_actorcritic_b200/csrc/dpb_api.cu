@@ -532,7 +532,11 @@ static int tc_finalize(dpb_handle* h, const tc::TcNet& t, const tc::TcSlab& g, c
 // and writes its outputs at its own index -- so any permutation gives the same per-path results.
 static bool tc_lifetime_sort_wanted(const dpb_handle* h, int64_t B_local, uint32_t flags) {
     static const bool off = getenv("DPB_NO_LIFETIME_SORT") != nullptr;
-    return !off && !(h->cfg.reserved[0] & 1) && h->cfg.scheme == DPB_SCHEME_NAIVE && !(flags & DPB_FLAG_PROPAGATE_ONLY) && B_local > 2 * tc::TC_PATHS;
+    // (only when there are more tiles than SMs: in a single wave every tile runs at once and the launch lasts as long as the
+    //  longest-lived path whatever the tiling -- the pre-pass would only add its own latency: lqr_d5 at 1024 paths 4.09 ms per
+    //  iteration with the sort, 3.25 ms without)
+    return !off && !(h->cfg.reserved[0] & 1) && h->cfg.scheme == DPB_SCHEME_NAIVE && !(flags & DPB_FLAG_PROPAGATE_ONLY) &&
+           (B_local + tc::TC_PATHS - 1) / tc::TC_PATHS > h->num_sms;
 }
 static int tc_lifetime_sort(dpb_handle* h, tc::TcKernelFn critic_kern, tc::TcArgs a /* by value: a forward-only copy */, const Layout& L, char* ws,
                             size_t smem, int64_t B_local, int32_t N, cudaStream_t st) {

@@ -509,7 +509,8 @@ def test_naive_lifetime_sort_is_a_relabelling():
     assert tr["scheme"] == "naive"
     from oracle import ref_solver as RS
     rng = np.random.RandomState(8)
-    B, N, T = 5000, int(e["num_time_interval_critic"]), float(e["total_time_critic"])
+    # (the sort is taken only when there are more tiles than SMs: 200 tiles)
+    B, N, T = 25500, int(e["num_time_interval_critic"]), float(e["total_time_critic"])
     res = []
     for sort in (False, True):
         eng = Engine(e, net, tr, dtype="float32", impl="tensor", lifetime_sort=sort)
